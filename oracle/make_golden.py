@@ -1,0 +1,177 @@
+"""Freeze outputs of the UNMODIFIED reference into tests/golden/*.npz  (run in the build container only).
+
+    python oracle/make_golden.py
+
+TEST INFRASTRUCTURE.  The reference (a Python program) cannot travel to the GPU box, so its results on
+seeded synthetic inputs are committed as small fixtures together with this generating script.  Every
+fixture records the inputs needed to replay it (scene seed or the tensors themselves, rays, the uniform
+draws of train mode) and the reference's outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_harness import import_reference          # noqa: E402
+from egonerf_b200.synthetic import make_scene, make_rays  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+coordinates_dict, RefEgoNeRF, ref_volume_renderer, ref_sample_pdf, ref_raw2alpha = import_reference()
+
+
+def build_reference(scene):
+    co = coordinates_dict['yinyang']('cpu', scene.aabb, exp_r=True, N_voxel=scene.n_voxels, r0=scene.r0,
+                                     interval_th=True)
+    reso = co.N_to_reso(scene.n_voxels, scene.aabb)
+    assert reso == scene.grid, (reso, scene.grid)
+    model = RefEgoNeRF(scene.aabb, reso, 'cpu', co, **scene.model_kwargs())
+    model.load_state_dict(scene.state_dict, strict=True)
+    if scene.emission is not None:
+        model.envmap.emission = scene.emission.clone().requires_grad_(True)
+    model.update_coarse_sigma_grid()
+    return co, model
+
+
+def ref_render(model, rays, is_train, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True):
+    return ref_volume_renderer(rays, model, chunk=rays.shape[0], n_coarse=n_coarse, n_fine=n_fine,
+                               is_train=is_train, exp_sampling=True, resampling=resampling,
+                               use_coarse_sample=use_coarse_sample, interval_th=True, device='cpu',
+                               white_bg=False)
+
+
+def npz(name, **kw):
+    arrs = {}
+    for k, v in kw.items():
+        if v is None:
+            continue
+        arrs[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def sd_checksum(sd):
+    return np.array([float(v.double().sum()) for v in sd.values()] +
+                    [float(v.double().abs().sum()) for v in sd.values()])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- 1. schedules and coordinate KATs (EgoNeRF.py:68-76, coordinates.py:110-156,442-498) -------
+    for tag, nvox, nf, r0 in (("indoor300", 27e6, (0.01, 15.), 0.03), ("indoor128", 128 ** 3, (0.01, 15.), 0.03),
+                              ("outdoor300", 27e6, (0.1, 300.), 0.05)):
+        sc = make_scene(n_voxels=32 ** 3, near_far=nf, r0=r0)     # aabb only depends on far
+        co = coordinates_dict['yinyang']('cpu', sc.aabb, exp_r=True, N_voxel=nvox, r0=r0, interval_th=True)
+
+        class _M:   # minimal object exposing what sample_ray_exp reads
+            near_far = list(nf)
+            coordinates = co
+            aabb = sc.aabb
+        rays = make_rays(4, 'probe', seed=3)
+        _, z, _ = RefEgoNeRF.sample_ray_exp(_M, rays[:, :3], rays[:, 3:], is_train=False, N_samples=128)
+        g = torch.Generator().manual_seed(5)
+        pts = torch.cat([
+            torch.tensor([[1., 0, 0], [0, 1., 0], [0, 0, 1.], [-1., 0, 0], [.3, -.2, .1], [3., -2, 1], [-5., .5, 7],
+                          [10., 10, 10], [0., 0, 0], [0, -1., 0], [0, 0, -1.], [40., 0, 0]]),
+            (torch.rand(2000, 3, generator=g) - .5) * 2 * nf[1],
+            torch.randn(2000, 3, generator=g) * 0.3])
+        unn = co.from_cartesian(pts)
+        nrm = co.normalize_coord(unn, downsample=2)
+        # the r ladder the reference rebuilds on every call: recover it through normalize_r's inverse property
+        npz(f"kat_coords_{tag}.npz", aabb=sc.aabb, grid=np.array(co.N_to_reso(nvox, sc.aabb)), r0=r0, near_far=np.array(nf),
+            far_r=co.far[0], z_coarse=z[0], points=pts, unnormalized=unn, normalized=nrm)
+
+    # ---- 2. stand-alone operators on a small grid (params stored) --------------------------------
+    small = make_scene(n_voxels=40 ** 3, seed=7)
+    co, model = build_reference(small)
+    g = torch.Generator().manual_seed(11)
+    M = 3000
+    c3 = torch.rand(M, 3, generator=g) * 2.2 - 1.1            # includes out-of-range taps
+    is_yang = torch.rand(M, generator=g) < 0.5
+    coords7 = torch.zeros(M, 7)
+    coords7[~is_yang, 0:3] = c3[~is_yang]
+    coords7[is_yang, 3:6] = c3[is_yang]
+    coords7[:, 6] = is_yang.float()
+    with torch.no_grad():
+        sig = model.compute_densityfeature(coords7)
+        sigc = model.compute_coarse_densityfeature(coords7)
+        app = model.compute_appfeature(coords7)
+        dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+        rgb = model.renderModule(None, dirs, app)
+    npz("ops_small.npz", seed=7, n_voxels=40 ** 3, coords7=coords7, sigma_feature=sig, coarse_sigma_feature=sigc,
+        app_feature=app, dirs=dirs, rgb=rgb, checksum=sd_checksum(small.state_dict))
+
+    # raw2alpha / sample_pdf (tensorBase.py:22-27, ray_utils.py:156-187)
+    sg = torch.rand(16, 128, generator=g) * 0.5 * (torch.rand(16, 128, generator=g) < 0.3)
+    ds = torch.rand(16, 128, generator=g) * 2
+    a, w, bgw = ref_raw2alpha(sg, ds)
+    bins = torch.sort(torch.rand(16, 127, generator=g) * 15, -1)[0]
+    fz_eval = ref_sample_pdf(bins, w[:, 1:-1], 128, is_train=False)
+    torch.manual_seed(99)
+    fz_train = ref_sample_pdf(bins, w[:, 1:-1], 128, is_train=True)
+    torch.manual_seed(99)
+    u_train = torch.rand(16, 128)
+    npz("composite_pdf.npz", sigma=sg, dist=ds, alpha=a, weight=w, bg=bgw, bins=bins, fine_eval=fz_eval,
+        fine_train=fz_train, u_train=u_train)
+
+    # ---- 3. whole-path renders ---------------------------------------------------------------------
+    def render_case(name, scene, rays, is_train, seed=1234, grads=False, **kw):
+        co, model = build_reference(scene)
+        N = rays.shape[0]
+        u_c = u_f = None
+        if is_train:
+            torch.manual_seed(seed)
+            u_c = torch.rand(N, 128)            # EgoNeRF.py:81 rand_like(r)
+            u_f = torch.rand(N, 128)            # ray_utils.py:169
+            torch.manual_seed(seed)
+        store = dict(rays=rays, is_train=int(is_train), u_coarse=u_c, u_fine=u_f)
+        if grads:
+            out = ref_render(model, rays, is_train, **kw)
+            g2 = torch.Generator().manual_seed(seed + 1)
+            wr = torch.randn(out[0].shape, generator=g2)
+            wa = torch.randn(out[4].shape, generator=g2) * 0.01
+            loss = (out[0] * wr).sum() + (out[4] * wa).sum()
+            if out[2] is not None:
+                wb = torch.randn(out[2].shape, generator=g2)
+                we = torch.randn(out[3].shape, generator=g2)
+                loss = loss + (out[2] * wb).sum() + (out[3] * we).sum()
+                store.update(w_bg=wb, w_env=we)
+            loss.backward()
+            store.update(w_rgb=wr, w_alpha=wa, loss=loss.detach())
+            for k, p in model.named_parameters():
+                store["grad:" + k] = p.grad if p.grad is not None else torch.zeros_like(p)
+            if scene.emission is not None:
+                store["grad:envmap.emission"] = model.envmap.emission.grad
+        else:
+            with torch.no_grad():
+                out = ref_render(model, rays, is_train, **kw)
+        store.update(rgb=out[0], depth=out[1], bg=out[2], env=out[3], alpha=out[4],
+                     checksum=sd_checksum(scene.state_dict))
+        npz(name, **store)
+
+    tiny = make_scene(n_voxels=40 ** 3, seed=7)
+    tiny_env = make_scene(n_voxels=40 ** 3, seed=8, envmap_h=32, near_far=(0.1, 300.), r0=0.05, density_shift=-10.)
+    r64 = make_rays(64, 'isotropic', seed=21)
+    r64p = make_rays(64, 'probe', seed=22)
+    render_case("render_tiny_eval.npz", tiny, r64, False)
+    render_case("render_tiny_train.npz", tiny, r64p, True)
+    render_case("render_tiny_env_eval.npz", tiny_env, r64, False)
+    render_case("render_tiny_env_train_grad.npz", tiny_env, r64p, True, grads=True)
+    render_case("render_tiny_train_grad.npz", tiny, r64, True, grads=True, seed=77)
+    render_case("render_tiny_noresample.npz", tiny, r64, False, resampling=False, n_fine=0)
+    render_case("render_tiny_fineonly.npz", tiny, r64, False, use_coarse_sample=False)
+    # BASELINE.json configs[1] / configs[2] shapes: scene regenerated from its seed, checksum pinned
+    render_case("render_128_eval.npz", make_scene(n_voxels=128 ** 3), make_rays(256, 'isotropic', seed=31), False)
+    render_case("render_300_eval.npz", make_scene(n_voxels=27e6), make_rays(128, 'isotropic', seed=32), False)
+    render_case("render_300_train.npz", make_scene(n_voxels=27e6), make_rays(128, 'isotropic', seed=33), True)
+    # other decoders that work through EgoNeRF.forward in the reference: MLP, RGB
+    render_case("render_tiny_mlp.npz", make_scene(n_voxels=40 ** 3, seed=9, shading='MLP'), r64, False)
+    render_case("render_tiny_rgb.npz", make_scene(n_voxels=40 ** 3, seed=10, shading='RGB', app_dim=3), r64, False)
+
+
+if __name__ == "__main__":
+    main()
