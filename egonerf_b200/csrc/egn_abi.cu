@@ -1,0 +1,243 @@
+// C ABI of libegn_b200 (include/egn.h): argument validation, workspace carve-up, launch sequencing.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "egn_device.cuh"
+#include "egn_host.h"
+
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+static int cuda_fail(const char* what, int e) {
+    return fail("%s: %s", what, cudaGetErrorString((cudaError_t)e));
+}
+
+extern "C" const char* egn_last_error(void) { return g_err; }
+extern "C" int32_t egn_abi_version(void) { return EGN_ABI_VERSION; }
+
+extern "C" int32_t egn_samples_per_ray(const EgnConfig* c) {
+    if (!c->resampling) return c->n_coarse;
+    return (c->use_coarse_sample ? c->n_coarse : 0) + c->n_fine;
+}
+
+static int validate(const EgnConfig* c, bool need_schedule) {
+    if (!c) return fail("null config");
+    if (c->c_sigma != EGN_CS || c->c_app != EGN_CA)
+        return fail("this build supports n_lamb_sigma=[%d]*3, n_lamb_sh=[%d]*3 (got %d, %d)", EGN_CS, EGN_CA, c->c_sigma, c->c_app);
+    for (int a = 0; a < 3; ++a)
+        if (c->grid[a] < 4) return fail("grid[%d]=%d too small", a, c->grid[a]);
+    if (c->grid[0] > EGN_MAX_KNOTS) return fail("N_r=%d exceeds %d", c->grid[0], EGN_MAX_KNOTS);
+    if (c->app_dim < 1 || c->app_dim > 27) return fail("app_dim=%d unsupported (1..27)", c->app_dim);
+    if (c->shading < 0 || c->shading > 3) return fail("unknown shading %d", c->shading);
+    if (c->shading == EGN_SHADE_SH && c->app_dim != 27) return fail("SH shading needs app_dim 27");
+    if (c->shading == EGN_SHADE_RGB && c->app_dim != 3) return fail("RGB shading needs app_dim 3");
+    if (c->shading <= EGN_SHADE_MLP) {
+        if (c->feature_c != EGN_HID) return fail("featureC=%d unsupported (%d)", c->feature_c, EGN_HID);
+        int in_dim = c->app_dim + 3 + 6 * c->view_pe + (c->shading == EGN_SHADE_MLP_FEA ? 2 * c->fea_pe * c->app_dim : 0);
+        if (in_dim > 152) return fail("MLP input width %d exceeds 152", in_dim);
+    }
+    if (need_schedule) {
+        if (c->n_coarse < 32 || c->n_coarse > 256 || c->n_coarse % 32) return fail("n_coarse=%d must be a multiple of 32 in [32,256]", c->n_coarse);
+        if (c->resampling && (c->n_fine < 32 || c->n_fine > 256 || c->n_fine % 32)) return fail("n_fine=%d must be a multiple of 32 in [32,256]", c->n_fine);
+        if (!c->r_knots || !c->z_coarse) return fail("r_knots / z_coarse tables missing");
+    }
+    return 0;
+}
+
+static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables) {
+    EgnKernelCfg k;
+    memset(&k, 0, sizeof(k));
+    k.lay = egn_make_layout(c->grid);
+    k.tables = tables;
+    k.r_knots = c->r_knots;
+    k.z_coarse = c->z_coarse;
+    for (int a = 0; a < 3; ++a) k.center[a] = c->center[a];
+    for (int a = 0; a < 2; ++a) { k.ang_near[a] = c->ang_near[a]; k.ang_inv[a] = c->ang_inv[a]; }
+    k.density_shift = c->density_shift;
+    k.distance_scale = c->distance_scale;
+    k.n_coarse = c->n_coarse; k.n_fine = c->resampling ? c->n_fine : 0;
+    k.S = egn_samples_per_ray(c);
+    k.use_coarse_sample = c->use_coarse_sample; k.resampling = c->resampling;
+    k.fea2dense = c->fea2dense; k.shading = c->shading; k.app_dim = c->app_dim;
+    k.view_pe = c->view_pe; k.fea_pe = c->fea_pe; k.env_h = c->env_h;
+    return k;
+}
+
+extern "C" int64_t egn_table_floats(const EgnConfig* c) {
+    if (validate(c, false)) return -1;
+    return egn_make_layout(c->grid).total;
+}
+
+extern "C" int32_t egn_pack_tables(const EgnConfig* c, const EgnParams* p, float* tables, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!p || !tables) return fail("null argument");
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i)
+            if (!p->density_plane[h][i] || !p->density_line[h][i] || !p->app_plane[h][i] || !p->app_line[h][i])
+                return fail("missing factor tensor h=%d i=%d", h, i);
+    int e = egn_launch_pack(c, p, tables, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_pack_tables", e) : 0;
+}
+
+extern "C" int32_t egn_unpack_table_grads(const EgnConfig* c, const float* d_tables, const EgnGrads* g, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!d_tables || !g) return fail("null argument");
+    int e = egn_launch_unpack(c, d_tables, g, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_unpack_table_grads", e) : 0;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------
+static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
+struct WsPlan { long long z, fsig, feat, rgbs, wgt, bgw, h1, h2, d_rgbs, d_fsig, d_feat, dz1, dz2, total; };
+static WsPlan plan_ws(const EgnConfig* c, long long n) {
+    const long long M = n * egn_samples_per_ray(c);
+    WsPlan w;
+    long long off = 0;
+    auto take = [&](long long floats) { long long o = off; off += align256(floats * 4); return o; };
+    w.z = take(M); w.fsig = take(M); w.feat = take(M * EGN_FEAT_STRIDE); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n);
+    w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
+    const bool mlp = c->shading <= EGN_SHADE_MLP;
+    w.h1 = take(mlp ? M * EGN_HID : 0); w.h2 = take(mlp ? M * EGN_HID : 0);
+    w.dz1 = take(mlp ? M * EGN_HID : 0); w.dz2 = take(mlp ? M * EGN_HID : 0);
+    w.total = off;
+    return w;
+}
+extern "C" int64_t egn_workspace_bytes(const EgnConfig* c, int64_t n) {
+    if (validate(c, false)) return -1;
+    return plan_ws(c, n).total;
+}
+// forward-only callers (eval) may pass a workspace of this many bytes instead: no backward scratch
+extern "C" int64_t egn_workspace_bytes_eval(const EgnConfig* c, int64_t n) {
+    if (validate(c, false)) return -1;
+    return plan_ws(c, n).d_rgbs;
+}
+
+extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                      int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
+                                      int64_t ray0, const EgnOutputs* out, void* workspace, void* stream) {
+    if (validate(c, true)) return 1;
+    if (!p || !tables || !rays || !out || !workspace) return fail("null argument");
+    if (!out->rgb || !out->depth || !out->alpha) return fail("rgb/depth/alpha outputs are required");
+    if (c->env_h > 0 && (!p->emission || !out->bg || !out->env)) return fail("envmap configured but emission/bg/env missing");
+    if (c->shading <= EGN_SHADE_MLP)
+        for (int l = 0; l < 3; ++l)
+            if (!p->mlp_w[l] || !p->mlp_b[l]) return fail("MLP weights missing");
+    if (!p->basis[0] || !p->basis[1]) return fail("basis matrices missing");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    EgnKernelCfg k = make_kcfg(c, tables);
+    WsPlan w = plan_ws(c, n);
+    char* base = (char*)workspace;
+    float* z = (float*)(base + w.z);
+    float* fsig = (float*)(base + w.fsig);
+    float* feat = (float*)(base + w.feat);
+    float* rgbs = (float*)(base + w.rgbs);
+    float* wgt = (float*)(base + w.wgt);
+    float* bgw = (float*)(base + w.bgw);
+    int e;
+    if ((e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z, st))) return cuda_fail("coarse", e);
+    if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
+    if (c->shading <= EGN_SHADE_MLP)
+        if ((e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st))) return cuda_fail("mlp", e);
+    if ((e = egn_launch_composite(k, p, rays, n, z, fsig, feat, rgbs, out, wgt, bgw, st))) return cuda_fail("composite", e);
+    return 0;
+}
+
+extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                       int64_t n, const void* workspace, const float* d_rgb, const float* d_bg,
+                                       const float* d_env, const float* d_alpha, float* d_tables, const EgnGrads* g,
+                                       void* stream) {
+    (void)c; (void)p; (void)tables; (void)rays; (void)n; (void)workspace; (void)d_rgb; (void)d_bg; (void)d_env;
+    (void)d_alpha; (void)d_tables; (void)g; (void)stream;
+    return fail("egn_render_backward: not built yet");
+}
+
+// ---- stand-alone operators ---------------------------------------------------------------------------
+extern "C" int32_t egn_density_feature(const EgnConfig* c, const float* tables, const float* coords7, int64_t m,
+                                       int32_t coarse, float* out, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!tables || !coords7 || !out) return fail("null argument");
+    if (m <= 0) return 0;
+    EgnKernelCfg k = make_kcfg(c, tables);
+    int e = egn_launch_gather_coords(k, nullptr, coords7, m, coarse, out, nullptr, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_density_feature", e) : 0;
+}
+
+extern "C" int32_t egn_app_feature(const EgnConfig* c, const EgnParams* p, const float* tables, const float* coords7,
+                                   int64_t m, float* fsig_scratch, float* out28, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!p || !tables || !coords7 || !out28 || !fsig_scratch) return fail("null argument");
+    if (!p->basis[0] || !p->basis[1]) return fail("basis matrices missing");
+    if (m <= 0) return 0;
+    EgnKernelCfg k = make_kcfg(c, tables);
+    int e = egn_launch_gather_coords(k, p, coords7, m, 0, fsig_scratch, out28, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_app_feature", e) : 0;
+}
+
+extern "C" int32_t egn_yinyang_coords(const EgnConfig* c, const float* xyz, int64_t m, float* coords7, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!xyz || !coords7 || !c->r_knots) return fail("null argument");
+    if (m <= 0) return 0;
+    EgnKernelCfg k = make_kcfg(c, nullptr);
+    int e = egn_launch_coords(k, xyz, m, coords7, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_yinyang_coords", e) : 0;
+}
+
+extern "C" int32_t egn_envmap_radiance(const EgnConfig* c, const float* emission, const float* dirs, int64_t n, float* out,
+                                       void* stream) {
+    if (!c || c->env_h <= 0) return fail("no envmap configured");
+    if (!emission || !dirs || !out) return fail("null argument");
+    if (n <= 0) return 0;
+    int e = egn_launch_envmap(c->env_h, emission, dirs, n, out, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_envmap_radiance", e) : 0;
+}
+
+extern "C" int32_t egn_envmap_backward(const EgnConfig* c, const float* emission, const float* dirs, int64_t n,
+                                       const float* d_out, float* d_emission, void* stream) {
+    if (!c || c->env_h <= 0) return fail("no envmap configured");
+    if (!emission || !dirs || !d_out || !d_emission) return fail("null argument");
+    if (n <= 0) return 0;
+    int e = egn_launch_envmap_bwd(c->env_h, emission, dirs, n, d_out, d_emission, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_envmap_backward", e) : 0;
+}
+
+// ---- host helpers -------------------------------------------------------------------------------------
+// "first K intervals forced to r0, the rest shifted" (EgoNeRF.py:72-76, coordinates.py:120-124), fp32 arithmetic
+static void force_linear_prefix(float* r, int n, float r0) {
+    int K = 0;
+    float cum = 0.f, cumK = 0.f;
+    for (int i = 0; i + 1 < n; ++i) {
+        float iv = r[i + 1] - r[i];
+        cum += iv;
+        if (iv <= r0) { ++K; }
+    }
+    cum = 0.f;
+    for (int i = 0; i < K; ++i) { cum += r[i + 1] - r[i]; }
+    cumK = cum;
+    for (int i = K + 1; i < n; ++i) r[i] = r[i] + r0 * (float)K - cumK;
+    for (int i = 0; i <= K && i < n; ++i) r[i] = (float)i * r0;
+}
+
+extern "C" int32_t egn_host_sample_schedule(float near_plane, float far_plane, float r0, int32_t n, float* z_out) {
+    if (n < 2 || !z_out) return fail("bad arguments");
+    const double ratio = exp(log(((double)far_plane - (double)near_plane) / (double)r0) / (double)(n - 1));
+    z_out[0] = 0.f;
+    for (int i = 1; i < n; ++i) z_out[i] = r0 * powf((float)ratio, (float)(i - 1));
+    force_linear_prefix(z_out, n, r0);
+    return 0;
+}
+
+extern "C" int32_t egn_host_r_knots(float far_r, float r0, int32_t n_r, float* knots) {
+    if (n_r < 2 || !knots) return fail("bad arguments");
+    const float ratio = powf(far_r / r0, (float)(1.0 / (double)(n_r - 1)));
+    knots[0] = 0.f;
+    for (int i = 1; i <= n_r; ++i) knots[i] = r0 * powf(ratio, (float)(i - 1));
+    force_linear_prefix(knots, n_r + 1, r0);
+    return 0;
+}

@@ -1,0 +1,663 @@
+// Forward kernels of the render path (sm_100a):
+//   egn_coarse_kernel    sample schedule -> Yin-Yang coords -> pooled density gather -> raw2alpha -> inverse CDF -> sort
+//   egn_gather_kernel    fine samples: coords -> 18-tap interleaved gather -> sigma feature + basis contraction
+//   egn_composite_kernel feature2density -> warp-scan transmittance -> rgb / depth / bg / env / alpha
+// Reference semantics: SURVEY.md Appendix A; citations are into changwoonchoi/EgoNeRF.
+#include "egn_device.cuh"
+#include "egn_host.h"
+
+#define FULL 0xffffffffu
+
+// -------------------------------------------------------------------------------------------------
+// One lane's float4 slice of P_i * L_i (i < 3) for one sample: EgoNeRF.compute_densityfeature /
+// compute_appfeature inner product terms (EgoNeRF.py:336-346, 394-412) with F.grid_sample(bilinear,
+// zeros padding, align_corners=True) written out as taps.  C = channels per texel of this table set,
+// `sub` = which float4 of the texel this lane owns.  All 18 loads are issued before any use.
+// -------------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void egn_gather_products(const float* __restrict__ tab, const long long pofs[3],
+                                                    const long long lofs[3], const int G[3], const float c[3],
+                                                    int sub, float4 prod[3]) {
+    int i0[3];
+    float fr[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float ix = egn_unnorm(c[a], G[a]);
+        float fl = floorf(ix);
+        fr[a] = ix - fl;
+        // clamp before the int conversion so far-out-of-range samples stay "invalid" instead of wrapping
+        i0[a] = (int)fminf(fmaxf(fl, -2.f), (float)G[a] + 1.f);
+    }
+    float4 t[3][4], l[3][2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+        const int W = G[ax], H = G[ay], L = G[al];
+        const int x0 = i0[ax], y0 = i0[ay], q0 = i0[al];
+        const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+        const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
+        const float* pb = tab + pofs[i] + ((long long)y0 * W + x0) * C + sub * 4;
+        t[i][0] = (vx0 & vy0) ? ldg4(pb) : f4zero();
+        t[i][1] = (vx1 & vy0) ? ldg4(pb + C) : f4zero();
+        t[i][2] = (vx0 & vy1) ? ldg4(pb + (long long)W * C) : f4zero();
+        t[i][3] = (vx1 & vy1) ? ldg4(pb + (long long)W * C + C) : f4zero();
+        const float* lb = tab + lofs[i] + (long long)q0 * C + sub * 4;
+        l[i][0] = (q0 >= 0 && q0 < L) ? ldg4(lb) : f4zero();
+        l[i][1] = (q0 + 1 >= 0 && q0 + 1 < L) ? ldg4(lb + C) : f4zero();
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float fx = fr[egn_mx(i)], fy = fr[egn_my(i)], fq = fr[egn_vl(i)];
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        float4 P = f4zero();
+        P = f4fma(gx * gy, t[i][0], P);
+        P = f4fma(fx * gy, t[i][1], P);
+        P = f4fma(gx * fy, t[i][2], P);
+        P = f4fma(fx * fy, t[i][3], P);
+        float4 Lv = f4zero();
+        Lv = f4fma(1.f - fq, l[i][0], Lv);
+        Lv = f4fma(fq, l[i][1], Lv);
+        prod[i] = f4mul(P, Lv);
+    }
+}
+__device__ __forceinline__ float hsum4(float4 v) { return (v.x + v.y) + (v.z + v.w); }
+
+// =================================================================================================
+// K1: coarse pass + resampling.  One warp per ray.
+// =================================================================================================
+#define K1_WARPS 8
+#define K1_MAXC 256
+
+__global__ void __launch_bounds__(K1_WARPS * 32)
+egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ rays, long long n, int is_train,
+                  const float* __restrict__ u_c, const float* __restrict__ u_f, unsigned long long seed,
+                  long long ray0, float near_plane, float* __restrict__ z_out) {
+    __shared__ float s_knots[EGN_MAX_KNOTS + 1];
+    __shared__ float s_r[K1_MAXC];
+    __shared__ float s_zc[K1_WARPS][K1_MAXC];
+    __shared__ float s_w[K1_WARPS][K1_MAXC];
+    __shared__ float s_zn[K1_WARPS][K1_MAXC];
+    const int nc = k.n_coarse, nf = k.n_fine;
+    for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) s_knots[i] = k.r_knots[i];
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) s_r[i] = k.z_coarse[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* zc = s_zc[warp];
+    float* sw = s_w[warp];
+    float* zn = s_zn[warp];
+    const int cnt = nc >> 5;                       // coarse samples per lane in the scans (nc % 32 == 0)
+
+    for (long long ray = (long long)blockIdx.x * K1_WARPS + warp; ray < n; ray += (long long)gridDim.x * K1_WARPS) {
+        const float ox = rays[ray * 6 + 0], oy = rays[ray * 6 + 1], oz = rays[ray * 6 + 2];
+        const float dx = rays[ray * 6 + 3], dy = rays[ray * 6 + 4], dz = rays[ray * 6 + 5];
+        // ---- 1. coarse depths: near + r, jittered by interval*U in train mode (EgoNeRF.py:69-82) ----
+        for (int j = lane; j < nc; j += 32) {
+            float r = s_r[j];
+            if (is_train) {
+                float iv = (j + 1 < nc) ? (s_r[j + 1] - s_r[j]) : (s_r[nc - 1] - s_r[nc - 2]);
+                float u = u_c ? u_c[ray * nc + j] : egn_u01(egn_philox(seed, (unsigned long long)(ray0 + ray), (unsigned)j).x);
+                r = r + iv * u;
+            }
+            zc[j] = near_plane + r;
+        }
+        __syncwarp();
+        if (!k.resampling) {                      // EgoNeRF.py:564-577: the coarse samples are the samples
+            for (int j = lane; j < nc; j += 32) z_out[ray * k.S + j] = zc[j];
+            __syncwarp();
+            continue;
+        }
+        // ---- 2. pooled-grid density of every coarse sample (EgoNeRF.py:520-528) ----
+        for (int t = 0; t < cnt; ++t) {
+            const int j = t * 32 + lane;
+            const float z = zc[j];
+            YYCoord cc = egn_cart_to_yinyang(ox + dx * z, oy + dy * z, oz + dz * z, k, s_knots);
+            float myf = 0.f;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {         // 8 samples per pass, 4 lanes (one float4 each) per sample
+                const int src = p * 8 + (lane >> 2);
+                float c[3];
+                c[0] = __shfl_sync(FULL, cc.c[0], src);
+                c[1] = __shfl_sync(FULL, cc.c[1], src);
+                c[2] = __shfl_sync(FULL, cc.c[2], src);
+                const int yang = __shfl_sync(FULL, cc.yang, src);
+                float4 prod[3];
+                egn_gather_products<EGN_CS>(k.tables, k.lay.pc[yang], k.lay.lc[yang], k.lay.Gc, c, lane & 3, prod);
+                float f = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float s = hsum4(prod[i]);
+                    s += __shfl_xor_sync(FULL, s, 1);
+                    s += __shfl_xor_sync(FULL, s, 2);
+                    f += fmaxf(s, 0.f);
+                }
+                const float tf = __shfl_sync(FULL, f, (lane & 7) * 4);
+                if ((lane >> 3) == p) myf = tf;
+            }
+            sw[j] = egn_density_act(myf, k.density_shift, k.fea2dense);
+        }
+        __syncwarp();
+        // ---- 3. raw2alpha (tensorBase.py:22-27): lane owns `cnt` consecutive samples, warp product scan ----
+        float a_loc[K1_MAXC / 32], m_loc[K1_MAXC / 32];
+        float prodl = 1.f;
+#pragma unroll
+        for (int q = 0; q < K1_MAXC / 32; ++q) {
+            if (q < cnt) {
+                const int j = lane * cnt + q;
+                const float dist = ((j + 1 < nc) ? (zc[j + 1] - zc[j]) : (zc[nc - 1] - zc[nc - 2])) * k.distance_scale;
+                const float alpha = 1.f - expf(-sw[j] * dist);
+                a_loc[q] = alpha;
+                m_loc[q] = 1.f - alpha + 1e-10f;
+                prodl *= m_loc[q];
+            }
+        }
+        float incl = prodl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            float o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl *= o;
+        }
+        float T = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) T = 1.f;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < K1_MAXC / 32; ++q) {
+            if (q < cnt) {
+                sw[lane * cnt + q] = a_loc[q] * T;     // weights
+                T *= m_loc[q];
+            }
+        }
+        __syncwarp();
+        // ---- 4. pdf / cdf over weights[1:-1] + 1e-5 (ray_utils.py:159-162) ----
+        const int nb = nc - 2;                      // number of pdf entries; cdf has nb + 1 = nc - 1 knots
+        float wp[K1_MAXC / 32];
+        float suml = 0.f;
+#pragma unroll
+        for (int q = 0; q < K1_MAXC / 32; ++q) {
+            if (q < cnt) {
+                const int kk = lane * cnt + q;
+                wp[q] = (kk < nb) ? (sw[kk + 1] + 1e-5f) : 0.f;
+                suml += wp[q];
+            }
+        }
+        float tot = suml;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
+        float pl = 0.f;
+#pragma unroll
+        for (int q = 0; q < K1_MAXC / 32; ++q)
+            if (q < cnt) { wp[q] = wp[q] / tot; pl += wp[q]; }
+        float inc2 = pl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            float o = __shfl_up_sync(FULL, inc2, d);
+            if (lane >= d) inc2 += o;
+        }
+        float run = inc2 - pl;                      // exclusive prefix of this lane's chunk
+        __syncwarp();
+        if (lane == 0) sw[0] = 0.f;                 // cdf[0]
+#pragma unroll
+        for (int q = 0; q < K1_MAXC / 32; ++q) {
+            if (q < cnt) {
+                const int kk = lane * cnt + q;
+                run += wp[q];
+                if (kk < nb) sw[kk + 1] = run;      // cdf[kk+1]
+            }
+        }
+        __syncwarp();
+        // ---- 5. inverse CDF (ray_utils.py:164-186) ----
+        const int ncdf = nc - 1;
+        const float step = 1.0f / (float)(nf - 1);
+        for (int i = lane; i < nf; i += 32) {
+            float u;
+            if (!is_train) u = (i < nf / 2) ? (0.f + step * (float)i) : (1.f - step * (float)(nf - i - 1));   // torch.linspace
+            else u = u_f ? u_f[ray * nf + i] : egn_u01(egn_philox(seed, (unsigned long long)(ray0 + ray), 0x10000u + (unsigned)i).x);
+            int lo = 0, hi = ncdf;                  // searchsorted(cdf, u, right=True)
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (sw[mid] > u) hi = mid; else lo = mid + 1;
+            }
+            const int below = max(lo - 1, 0), above = min(lo, ncdf - 1);
+            const float c0 = sw[below], c1 = sw[above];
+            const float b0 = .5f * (zc[below + 1] + zc[below]), b1 = .5f * (zc[above + 1] + zc[above]);
+            float den = c1 - c0;
+            if (den < 1e-5f) den = 1.f;
+            const float tt = (u - c0) / den;
+            zn[i] = b0 + tt * (b1 - b0);
+        }
+        __syncwarp();
+        // ---- 6. sort(cat(coarse, new)) (EgoNeRF.py:536-539) as a rank sort; ties broken by position ----
+        const int na = k.use_coarse_sample ? nc : 0;
+        const int S = na + nf;
+        float v[2 * K1_MAXC / 32];
+        int rk[2 * K1_MAXC / 32];
+        const int E = S >> 5;
+#pragma unroll
+        for (int e = 0; e < 2 * K1_MAXC / 32; ++e) {
+            rk[e] = 0;
+            if (e < E) { const int a = e * 32 + lane; v[e] = (a < na) ? zc[a] : zn[a - na]; }
+            else v[e] = 0.f;
+        }
+        for (int b = 0; b < S; ++b) {
+            const float vb = (b < na) ? zc[b] : zn[b - na];
+#pragma unroll
+            for (int e = 0; e < 2 * K1_MAXC / 32; ++e) {
+                const int a = e * 32 + lane;
+                rk[e] += (vb < v[e]) || (vb == v[e] && b < a);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2 * K1_MAXC / 32; ++e)
+            if (e < E) z_out[ray * S + rk[e]] = v[e];
+        __syncwarp();
+    }
+}
+
+int egn_launch_coarse(const EgnKernelCfg& k, const float* rays, long long n, int is_train, const float* u_c,
+                      const float* u_f, unsigned long long seed, long long ray0, float near_plane, float* z_out,
+                      cudaStream_t st) {
+    long long blocks = (n + K1_WARPS - 1) / K1_WARPS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    egn_coarse_kernel<<<(unsigned)blocks, K1_WARPS * 32, 0, st>>>(k, rays, n, is_train, u_c, u_f, seed, ray0, near_plane, z_out);
+    return (int)cudaGetLastError();
+}
+
+// =================================================================================================
+// K2: fine gather.  A warp handles 16 samples per round: lanes 0-15 compute their sample's Yin-Yang
+// coordinate; then 8 iterations gather 2 samples each (16 lanes x float4 = one 256-byte tap per
+// half-warp); the appearance products go to a per-warp smem tile and are contracted with
+// basis_mat_{yin,yang} (EgoNeRF.py:409,412) as a 16 x 28 x 144 register-tiled product.
+// =================================================================================================
+#define K2_WARPS 16
+#define K2_VT 148                 // v-tile row stride (floats): conflict-free float4 rows
+#define K2_K (3 * EGN_CA)         // 144
+
+struct K2Smem {
+    float BT[2][K2_K][32];        // basis, k-major, outputs padded 28 -> 32
+    float vt[K2_WARPS][16][K2_VT];
+    float knots[EGN_MAX_KNOTS + 1];
+};
+
+template <bool FROM_COORDS>
+__global__ void __launch_bounds__(K2_WARPS * 32, 1)
+egn_gather_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
+                  const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
+                  const float* __restrict__ zs, const float* __restrict__ coords7, float* __restrict__ fsig,
+                  float* __restrict__ feat) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K2Smem& sm = *reinterpret_cast<K2Smem*>(smem_raw);
+    for (int i = threadIdx.x; i < 2 * K2_K * 32; i += blockDim.x) {
+        const int h = i / (K2_K * 32), kk = (i / 32) % K2_K, o = i % 32;
+        const float* B = h ? basis1 : basis0;
+        sm.BT[h][kk][o] = (o < k.app_dim && B) ? B[o * K2_K + kk] : 0.f;
+    }
+    if (!FROM_COORDS)
+        for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) sm.knots[i] = k.r_knots[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float(*vt)[K2_VT] = sm.vt[warp];
+    const long long rounds = (M + 15) / 16;
+    const int sg = lane & 3, og = lane >> 2;
+
+    for (long long r = (long long)blockIdx.x * K2_WARPS + warp; r < rounds; r += (long long)gridDim.x * K2_WARPS) {
+        // ---- a. coordinate of sample (lane & 15) ----
+        const long long m = r * 16 + (lane & 15);
+        YYCoord cc;
+        cc.c[0] = cc.c[1] = cc.c[2] = -3.f;       // out of range -> every tap reads zero
+        cc.yang = 0;
+        if (m < M) {
+            if (FROM_COORDS) {
+                const float* c7 = coords7 + m * 7;
+                cc.yang = (c7[6] != 0.f);           // EgoNeRF.py:292: last column == 0 selects Yin
+                cc.c[0] = c7[cc.yang * 3 + 0]; cc.c[1] = c7[cc.yang * 3 + 1]; cc.c[2] = c7[cc.yang * 3 + 2];
+            } else {
+                const long long ray = m / k.S;
+                const float z = zs[m];
+                const float* ry = rays + ray * 6;
+                cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, sm.knots);
+            }
+        }
+        // ---- b. gather: 2 samples per iteration ----
+        float myf = 0.f;
+        const int sub = lane & 15;
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+            const int src = 2 * it + (lane >> 4);
+            float c[3];
+            c[0] = __shfl_sync(FULL, cc.c[0], src);
+            c[1] = __shfl_sync(FULL, cc.c[1], src);
+            c[2] = __shfl_sync(FULL, cc.c[2], src);
+            const int yang = __shfl_sync(FULL, cc.yang, src);
+            float4 prod[3];
+            egn_gather_products<EGN_CF>(k.tables, k.lay.pf[yang], k.lay.lf[yang], k.lay.G, c, sub, prod);
+            float f = 0.f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float s = hsum4(prod[i]);          // only lanes sub < 4 carry density channels
+                s += __shfl_xor_sync(FULL, s, 1);
+                s += __shfl_xor_sync(FULL, s, 2);
+                f += fmaxf(s, 0.f);
+                if (sub >= EGN_CS / 4)
+                    *reinterpret_cast<float4*>(&vt[src][i * EGN_CA + (sub - EGN_CS / 4) * 4]) = prod[i];
+            }
+            const float t0 = __shfl_sync(FULL, f, 0), t1 = __shfl_sync(FULL, f, 16);
+            if (lane == 2 * it) myf = t0;
+            if (lane == 2 * it + 1) myf = t1;
+        }
+        __syncwarp();
+        if (lane < 16 && m < M) fsig[m] = myf;
+        // ---- c. basis contraction: lane = (og, sg): samples sg + 4a, outputs 4og .. 4og+3 ----
+        if (feat != nullptr) {
+            const unsigned ymask = __ballot_sync(FULL, cc.yang != 0) & 0xffffu;
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            for (int h = 0; h < 2; ++h) {
+                if (h == 0 && ymask == 0xffffu) continue;     // no Yin sample in this round
+                if (h == 1 && ymask == 0u) continue;          // no Yang sample
+                const bool mixed = (ymask != 0u) && (ymask != 0xffffu);
+                float sel[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) sel[a] = (!mixed || (int)((ymask >> (sg + 4 * a)) & 1u) == h) ? 1.f : 0.f;
+                const float(*BT)[32] = sm.BT[h];
+#pragma unroll 3
+                for (int k4 = 0; k4 < K2_K / 4; ++k4) {
+                    float4 va[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        va[a] = *reinterpret_cast<const float4*>(&vt[sg + 4 * a][k4 * 4]);
+                        if (mixed) { va[a].x *= sel[a]; va[a].y *= sel[a]; va[a].z *= sel[a]; va[a].w *= sel[a]; }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&BT[k4 * 4 + kk][og * 4]);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const float x = kk == 0 ? va[a].x : kk == 1 ? va[a].y : kk == 2 ? va[a].z : va[a].w;
+                            acc[a][0] = fmaf(x, b4.x, acc[a][0]);
+                            acc[a][1] = fmaf(x, b4.y, acc[a][1]);
+                            acc[a][2] = fmaf(x, b4.z, acc[a][2]);
+                            acc[a][3] = fmaf(x, b4.w, acc[a][3]);
+                        }
+                    }
+                }
+            }
+            if (og < EGN_FEAT_STRIDE / 4) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const long long mm = r * 16 + sg + 4 * a;
+                    if (mm < M)
+                        *reinterpret_cast<float4*>(feat + mm * EGN_FEAT_STRIDE + og * 4) =
+                            make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int k2_grid(long long M) {
+    long long rounds = (M + 15) / 16;
+    long long blocks = (rounds + K2_WARPS - 1) / K2_WARPS;
+    if (blocks > 148) blocks = 148;               // 1 CTA / SM (187 KB smem), persistent over rounds
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int egn_launch_gather(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                      float* fsig, float* feat, cudaStream_t st) {
+    const long long M = n * k.S;
+    auto kern = egn_gather_kernel<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
+    kern<<<k2_grid(M), K2_WARPS * 32, sizeof(K2Smem), st>>>(k, p->basis[0], p->basis[1], rays, M, z, nullptr, fsig, feat);
+    return (int)cudaGetLastError();
+}
+
+// coarse stand-alone operator (compute_coarse_densityfeature, EgoNeRF.py:232-289): 4 lanes per sample
+__global__ void __launch_bounds__(256)
+egn_coarse_feature_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ coords7, long long M,
+                          float* __restrict__ fsig) {
+    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 2;
+    const int sub = threadIdx.x & 3;
+    float c[3] = {-3.f, -3.f, -3.f};
+    int yang = 0;
+    if (g < M) {
+        const float* c7 = coords7 + g * 7;
+        yang = (c7[6] != 0.f);
+        c[0] = c7[yang * 3]; c[1] = c7[yang * 3 + 1]; c[2] = c7[yang * 3 + 2];
+    }
+    float4 prod[3];
+    egn_gather_products<EGN_CS>(k.tables, k.lay.pc[yang], k.lay.lc[yang], k.lay.Gc, c, sub, prod);
+    float f = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float s = hsum4(prod[i]);
+        s += __shfl_xor_sync(FULL, s, 1);
+        s += __shfl_xor_sync(FULL, s, 2);
+        f += fmaxf(s, 0.f);
+    }
+    if (g < M && sub == 0) fsig[g] = f;
+}
+
+int egn_launch_gather_coords(const EgnKernelCfg& k, const EgnParams* p, const float* coords7, long long m, int coarse,
+                             float* fsig, float* feat, cudaStream_t st) {
+    if (coarse) {
+        long long threads = m * 4;
+        egn_coarse_feature_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(k, coords7, m, fsig);
+        return (int)cudaGetLastError();
+    }
+    auto kern = egn_gather_kernel<true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
+    kern<<<k2_grid(m), K2_WARPS * 32, sizeof(K2Smem), st>>>(k, p ? p->basis[0] : nullptr, p ? p->basis[1] : nullptr,
+                                                              nullptr, m, nullptr, coords7, fsig, feat);
+    return (int)cudaGetLastError();
+}
+
+// coordinates operator (from_cartesian + normalize_coord, coordinates.py:442-498): one thread per point
+__global__ void __launch_bounds__(256)
+egn_coords_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ xyz, long long M,
+                  float* __restrict__ coords7) {
+    const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    YYCoord cc = egn_cart_to_yinyang(xyz[m * 3], xyz[m * 3 + 1], xyz[m * 3 + 2], k, k.r_knots);
+    // the inactive hemisphere's raw coordinates are all zero in the reference (coordinates.py:474,487-496);
+    // normalising zeros gives the constants below (r=0 -> -1, angle 0 -> (0-near)*inv*2-1)
+    const float z1 = (0.f - k.ang_near[0]) * k.ang_inv[0] * 2.f - 1.f;
+    const float z2 = (0.f - k.ang_near[1]) * k.ang_inv[1] * 2.f - 1.f;
+    float* o = coords7 + m * 7;
+    const int a = cc.yang ? 3 : 0, b = cc.yang ? 0 : 3;
+    o[a] = cc.c[0]; o[a + 1] = cc.c[1]; o[a + 2] = cc.c[2];
+    o[b] = -1.f; o[b + 1] = z1; o[b + 2] = z2;
+    o[6] = (float)cc.yang;
+}
+
+int egn_launch_coords(const EgnKernelCfg& k, const float* xyz, long long m, float* coords7, cudaStream_t st) {
+    egn_coords_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k, xyz, m, coords7);
+    return (int)cudaGetLastError();
+}
+
+// =================================================================================================
+// Envmap (models/envmap.py:6-34): equirect (3, 2h, h) bilinear + sigmoid.
+// =================================================================================================
+struct EnvTap { int x0, y0; float fx, fy; };
+__device__ __forceinline__ EnvTap egn_env_tap(float dx, float dy, float dz, int h) {
+    const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);     // F.normalize eps
+    dx /= nrm; dy /= nrm; dz /= nrm;
+    const float u = (dz + 1.f) * 0.5f;
+    const float v = (atan2f(dy, dx) + 3.14159265358979323846f) / 6.28318530717958647692f;
+    const float ix = egn_unnorm(2.f * u - 1.f, h), iy = egn_unnorm(2.f * v - 1.f, 2 * h);
+    EnvTap t;
+    const float flx = floorf(ix), fly = floorf(iy);
+    t.x0 = (int)flx; t.y0 = (int)fly; t.fx = ix - flx; t.fy = iy - fly;
+    return t;
+}
+__device__ __forceinline__ void egn_env_radiance(const float* __restrict__ em, int h, float dx, float dy, float dz, float out[3]) {
+    const EnvTap t = egn_env_tap(dx, dy, dz, h);
+    const int W = h, H = 2 * h;
+    const float w[4] = {(1.f - t.fx) * (1.f - t.fy), t.fx * (1.f - t.fy), (1.f - t.fx) * t.fy, t.fx * t.fy};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int x = t.x0 + (q & 1), y = t.y0 + (q >> 1);
+            if (x >= 0 && x < W && y >= 0 && y < H) acc = fmaf(w[q], __ldg(em + ((long long)ch * H + y) * W + x), acc);
+        }
+        out[ch] = egn_sigmoid(acc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+egn_envmap_kernel(int h, const float* __restrict__ em, const float* __restrict__ dirs, long long n, float* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[3];
+    egn_env_radiance(em, h, dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2], o);
+    out[i * 3] = o[0]; out[i * 3 + 1] = o[1]; out[i * 3 + 2] = o[2];
+}
+int egn_launch_envmap(int env_h, const float* emission, const float* dirs, long long n, float* out, cudaStream_t st) {
+    egn_envmap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(env_h, emission, dirs, n, out);
+    return (int)cudaGetLastError();
+}
+
+// d_out is the gradient w.r.t. the sigmoid output
+__global__ void __launch_bounds__(256)
+egn_envmap_bwd_kernel(int h, const float* __restrict__ em, const float* __restrict__ dirs, long long n,
+                      const float* __restrict__ d_out, float* __restrict__ d_em) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[3];
+    egn_env_radiance(em, h, dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2], o);
+    const EnvTap t = egn_env_tap(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2], h);
+    const int W = h, H = 2 * h;
+    const float w[4] = {(1.f - t.fx) * (1.f - t.fy), t.fx * (1.f - t.fy), (1.f - t.fx) * t.fy, t.fx * t.fy};
+    for (int ch = 0; ch < 3; ++ch) {
+        const float g = d_out[i * 3 + ch] * o[ch] * (1.f - o[ch]);
+        for (int q = 0; q < 4; ++q) {
+            const int x = t.x0 + (q & 1), y = t.y0 + (q >> 1);
+            if (x >= 0 && x < W && y >= 0 && y < H) atomicAdd(d_em + ((long long)ch * H + y) * W + x, w[q] * g);
+        }
+    }
+}
+int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, long long n, const float* d_out,
+                          float* d_emission, cudaStream_t st) {
+    egn_envmap_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(env_h, emission, dirs, n, d_out, d_emission);
+    return (int)cudaGetLastError();
+}
+
+// =================================================================================================
+// K4: compositing (tensorBase.py:22-27, EgoNeRF.py:579-598).  One warp per ray, lane owns S/32
+// consecutive samples; transmittance = warp-shuffle product scan.
+// =================================================================================================
+#define K4_MAXE 16
+
+__device__ __forceinline__ void egn_sample_color(const EgnKernelCfg& k, const float* __restrict__ feat,
+                                                 const float* __restrict__ rgbs, long long m, const float sh[9], float c[3]) {
+    if (k.shading == EGN_SHADE_RGB) {              // RGBRender (tensorBase.py:37-39)
+        c[0] = feat[m * EGN_FEAT_STRIDE]; c[1] = feat[m * EGN_FEAT_STRIDE + 1]; c[2] = feat[m * EGN_FEAT_STRIDE + 2];
+    } else if (k.shading == EGN_SHADE_SH) {        // SHRender (tensorBase.py:30-34)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float a = 0.f;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) a += sh[b] * feat[m * EGN_FEAT_STRIDE + ch * 9 + b];
+            c[ch] = fmaxf(a + 0.5f, 0.f);
+        }
+    } else {
+        c[0] = rgbs[m * 3]; c[1] = rgbs[m * 3 + 1]; c[2] = rgbs[m * 3 + 2];
+    }
+}
+__device__ __forceinline__ void egn_sh_basis(float x, float y, float z, float sh[9]) {   // models/sh.py:87-116
+    sh[0] = 0.28209479177387814f;
+    sh[1] = -0.4886025119029199f * y; sh[2] = 0.4886025119029199f * z; sh[3] = -0.4886025119029199f * x;
+    const float xx = x * x, yy = y * y, zz = z * z;
+    sh[4] = 1.0925484305920792f * (x * y); sh[5] = -1.0925484305920792f * (y * z);
+    sh[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    sh[7] = -1.0925484305920792f * (x * z); sh[8] = 0.5462742152960396f * (xx - yy);
+}
+
+__global__ void __launch_bounds__(256)
+egn_composite_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ emission,
+                     const float* __restrict__ rays, long long n, const float* __restrict__ zs,
+                     const float* __restrict__ fsig, const float* __restrict__ feat, const float* __restrict__ rgbs,
+                     EgnOutputs out, float* __restrict__ wgt, float* __restrict__ bgw) {
+    const int lane = threadIdx.x & 31;
+    const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n) return;
+    const int S = k.S, cnt = S >> 5;
+    const float dx = rays[ray * 6 + 3], dy = rays[ray * 6 + 4], dz = rays[ray * 6 + 5];
+    float sh[9];
+    if (k.shading == EGN_SHADE_SH) egn_sh_basis(dx, dy, dz, sh);
+    const long long base = ray * S;
+    const int acols = S + (k.env_h > 0 ? 1 : 0);
+    float a_loc[K4_MAXE], m_loc[K4_MAXE];
+    float prodl = 1.f;
+#pragma unroll
+    for (int q = 0; q < K4_MAXE; ++q) {
+        if (q < cnt) {
+            const int j = lane * cnt + q;
+            const float zj = zs[base + j];
+            const float dist = ((j + 1 < S) ? (zs[base + j + 1] - zj) : (zj - zs[base + j - 1])) * k.distance_scale;
+            const float sigma = egn_density_act(fsig[base + j], k.density_shift, k.fea2dense);
+            const float alpha = 1.f - expf(-sigma * dist);
+            a_loc[q] = alpha;
+            m_loc[q] = 1.f - alpha + 1e-10f;
+            prodl *= m_loc[q];
+            out.alpha[ray * acols + j] = alpha;
+        }
+    }
+    float incl = prodl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl *= o;
+    }
+    float T = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) T = 1.f;
+    const float Tend = __shfl_sync(FULL, incl, 31);       // bg_weight = T[:, -1]
+    float acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f;
+#pragma unroll
+    for (int q = 0; q < K4_MAXE; ++q) {
+        if (q < cnt) {
+            const int j = lane * cnt + q;
+            const float w = a_loc[q] * T;
+            T *= m_loc[q];
+            float c[3];
+            egn_sample_color(k, feat, rgbs, base + j, sh, c);
+            acc += w; cr = fmaf(w, c[0], cr); cg = fmaf(w, c[1], cg); cb = fmaf(w, c[2], cb);
+            dep = fmaf(w, zs[base + j], dep);
+            if (wgt) wgt[base + j] = w;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, d); cr += __shfl_xor_sync(FULL, cr, d); cg += __shfl_xor_sync(FULL, cg, d);
+        cb += __shfl_xor_sync(FULL, cb, d); dep += __shfl_xor_sync(FULL, dep, d);
+    }
+    if (lane == 0) {
+        if (k.env_h > 0) {
+            float e[3];
+            egn_env_radiance(emission, k.env_h, dx, dy, dz, e);
+            const float b0 = Tend * e[0], b1 = Tend * e[1], b2 = Tend * e[2];
+            out.env[ray * 3] = e[0]; out.env[ray * 3 + 1] = e[1]; out.env[ray * 3 + 2] = e[2];
+            out.bg[ray * 3] = b0; out.bg[ray * 3 + 1] = b1; out.bg[ray * 3 + 2] = b2;
+            cr += b0; cg += b1; cb += b2;
+            out.alpha[ray * acols + S] = 1.f;       // EgoNeRF.py:587
+        }
+        out.rgb[ray * 3] = fminf(fmaxf(cr, 0.f), 1.f);
+        out.rgb[ray * 3 + 1] = fminf(fmaxf(cg, 0.f), 1.f);
+        out.rgb[ray * 3 + 2] = fminf(fmaxf(cb, 0.f), 1.f);
+        out.depth[ray] = dep + (1.f - acc) * dz;     // EgoNeRF.py:598: rays_chunk[..., -1] is d_z
+        if (bgw) bgw[ray] = Tend;
+    }
+}
+
+int egn_launch_composite(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                         const float* fsig, const float* feat, const float* rgbs, const EgnOutputs* out, float* wgt,
+                         float* bgw, cudaStream_t st) {
+    long long threads = n * 32;
+    egn_composite_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(k, p->emission, rays, n, z, fsig, feat, rgbs,
+                                                                           *out, wgt, bgw);
+    return (int)cudaGetLastError();
+}

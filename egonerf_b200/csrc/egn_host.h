@@ -1,0 +1,47 @@
+// Internal launch prototypes shared between the translation units of libegn_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include "egn_device.cuh"
+
+// workspace carve-up (per ray chunk of n rays, S samples/ray): see egn_abi.cu
+struct EgnWorkspace {
+    float* z;        // (n,S)      sorted sample depths (fine_z_vals, EgoNeRF.py:537)
+    float* fsig;     // (n,S)      density feature before feature2density
+    float* feat;     // (n,S,28)   appearance feature (27 used)
+    float* rgbs;     // (n,S,3)    decoded sample colours
+    float* wgt;      // (n,S)      compositing weights (saved for backward)
+    float* bgw;      // (n)        background weight T_S
+    float* d_rgbs;   // (n,S,3)    backward scratch
+    float* d_fsig;   // (n,S)
+    float* d_feat;   // (n,S,28)
+};
+
+int egn_launch_pack(const EgnConfig* cfg, const EgnParams* params, float* tables, cudaStream_t st);
+int egn_launch_unpack(const EgnConfig* cfg, const float* d_tables, const EgnGrads* grads, cudaStream_t st);
+
+int egn_launch_coarse(const EgnKernelCfg& k, const float* rays, long long n, int is_train, const float* u_c,
+                      const float* u_f, unsigned long long seed, long long ray0, float near_plane, float* z_out,
+                      cudaStream_t st);
+int egn_launch_gather(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                      float* fsig, float* feat, cudaStream_t st);
+int egn_launch_gather_coords(const EgnKernelCfg& k, const EgnParams* p, const float* coords7, long long m, int coarse,
+                             float* fsig, float* feat, cudaStream_t st);
+int egn_launch_mlp(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
+                   float* rgbs, cudaStream_t st);
+int egn_launch_composite(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                         const float* fsig, const float* feat, const float* rgbs, const EgnOutputs* out, float* wgt,
+                         float* bgw, cudaStream_t st);
+int egn_launch_coords(const EgnKernelCfg& k, const float* xyz, long long m, float* coords7, cudaStream_t st);
+int egn_launch_envmap(int env_h, const float* emission, const float* dirs, long long n, float* out, cudaStream_t st);
+int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, long long n, const float* d_out,
+                          float* d_emission, cudaStream_t st);
+
+// backward
+int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                             const float* fsig, const float* feat, const float* rgbs, const float* wgt, const float* bgw,
+                             const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
+                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, cudaStream_t st);
+int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
+                       const float* rgbs, const float* d_rgbs, float* d_feat, const EgnGrads* g, cudaStream_t st);
+int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                          const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st);

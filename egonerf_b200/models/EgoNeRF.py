@@ -1,0 +1,406 @@
+"""Drop-in `EgoNeRF` module: the reference's operator surface (models/EgoNeRF.py:27-602, models/tensorBase.py:132-268)
+on top of libegn_b200.  Parameter names, shapes and state_dict keys are the reference's, so checkpoints and
+`train.py`'s optimiser groups work unchanged; `forward` hands raw device pointers to the C ABI.
+
+No CPU path: every compute entry point raises if the tensors are not on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from math import pi
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+from .coordinates import YinYangSphericalCoords, sample_schedule
+from .envmap import EnvironmentMap
+from .decoders import MLPRender_Fea, MLPRender, SHRender, RGBRender
+
+MAT_MODE = [[0, 1], [0, 2], [1, 2]]     # EgoNeRF.py:30-33
+VEC_MODE = [2, 1, 0]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"egonerf_b200: {what} must be a CUDA tensor — there is no CPU fallback")
+
+
+class _VolumeRender(torch.autograd.Function):
+    """EgoNeRF.forward (EgoNeRF.py:491-602) as one autograd node around egn_render_forward / egn_render_backward."""
+
+    @staticmethod
+    def forward(ctx, model, opts, rays, u_coarse, u_fine, *params):
+        lib = _lib.load()
+        n = rays.shape[0]
+        cfg = model._config(opts)
+        S = lib.egn_samples_per_ray(cfg)
+        has_env = cfg.env_h > 0
+        dev = rays.device
+        need_grad = opts["is_train"] and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        rgb = torch.empty(n, 3, device=dev)
+        depth = torch.empty(n, device=dev)
+        alpha = torch.empty(n, S + (1 if has_env else 0), device=dev)
+        bg = torch.empty(n, 3, device=dev) if has_env else None
+        env = torch.empty(n, 3, device=dev) if has_env else None
+        nbytes = lib.egn_workspace_bytes(cfg, n) if need_grad else lib.egn_workspace_bytes_eval(cfg, n)
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        out = _lib.EgnOutputs(rgb.data_ptr(), depth.data_ptr(), bg.data_ptr() if has_env else None,
+                              env.data_ptr() if has_env else None, alpha.data_ptr())
+        P = model._params_struct()
+        tables = model._render_tables()
+        _lib.check(lib.egn_render_forward(cfg, P, tables.data_ptr(), rays.data_ptr(), n, int(opts["is_train"]),
+                                          _lib.ptr(u_coarse), _lib.ptr(u_fine), int(opts["seed"]), int(opts["ray_index0"]),
+                                          out, ws.data_ptr(), _stream()))
+        ctx.mark_non_differentiable(depth)
+        if need_grad:
+            ctx.model, ctx.opts, ctx.n = model, opts, n
+            ctx.save_for_backward(rays, ws, tables)
+        ctx.has_env = has_env
+        ctx.need_grad = need_grad
+        if has_env:
+            return rgb, depth, bg, env, alpha
+        return rgb, depth, alpha
+
+    @staticmethod
+    def backward(ctx, *douts):
+        if not ctx.need_grad:
+            raise RuntimeError("egonerf_b200: backward through a forward that was run without gradients")
+        lib = _lib.load()
+        model, opts = ctx.model, ctx.opts
+        rays, ws, tables = ctx.saved_tensors
+        if ctx.has_env:
+            d_rgb, _, d_bg, d_env, d_alpha = douts
+        else:
+            d_rgb, _, d_alpha = douts
+            d_bg = d_env = None
+        c = lambda t: None if t is None else t.contiguous().float()
+        d_rgb, d_bg, d_env, d_alpha = c(d_rgb), c(d_bg), c(d_env), c(d_alpha)
+        cfg = model._config(opts)
+        d_tables = torch.zeros_like(tables)
+        plist = model._param_list()
+        grads = [torch.zeros_like(p) if i >= 24 else torch.empty_like(p) for i, p in enumerate(plist)]
+        G = model._grads_struct(grads)
+        _lib.check(lib.egn_render_backward(cfg, model._params_struct(), tables.data_ptr(), rays.data_ptr(), ctx.n,
+                                           ws.data_ptr(), _lib.ptr(d_rgb), _lib.ptr(d_bg), _lib.ptr(d_env),
+                                           _lib.ptr(d_alpha), d_tables.data_ptr(), G, _stream()))
+        _lib.check(lib.egn_unpack_table_grads(cfg, d_tables.data_ptr(), G, _stream()))
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class EgoNeRF(torch.nn.Module):
+    """Yin-Yang VM-decomposed radiance field (reference: models/EgoNeRF.py:27, ctor kwargs models/tensorBase.py:133-139)."""
+
+    def __init__(self, aabb, gridSize, device, coordinates, density_n_comp=8, appearance_n_comp=24, app_dim=27,
+                 shadingMode='MLP_PE', alphaMask=None, near_far=[2.0, 6.0], density_shift=-10, alphaMask_thres=0.001,
+                 distance_scale=25, rayMarch_weight_thres=0.0001, pos_pe=6, view_pe=6, fea_pe=6, featureC=128,
+                 step_ratio=2.0, fea2denseAct='softplus', use_envmap=False, envmap_res_H=1000, envmap=None,
+                 coarse_sigma_grid_update_rule=None, coarse_sigma_grid_reso=None, interval_th=False):
+        super().__init__()
+        if not isinstance(coordinates, YinYangSphericalCoords):
+            raise TypeError("EgoNeRF needs egonerf_b200.models.coordinates.YinYangSphericalCoords")
+        if isinstance(density_n_comp, int):
+            density_n_comp = [density_n_comp] * 3
+        if isinstance(appearance_n_comp, int):
+            appearance_n_comp = [appearance_n_comp] * 3
+        self.density_n_comp, self.app_n_comp, self.app_dim = list(density_n_comp), list(appearance_n_comp), app_dim
+        self.aabb = aabb
+        self.alphaMask = alphaMask
+        self.device = device
+        self.density_shift, self.alphaMask_thres, self.distance_scale = density_shift, alphaMask_thres, distance_scale
+        self.rayMarch_weight_thres, self.fea2denseAct = rayMarch_weight_thres, fea2denseAct
+        self.near_far, self.step_ratio = near_far, step_ratio
+        self.gridSize = torch.LongTensor(list(gridSize)).to(device)
+        self.matMode_yin = self.matMode_yang = MAT_MODE
+        self.vecMode_yin = self.vecMode_yang = VEC_MODE
+        self.coordinates = coordinates
+        self.coarse_sigma_grid_update_rule = coarse_sigma_grid_update_rule
+        self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = shadingMode, pos_pe, view_pe, fea_pe, featureC
+
+        self.envmap = None
+        if use_envmap:
+            if envmap is None:
+                self.init_envmap(envmap_res_H, init_strategy='random', device=device)
+            else:
+                self.envmap = EnvironmentMap(h=envmap.emission.shape[2], init_strategy='zero', device=device)
+                self.envmap.load_envmap(envmap.emission, device=device)
+        self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
+        self.init_svd_volume(gridSize[0], device)
+        self._tables = None
+        self._tables_key = None
+        self._sched = {}
+
+    # ---- parameters (EgoNeRF.py:96-122) -------------------------------------------------------------
+    def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
+        if shadingMode == 'MLP_Fea':
+            self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        elif shadingMode == 'MLP':
+            self.renderModule = MLPRender(self.app_dim, view_pe, featureC).to(device)
+        elif shadingMode == 'SH':
+            self.renderModule = SHRender
+        elif shadingMode == 'RGB':
+            assert self.app_dim == 3
+            self.renderModule = RGBRender
+        else:
+            # MLP_PE crashes inside the reference's own EgoNeRF.forward (7-D points)
+            raise NotImplementedError(f"shadingMode {shadingMode!r} is not supported by the EgoNeRF path")
+
+    def init_one_svd(self, n_component, gridSize, scale, device):
+        planes, lines = {}, {}
+        for h in ('yin', 'yang'):
+            planes[h] = torch.nn.ParameterList([torch.nn.Parameter(scale * torch.randn(
+                (1, n_component[i], gridSize[MAT_MODE[i][1]], gridSize[MAT_MODE[i][0]]))) for i in range(3)]).to(device)
+            lines[h] = torch.nn.ParameterList([torch.nn.Parameter(scale * torch.randn(
+                (1, n_component[i], gridSize[VEC_MODE[i]], 1))) for i in range(3)]).to(device)
+        return planes['yin'], lines['yin'], planes['yang'], lines['yang']
+
+    def init_svd_volume(self, res, device):
+        g = self.gridSize.tolist()
+        self.density_plane_yin, self.density_line_yin, self.density_plane_yang, self.density_line_yang = \
+            self.init_one_svd(self.density_n_comp, g, 0.1, device)
+        self.app_plane_yin, self.app_line_yin, self.app_plane_yang, self.app_line_yang = \
+            self.init_one_svd(self.app_n_comp, g, 0.1, device)
+        self.basis_mat_yin = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+        self.basis_mat_yang = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+
+    def init_envmap(self, envmap_res_H, init_strategy='zero', device='cuda'):
+        self.envmap = EnvironmentMap(h=envmap_res_H, init_strategy=init_strategy, device=device)
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001, lr_init_envmap=0.1):
+        """EgoNeRF.py:139-156."""
+        groups = []
+        for h in ('yin', 'yang'):
+            groups += [{'params': getattr(self, f'density_line_{h}'), 'lr': lr_init_spatialxyz},
+                       {'params': getattr(self, f'density_plane_{h}'), 'lr': lr_init_spatialxyz},
+                       {'params': getattr(self, f'app_line_{h}'), 'lr': lr_init_spatialxyz},
+                       {'params': getattr(self, f'app_plane_{h}'), 'lr': lr_init_spatialxyz},
+                       {'params': getattr(self, f'basis_mat_{h}').parameters(), 'lr': lr_init_network}]
+        if isinstance(self.renderModule, torch.nn.Module):
+            groups += [{'params': self.renderModule.parameters(), 'lr': lr_init_network}]
+        if self.envmap is not None:
+            groups += [{'params': self.envmap.emission, 'lr': lr_init_envmap}]
+        return groups
+
+    # ---- checkpoint surface (tensorBase.py:241-268, EgoNeRF.py:158-187) -------------------------------
+    def get_kwargs(self):
+        return {'aabb': self.aabb, 'gridSize': self.gridSize.tolist(), 'density_n_comp': self.density_n_comp,
+                'appearance_n_comp': self.app_n_comp, 'app_dim': self.app_dim, 'density_shift': self.density_shift,
+                'alphaMask_thres': self.alphaMask_thres, 'distance_scale': self.distance_scale,
+                'rayMarch_weight_thres': self.rayMarch_weight_thres, 'fea2denseAct': self.fea2denseAct,
+                'near_far': self.near_far, 'step_ratio': self.step_ratio, 'shadingMode': self.shadingMode,
+                'pos_pe': self.pos_pe, 'view_pe': self.view_pe, 'fea_pe': self.fea_pe, 'featureC': self.featureC,
+                'coordinates': self.coordinates, 'use_envmap': self.envmap is not None, 'envmap': self.envmap,
+                'coarse_sigma_grid_update_rule': self.coarse_sigma_grid_update_rule}
+
+    def save(self, path, global_step):
+        ckpt = {'kwargs': self.get_kwargs(), 'state_dict': self.state_dict(), 'global_step': global_step}
+        if self.envmap is not None:
+            ckpt.update({'envmap.emission': self.envmap.emission.detach().cpu().numpy(),
+                         'envmap_res_H': self.envmap.emission.shape[2]})
+        torch.save(ckpt, path)
+
+    def load(self, ckpt):
+        if self.envmap is not None:
+            self.envmap = EnvironmentMap(h=ckpt['envmap_res_H'], init_strategy='zero', device=self.device)
+            self.envmap.load_envmap(emission=ckpt['envmap.emission'], device=self.device)
+        self.load_state_dict(ckpt['state_dict'])
+        self.update_coarse_sigma_grid()
+        return ckpt['global_step']
+
+    # ---- render tables ------------------------------------------------------------------------------
+    def _factor_params(self):
+        out = []
+        for h in ('yin', 'yang'):
+            for kind in ('density_plane', 'density_line', 'app_plane', 'app_line'):
+                out += list(getattr(self, f'{kind}_{h}'))
+        return out                                   # 24 tensors: [h][kind][i]
+
+    def _param_list(self):
+        ps = self._factor_params() + [self.basis_mat_yin.weight, self.basis_mat_yang.weight]
+        if isinstance(self.renderModule, torch.nn.Module):
+            ps += [self.renderModule.mlp[0].weight, self.renderModule.mlp[0].bias, self.renderModule.mlp[2].weight,
+                   self.renderModule.mlp[2].bias, self.renderModule.mlp[4].weight, self.renderModule.mlp[4].bias]
+        if self.envmap is not None:
+            ps += [self.envmap.emission]
+        return ps
+
+    def _fill_struct(self, S, tensors):
+        f = tensors[:24]
+        for hi in range(2):
+            for ki, kind in enumerate(('density_plane', 'density_line', 'app_plane', 'app_line')):
+                for i in range(3):
+                    getattr(S, kind)[hi][i] = _lib.ptr(f[hi * 12 + ki * 3 + i])
+        S.basis[0], S.basis[1] = _lib.ptr(tensors[24]), _lib.ptr(tensors[25])
+        k = 26
+        if isinstance(self.renderModule, torch.nn.Module):
+            for l in range(3):
+                S.mlp_w[l] = _lib.ptr(tensors[k + 2 * l])
+                S.mlp_b[l] = _lib.ptr(tensors[k + 2 * l + 1])
+            k += 6
+        if self.envmap is not None:
+            S.emission = _lib.ptr(tensors[k])
+        return S
+
+    def _params_struct(self):
+        return self._fill_struct(_lib.EgnParams(), [p.detach() for p in self._param_list()])
+
+    def _grads_struct(self, grads):
+        return self._fill_struct(_lib.EgnGrads(), grads)
+
+    def update_coarse_sigma_grid(self):
+        """Reference: AvgPool refresh of the coarse density grid (EgoNeRF.py:124-133, called every iteration by
+        train.py:356-357).  Here: re-pack the render tables (interleaved fine tables + pooled coarse tables)."""
+        self._tables_key = None
+
+    def _render_tables(self):
+        fp = self._factor_params()
+        _need_cuda(fp[0], "model parameters")
+        key = tuple((p.data_ptr(), p._version) for p in fp)
+        if self._tables is None or key != self._tables_key:
+            lib = _lib.load()
+            cfg = self._config(None)
+            nfl = lib.egn_table_floats(cfg)
+            if nfl < 0:
+                _lib.check(1)
+            if self._tables is None or self._tables.numel() != nfl:
+                self._tables = torch.empty(int(nfl), device=fp[0].device, dtype=torch.float32)
+            else:
+                self._tables = torch.empty_like(self._tables)     # saved-for-backward tables must not be overwritten
+            _lib.check(lib.egn_pack_tables(cfg, self._params_struct(), self._tables.data_ptr(), _stream()))
+            self._tables_key = key
+        return self._tables
+
+    def _config(self, opts):
+        co = self.coordinates
+        cfg = _lib.EgnConfig()
+        cfg.grid[:] = self.gridSize.tolist()
+        if len(set(self.density_n_comp)) != 1 or len(set(self.app_n_comp)) != 1:
+            raise NotImplementedError("n_lamb_sigma / n_lamb_sh must be equal across the three factor pairs")
+        cfg.c_sigma, cfg.c_app, cfg.app_dim = self.density_n_comp[0], self.app_n_comp[0], self.app_dim
+        cfg.shading = _lib.SHADING[self.shadingMode]
+        cfg.view_pe, cfg.fea_pe, cfg.feature_c = self.view_pe, self.fea_pe, self.featureC
+        cfg.fea2dense = _lib.ACT[self.fea2denseAct]
+        cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0
+        cfg.center[:] = co.center.cpu().tolist()
+        cfg.near_plane = self.near_far[0]
+        cfg.density_shift, cfg.distance_scale = self.density_shift, self.distance_scale
+        near, inv = co.near.cpu(), co.inv_diff.cpu()
+        cfg.ang_near[:] = [float(near[1]), float(near[2])]
+        cfg.ang_inv[:] = [float(inv[1]), float(inv[2])]
+        dev = self.density_plane_yin[0].device
+        if 'knots' not in self._sched:
+            self._sched['knots'] = co.r_knots().to(dev).contiguous()
+        cfg.r_knots = self._sched['knots'].data_ptr()
+        if opts is not None:
+            nc = int(opts["n_coarse"])
+            cfg.n_coarse, cfg.n_fine = nc, int(opts["n_fine"])
+            cfg.use_coarse_sample, cfg.resampling = int(opts["use_coarse_sample"]), int(opts["resampling"])
+            if ('z', nc) not in self._sched:
+                self._sched[('z', nc)] = sample_schedule(self.near_far[0], self.near_far[1], co.r0, nc).to(dev).contiguous()
+            cfg.z_coarse = self._sched[('z', nc)].data_ptr()
+        return cfg
+
+    # ---- stand-alone operators ------------------------------------------------------------------------
+    def feature2density(self, density_features):
+        """tensorBase.py:415-419 (element-wise; plain torch)."""
+        if self.fea2denseAct == "softplus":
+            return F.softplus(density_features + self.density_shift)
+        return F.relu(density_features)
+
+    def _gather(self, coords_sampled, coarse=False, want_app=False):
+        _need_cuda(coords_sampled, "coords_sampled")
+        lib = _lib.load()
+        c7 = coords_sampled.detach().reshape(-1, 7).contiguous().float()
+        m = c7.shape[0]
+        cfg = self._config(None)
+        tables = self._render_tables()
+        sig = torch.empty(m, device=c7.device)
+        if want_app:
+            feat = torch.empty(m, 28, device=c7.device)
+            _lib.check(lib.egn_app_feature(cfg, self._params_struct(), tables.data_ptr(), c7.data_ptr(), m,
+                                           sig.data_ptr(), feat.data_ptr(), _stream()))
+            return feat[:, :self.app_dim].reshape(*coords_sampled.shape[:-1], self.app_dim)
+        _lib.check(lib.egn_density_feature(cfg, tables.data_ptr(), c7.data_ptr(), m, int(coarse), sig.data_ptr(), _stream()))
+        return sig.view(coords_sampled.shape[:-1])
+
+    def compute_densityfeature(self, coords_sampled):
+        """EgoNeRF.py:291-347 (forward only; gradients flow through `forward`)."""
+        return self._gather(coords_sampled)
+
+    def compute_coarse_densityfeature(self, coords_sampled, coarse_sigma_grid_update_rule='conv'):
+        """EgoNeRF.py:232-289."""
+        return self._gather(coords_sampled, coarse=True)
+
+    def compute_appfeature(self, coords_sampled):
+        """EgoNeRF.py:349-413."""
+        return self._gather(coords_sampled, want_app=True)
+
+    # ---- regularisers on the factor tensors: plain torch on the same Parameters ------
+    def vectorDiffs(self, vector_comps):
+        total = 0
+        for v in vector_comps:
+            n_comp, n_size = v.shape[1:-1]
+            dotp = torch.matmul(v.view(n_comp, n_size), v.view(n_comp, n_size).transpose(-1, -2))
+            total = total + torch.mean(torch.abs(dotp.view(-1)[1:].view(n_comp - 1, n_comp + 1)[..., :-1]))
+        return total
+
+    def vector_comp_diffs(self):
+        return sum(self.vectorDiffs(getattr(self, f'{k}_line_{h}')) for k in ('density', 'app') for h in ('yin', 'yang'))
+
+    def density_L1(self):
+        total = 0
+        for h in ('yin', 'yang'):
+            for i in range(3):
+                total = total + torch.mean(torch.abs(getattr(self, f'density_plane_{h}')[i])) \
+                    + torch.mean(torch.abs(getattr(self, f'density_line_{h}')[i]))
+        return total
+
+    def TV_loss_density(self, reg):
+        return sum(reg(getattr(self, f'density_plane_{h}')[i]) * 1e-2 for i in range(3) for h in ('yin', 'yang'))
+
+    def TV_loss_app(self, reg):
+        return sum(reg(getattr(self, f'app_plane_{h}')[i]) * 1e-2 for i in range(3) for h in ('yin', 'yang'))
+
+    def upsample_volume_grid(self, res_target):
+        raise NotImplementedError("coarse-to-fine upsampling is disabled in every shipped config "
+                                  "(configs/EgoNeRF/common.txt:12); SURVEY.md §8 f4")
+
+    def updateAlphaMask(self, gridSize=None):
+        raise NotImplementedError("alpha-mask update is disabled in every shipped config (common.txt:13); SURVEY.md §8 f4")
+
+    # ---- forward --------------------------------------------------------------------------------------
+    def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, n_coarse=-1, n_fine=0,
+                exp_sampling=False, pretrain_envmap=False, pivotal_sample_th=0., resampling=False,
+                use_coarse_sample=True, interval_th=False, u_coarse=None, u_fine=None, seed=None, ray_index0=0):
+        """Same signature and return tuple as the reference (EgoNeRF.py:491-602).  Extra keyword-only extensions:
+        `u_coarse` / `u_fine` inject the train-mode uniforms (reproducible parity tests), `seed` / `ray_index0` key
+        the in-kernel generator so that ray-sharded runs draw disjoint streams."""
+        _need_cuda(rays_chunk, "rays_chunk")
+        if pretrain_envmap:
+            return self.envmap.get_radiance(rays_chunk[:, 3:6])
+        if ndc_ray:
+            raise NotImplementedError          # EgoNeRF.py:503-504
+        if not exp_sampling:
+            raise NotImplementedError("uniform marching (exp_sampling=False, tensorBase.py:308-327) is not built; "
+                                      "every shipped config samples exponentially")
+        if n_coarse <= 0:
+            raise ValueError("n_coarse must be given")
+        rays = rays_chunk.detach().contiguous().float()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if is_train and u_coarse is None else 0
+        opts = dict(is_train=bool(is_train), n_coarse=n_coarse, n_fine=n_fine if resampling else 0,
+                    resampling=bool(resampling), use_coarse_sample=bool(use_coarse_sample), seed=seed,
+                    ray_index0=ray_index0)
+        uc = u_coarse.contiguous().float() if u_coarse is not None else None
+        uf = u_fine.contiguous().float() if u_fine is not None else None
+        outs = _VolumeRender.apply(self, opts, rays, uc, uf, *self._param_list())
+        if self.envmap is not None:
+            rgb, depth, bg, env, alpha = outs
+            return rgb, depth, bg, env, alpha
+        rgb, depth, alpha = outs
+        return rgb, depth, None, None, alpha

@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference's Yin-Yang coordinate object (models/coordinates.py:432-520 on top of
+GenericSphericalCoords :73-266).  It holds the scalars and the two exponential ladders the kernels need; the
+per-sample arithmetic (from_cartesian / normalize_coord) runs in libegn_b200 (`egn_yinyang_coords`).
+
+Only what the EgoNeRF path uses is mirrored: `exp_r=True` with `interval_th=True`, which is what every shipped
+config selects (configs/EgoNeRF/common.txt:2-3,14).  The other eight coordinate systems of the reference are
+out of scope.
+"""
+from __future__ import annotations
+
+from math import exp, log, pi, sqrt
+
+import torch
+
+from .. import _lib
+
+
+def exp_ladder(r0, ratio, index: torch.Tensor) -> torch.Tensor:
+    """r_0 = 0, r_i = r0 * ratio**(i-1) in fp32 (extra/test_exp_r.py:10-15)."""
+    r = torch.zeros(index.shape, dtype=torch.float32)
+    nz = index > 0
+    r[nz] = r0 * ratio ** (index[nz] - 1)
+    return r
+
+
+def clamp_short_intervals(r: torch.Tensor, r0: float) -> torch.Tensor:
+    """Intervals not longer than r0 become exactly r0 and the tail is shifted to stay continuous
+    (EgoNeRF.py:72-76, coordinates.py:120-124)."""
+    step = r[1:] - r[:-1]
+    n_short = int((step <= r0).sum())
+    run = torch.cumsum(step, dim=0)
+    out = r.clone()
+    out[:n_short + 1] = torch.arange(n_short + 1) * r0
+    out[n_short + 1:] = r[n_short + 1:] + r0 * (step <= r0).sum() - run[n_short - 1]
+    return out
+
+
+def sample_schedule(near: float, far: float, r0: float, n: int) -> torch.Tensor:
+    """Radii of the n coarse samples (without `near`), EgoNeRF.sample_ray_exp interval_th branch (EgoNeRF.py:69-76)."""
+    ratio = exp(log((far - near) / r0) / (n - 1))
+    return clamp_short_intervals(exp_ladder(r0, ratio, torch.arange(n).float()), r0)
+
+
+class YinYangSphericalCoords:
+    """[r_n, theta_n, phi_n, r_e, theta_e, phi_e, Y]: Y = 0 Yin grid, 1 Yang grid."""
+
+    def __init__(self, device, aabb, exp_r=True, N_voxel=None, r0=None, interval_th=False):
+        if not exp_r or not interval_th:
+            raise NotImplementedError("egonerf_b200 implements the exp_r + interval_th Yin-Yang grid only "
+                                      "(the configuration of every shipped EgoNeRF config)")
+        self.device = device
+        self.aabb = aabb.to(device)
+        self.center = self.aabb.sum(0).div(2)
+        self.exp_r = exp_r
+        self.interval_th = interval_th
+        self.update_aabb(aabb)
+        self.set_resolution(self.N_to_reso(N_voxel, aabb), r0=r0)
+
+    # ---- scalars (coordinates.py:187-204, 500-505) --------------------------------------------------
+    def _get_max_r(self, aabb):
+        lo, hi = aabb.tolist()
+        corners = torch.tensor([[lo[b] if (i >> b) & 1 else hi[b] for b in range(3)] for i in range(8)],
+                               dtype=torch.float32)
+        return (corners - self.center.cpu()).pow(2).sum(1).sqrt().amax()
+
+    def update_aabb(self, new_aabb):
+        max_r = self._get_max_r(new_aabb.cpu())
+        self.near = torch.tensor([0, pi / 4, -3 * pi / 4, 0, pi / 4, -3 * pi / 4], dtype=torch.float32, device=self.device)
+        self.far = torch.tensor([max_r, 3 * pi / 4, 3 * pi / 4, max_r, 3 * pi / 4, 3 * pi / 4], dtype=torch.float32,
+                                device=self.device)
+        self.inv_diff = 1.0 / (self.far - self.near)
+
+    def N_to_reso(self, n_voxels, bbox=None):
+        n_r = int(pow(n_voxels, 1 / 3) / 2)
+        n_t = int(n_r * 2 * sqrt(3) / 3)
+        n_p = n_t * 3
+        return [n_r + n_r % 2, n_t + n_t % 2, n_p + n_p % 2]
+
+    def set_resolution(self, resolution, r0=None):
+        self.N_r, self.N_theta, self.N_phi = resolution
+        self.r0 = r0 if r0 is not None else 0.05
+        self.ratio = pow(self.far[0].cpu() / self.r0, 1 / (self.N_r - 1))
+        self._knots = None
+
+    # ---- ladders ------------------------------------------------------------------------------------
+    def r_knots(self) -> torch.Tensor:
+        """The N_r + 1 knot radii normalize_r rebuilds on every call (coordinates.py:118-124), fp32, CPU."""
+        if self._knots is None:
+            ratio = pow(self.far[0].cpu() / self.r0, 1 / (self.N_r - 1))
+            self._knots = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(self.N_r + 1)), self.r0)
+        return self._knots
+
+    # ---- operators (run in libegn_b200) -------------------------------------------------------------
+    def _cfg(self):
+        cfg = _lib.EgnConfig()
+        cfg.grid[:] = [self.N_r, self.N_theta, self.N_phi]
+        cfg.c_sigma, cfg.c_app, cfg.app_dim, cfg.shading, cfg.feature_c = 16, 48, 27, 2, 128
+        cfg.app_dim = 3
+        c = self.center.cpu().tolist()
+        cfg.center[:] = c
+        near, inv = self.near.cpu(), self.inv_diff.cpu()
+        cfg.ang_near[:] = [float(near[1]), float(near[2])]
+        cfg.ang_inv[:] = [float(inv[1]), float(inv[2])]
+        self._knots_dev = self.r_knots().to(self.device).contiguous()
+        cfg.r_knots = self._knots_dev.data_ptr()
+        return cfg
+
+    def cart_to_normalized(self, xyz: torch.Tensor) -> torch.Tensor:
+        """normalize_coord(from_cartesian(xyz)) (coordinates.py:442-498) for (..., 3) device points."""
+        lib = _lib.load()
+        if not xyz.is_cuda:
+            raise RuntimeError("egonerf_b200 runs on CUDA tensors only (no CPU fallback)")
+        flat = xyz.reshape(-1, 3).contiguous().float()
+        out = torch.empty(flat.shape[0], 7, device=xyz.device, dtype=torch.float32)
+        cfg = self._cfg()
+        _lib.check(lib.egn_yinyang_coords(cfg, flat.data_ptr(), flat.shape[0], out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+        return out.view(*xyz.shape[:-1], 7)
+
+
+coordinates_dict = {"yinyang": YinYangSphericalCoords}

@@ -1,0 +1,174 @@
+/*
+ * egn.h — C ABI of libegn_b200.so: the B200 (sm_100a) volume-rendering path of EgoNeRF.
+ *
+ * The reference (changwoonchoi/EgoNeRF) has no FFI layer: its boundary for this path is the Python
+ * operator surface.  Each entry point below names the reference function(s) it
+ * replaces (file:line under the reference tree).  The host-side mirror that binds them with ctypes
+ * is egonerf_b200/_lib.py; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every pointer marked "device" is a CUDA device pointer that
+ *     the CALLER owns (PyTorch's caching allocator in the Python mirror); the library allocates
+ *     nothing and keeps no global mutable state, so all entry points are re-entrant (autograd calls
+ *     backward from its own thread).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - return value: 0 = ok, non-zero = error; egn_last_error() returns a thread-local message.
+ *   - all floating-point data is IEEE fp32 unless a mode says otherwise.
+ */
+#ifndef EGN_H_
+#define EGN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGN_ABI_VERSION 1
+
+/* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
+enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
+/* TensorBase.feature2density (models/tensorBase.py:415-419) */
+enum { EGN_ACT_SOFTPLUS = 0, EGN_ACT_RELU = 1 };
+/* MLP arithmetic: exact fp32 FFMA, or tcgen05 tensor cores with a 3-term bf16 split (fp32-equivalent) */
+enum { EGN_MLP_FP32 = 0, EGN_MLP_TC_SPLIT = 1, EGN_MLP_TC_BF16 = 2 };
+
+/* Static description of one model / scene.  Scalars mirror the constructor arguments of
+ * EgoNeRF / TensorBase (models/tensorBase.py:133-139) and YinYangSphericalCoords
+ * (models/coordinates.py:432-520). */
+typedef struct EgnConfig {
+    int32_t grid[3];          /* [N_r, N_theta, N_phi] per hemisphere (coordinates.py:507-520) */
+    int32_t c_sigma;          /* density components per plane, n_lamb_sigma[i] (all three equal) */
+    int32_t c_app;            /* appearance components per plane, n_lamb_sh[i] (all three equal) */
+    int32_t app_dim;          /* basis_mat output width (27) */
+    int32_t shading;          /* EGN_SHADE_* */
+    int32_t view_pe, fea_pe;  /* positional-encoding frequencies (tensorBase.py:14-19) */
+    int32_t feature_c;        /* MLP hidden width (128) */
+    int32_t fea2dense;        /* EGN_ACT_* */
+    int32_t n_coarse;         /* coarse samples per ray */
+    int32_t n_fine;           /* inverse-CDF draws per ray (0 when resampling is off) */
+    int32_t use_coarse_sample;/* EgoNeRF.py:536-539 */
+    int32_t resampling;       /* EgoNeRF.py:525 */
+    int32_t env_h;            /* envmap is (3, 2*env_h, env_h); 0 = no envmap (models/envmap.py:17-23) */
+    int32_t mlp_mode;         /* EGN_MLP_* */
+    float   center[3];        /* coordinates.center = aabb.sum(0)/2 (coordinates.py:77) */
+    float   near_plane;       /* near_far[0] */
+    float   density_shift;
+    float   distance_scale;
+    float   ang_near[2];      /* fp32(pi/4), fp32(-3pi/4)            (coordinates.py:500-505) */
+    float   ang_inv[2];       /* 1/(far-near) of theta, phi in fp32  (coordinates.py:505) */
+    const float* r_knots;     /* device, N_r+1 : reference r ladder of normalize_r (coordinates.py:118-124) */
+    const float* z_coarse;    /* device, n_coarse : r schedule of sample_ray_exp WITHOUT near (EgoNeRF.py:69-76);
+                                 the kernels add near_plane and, in train mode, the interval jitter (:78-82) */
+} EgnConfig;
+
+/* Parameters in the REFERENCE layout (contiguous NCHW fp32, shapes of EgoNeRF.init_one_svd,
+ * models/EgoNeRF.py:102-122): hemisphere h (0 = yin, 1 = yang), factor i (matMode [[0,1],[0,2],[1,2]],
+ * vecMode [2,1,0]).  plane[h][i] is (1,C,G[m1],G[m0]); line[h][i] is (1,C,G[v],1). */
+typedef struct EgnParams {
+    const float* density_plane[2][3];
+    const float* density_line[2][3];
+    const float* app_plane[2][3];
+    const float* app_line[2][3];
+    const float* basis[2];    /* basis_mat_{yin,yang}.weight (app_dim, 3*c_app) */
+    const float* mlp_w[3];    /* renderModule.mlp.{0,2,4}.weight (out,in) ; NULL for RGB / SH */
+    const float* mlp_b[3];    /* renderModule.mlp.{0,2,4}.bias */
+    const float* emission;    /* envmap.emission (3, 2*env_h, env_h) or NULL */
+} EgnParams;
+
+/* Gradients, same layout as EgnParams.  basis / mlp / emission buffers are ACCUMULATED into (caller zeroes);
+ * the factor plane/line buffers are written by egn_unpack_table_grads. */
+typedef struct EgnGrads {
+    float* density_plane[2][3];
+    float* density_line[2][3];
+    float* app_plane[2][3];
+    float* app_line[2][3];
+    float* basis[2];
+    float* mlp_w[3];
+    float* mlp_b[3];
+    float* emission;
+} EgnGrads;
+
+/* Per-ray outputs of EgoNeRF.forward (models/EgoNeRF.py:602): all device, caller-allocated. */
+typedef struct EgnOutputs {
+    float* rgb;     /* (n,3)   rgb_map, clamped to [0,1] (EgoNeRF.py:593) */
+    float* depth;   /* (n)     depth_map (EgoNeRF.py:595-598) */
+    float* bg;      /* (n,3)   bg_map = bg_weight * env, NULL without envmap */
+    float* env;     /* (n,3)   env_map, NULL without envmap */
+    float* alpha;   /* (n, S [+1 with envmap])  per-sample alpha (EgoNeRF.py:587,602) */
+} EgnOutputs;
+
+const char* egn_last_error(void);
+int32_t     egn_abi_version(void);
+
+/* S = samples composited per ray (EgoNeRF.py:536-539). */
+int32_t egn_samples_per_ray(const EgnConfig* cfg);
+
+/* ---- render tables -------------------------------------------------------------------------
+ * The kernels gather from "render tables": channels-last copies of the factor planes/lines with
+ * density and appearance channels interleaved per texel ([H][W][c_sigma+c_app], one tap = one
+ * contiguous run), plus the 2x average-pooled density tables of the coarse pass.
+ * egn_pack_tables replaces EgoNeRF.update_coarse_sigma_grid (models/EgoNeRF.py:124-133) and is
+ * re-run whenever the parameters change (once per optimiser step in training). */
+int64_t egn_table_floats(const EgnConfig* cfg);
+int32_t egn_pack_tables(const EgnConfig* cfg, const EgnParams* params, float* tables /*device*/, void* stream);
+/* inverse scatter for training: writes d(tables) (table layout) into the reference-layout factor grads
+ * (overwrites grads->{density,app}_{plane,line}; the other members are untouched) */
+int32_t egn_unpack_table_grads(const EgnConfig* cfg, const float* d_tables /*device*/, const EgnGrads* grads,
+                               void* stream);
+
+/* ---- whole path -------------------------------------------------------------------------------
+ * egn_render_forward replaces EgoNeRF.forward (models/EgoNeRF.py:491-602) for one ray chunk, i.e.
+ * sample_ray_exp (:56-87), YinYangSphericalCoords.from_cartesian / normalize_coord
+ * (models/coordinates.py:442-498, 110-156), compute_coarse_densityfeature (:232-289), raw2alpha
+ * (models/tensorBase.py:22-27), sample_pdf (dataLoader/ray_utils.py:156-187), the sort (:537),
+ * compute_densityfeature (:291-347), compute_appfeature (:349-413), renderModule
+ * (models/tensorBase.py:30-129), EnvironmentMap.get_radiance (models/envmap.py:25-34) and the
+ * compositing of :579-598.
+ *   rays      device (n,6) = [origin, direction]
+ *   is_train  0: deterministic schedule + linspace u (EgoNeRF.py:515-516, ray_utils.py:165-167)
+ *             1: jittered; the uniforms come from u_coarse (n,n_coarse) / u_fine (n,n_fine) when given,
+ *                else from a counter-based generator keyed by (seed, ray_index0 + ray, sample)
+ *   workspace device, egn_workspace_bytes(cfg, n) bytes; after the call it holds the per-sample
+ *             state (z, sigma feature, app feature, sample rgb) that egn_render_backward consumes. */
+int64_t egn_workspace_bytes(const EgnConfig* cfg, int64_t n_rays);
+int64_t egn_workspace_bytes_eval(const EgnConfig* cfg, int64_t n_rays);   /* forward-only (no backward scratch) */
+int32_t egn_render_forward(const EgnConfig* cfg, const EgnParams* params, const float* tables,
+                           const float* rays, int64_t n_rays, int32_t is_train,
+                           const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
+                           const EgnOutputs* out, void* workspace, void* stream);
+
+/* Backward of the above w.r.t. every parameter that receives a gradient in the reference (SURVEY.md
+ * Appendix A10): fine density/appearance planes+lines, both basis matrices, the MLP, the envmap —
+ * through rgb, bg, env and alpha; not through depth, the coarse pass, coordinates or rays.
+ * d_* may be NULL (treated as zero).  d_tables (egn_table_floats floats, caller-zeroed) receives the
+ * factor-table gradients in table layout; run egn_unpack_table_grads afterwards. */
+int32_t egn_render_backward(const EgnConfig* cfg, const EgnParams* params, const float* tables,
+                            const float* rays, int64_t n_rays, const void* workspace,
+                            const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
+                            float* d_tables, const EgnGrads* grads, void* stream);
+
+/* ---- stand-alone operators --------------------------------------------------------------------
+ * coords: device (m,7) normalised Yin-Yang coordinates [r,theta,phi | r,theta,phi | Y] as produced by
+ * YinYangSphericalCoords.normalize_coord (models/coordinates.py:442-466). */
+int32_t egn_density_feature(const EgnConfig* cfg, const float* tables, const float* coords7, int64_t m,
+                            int32_t coarse, float* out /*(m)*/, void* stream);        /* EgoNeRF.py:291-347 / 232-289 */
+/* one gather serves both operators: sigma_out (m) = compute_densityfeature, feat_out (m,28) = compute_appfeature
+ * (rows padded from app_dim to 28 floats) */
+int32_t egn_app_feature(const EgnConfig* cfg, const EgnParams* params, const float* tables, const float* coords7,
+                        int64_t m, float* sigma_out /*(m)*/, float* feat_out /*(m,28)*/, void* stream);  /* EgoNeRF.py:349-413 */
+int32_t egn_yinyang_coords(const EgnConfig* cfg, const float* xyz /*(m,3)*/, int64_t m,
+                           float* coords7 /*(m,7) normalised*/, void* stream);       /* coordinates.py:442-498 */
+int32_t egn_envmap_radiance(const EgnConfig* cfg, const float* emission, const float* dirs /*(n,3)*/, int64_t n,
+                            float* out /*(n,3)*/, void* stream);                     /* envmap.py:25-34 */
+int32_t egn_envmap_backward(const EgnConfig* cfg, const float* emission, const float* dirs, int64_t n,
+                            const float* d_out, float* d_emission, void* stream);
+
+/* ---- host helpers (no GPU): the two ladders, for callers that do not build them with torch ------ */
+int32_t egn_host_sample_schedule(float near_plane, float far_plane, float r0, int32_t n, float* z_out);   /* EgoNeRF.py:69-76 */
+int32_t egn_host_r_knots(float far_r, float r0, int32_t n_r, float* knots_out /*n_r+1*/);                  /* coordinates.py:118-124 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGN_H_ */
