@@ -118,9 +118,8 @@ extern "C" int64_t egn_workspace_bytes_eval(const EgnConfig* c, int64_t n) {
     return plan_ws(c, n).d_rgbs;
 }
 
-extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
-                                      int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
-                                      int64_t ray0, const EgnOutputs* out, void* workspace, void* stream) {
+static int check_render_args(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                             const EgnOutputs* out, const void* workspace) {
     if (validate(c, true)) return 1;
     if (!p || !tables || !rays || !out || !workspace) return fail("null argument");
     if (!out->rgb || !out->depth || !out->alpha) return fail("rgb/depth/alpha outputs are required");
@@ -129,6 +128,24 @@ extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, co
         for (int l = 0; l < 3; ++l)
             if (!p->mlp_w[l] || !p->mlp_b[l]) return fail("MLP weights missing");
     if (!p->basis[0] || !p->basis[1]) return fail("basis matrices missing");
+    return 0;
+}
+
+extern "C" int32_t egn_sample_rays(const EgnConfig* c, const float* tables, const float* rays, int64_t n, int32_t is_train,
+                                   const float* u_c, const float* u_f, uint64_t seed, int64_t ray0, float* z_out,
+                                   void* stream) {
+    if (validate(c, true)) return 1;
+    if (!tables || !rays || !z_out) return fail("null argument");
+    if (n <= 0) return 0;
+    EgnKernelCfg k = make_kcfg(c, tables);
+    int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z_out, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_sample_rays", e) : 0;
+}
+
+extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                      int64_t n, const float* z_vals, const EgnOutputs* out, void* workspace,
+                                      void* stream) {
+    if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     EgnKernelCfg k = make_kcfg(c, tables);
@@ -141,12 +158,23 @@ extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, co
     float* wgt = (float*)(base + w.wgt);
     float* bgw = (float*)(base + w.bgw);
     int e;
-    if ((e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z, st))) return cuda_fail("coarse", e);
+    if (z_vals && z_vals != z)
+        if ((e = (int)cudaMemcpyAsync(z, z_vals, sizeof(float) * n * k.S, cudaMemcpyDeviceToDevice, st))) return cuda_fail("z copy", e);
     if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
     if (c->shading <= EGN_SHADE_MLP)
         if ((e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st))) return cuda_fail("mlp", e);
     if ((e = egn_launch_composite(k, p, rays, n, z, fsig, feat, rgbs, out, wgt, bgw, st))) return cuda_fail("composite", e);
     return 0;
+}
+
+extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                      int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
+                                      int64_t ray0, const EgnOutputs* out, void* workspace, void* stream) {
+    if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
+    if (n <= 0) return 0;
+    float* z = (float*)((char*)workspace + plan_ws(c, n).z);
+    if (egn_sample_rays(c, tables, rays, n, is_train, u_c, u_f, seed, ray0, z, stream)) return 1;
+    return egn_render_samples(c, p, tables, rays, n, nullptr, out, workspace, stream);
 }
 
 extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
@@ -181,7 +209,8 @@ extern "C" int32_t egn_app_feature(const EgnConfig* c, const EgnParams* p, const
 }
 
 extern "C" int32_t egn_yinyang_coords(const EgnConfig* c, const float* xyz, int64_t m, float* coords7, void* stream) {
-    if (validate(c, false)) return 1;
+    if (!c) return fail("null config");
+    if (c->grid[0] < 4 || c->grid[0] > EGN_MAX_KNOTS) return fail("N_r=%d out of range", c->grid[0]);
     if (!xyz || !coords7 || !c->r_knots) return fail("null argument");
     if (m <= 0) return 0;
     EgnKernelCfg k = make_kcfg(c, nullptr);

@@ -35,7 +35,7 @@ class _VolumeRender(torch.autograd.Function):
     """EgoNeRF.forward (EgoNeRF.py:491-602) as one autograd node around egn_render_forward / egn_render_backward."""
 
     @staticmethod
-    def forward(ctx, model, opts, rays, u_coarse, u_fine, *params):
+    def forward(ctx, model, opts, rays, u_coarse, u_fine, z_vals, *params):
         lib = _lib.load()
         n = rays.shape[0]
         cfg = model._config(opts)
@@ -54,9 +54,15 @@ class _VolumeRender(torch.autograd.Function):
                               env.data_ptr() if has_env else None, alpha.data_ptr())
         P = model._params_struct()
         tables = model._render_tables()
-        _lib.check(lib.egn_render_forward(cfg, P, tables.data_ptr(), rays.data_ptr(), n, int(opts["is_train"]),
-                                          _lib.ptr(u_coarse), _lib.ptr(u_fine), int(opts["seed"]), int(opts["ray_index0"]),
-                                          out, ws.data_ptr(), _stream()))
+        if z_vals is not None:
+            if tuple(z_vals.shape) != (n, S):
+                raise ValueError(f"z_vals must be ({n}, {S})")
+            _lib.check(lib.egn_render_samples(cfg, P, tables.data_ptr(), rays.data_ptr(), n, z_vals.data_ptr(), out,
+                                              ws.data_ptr(), _stream()))
+        else:
+            _lib.check(lib.egn_render_forward(cfg, P, tables.data_ptr(), rays.data_ptr(), n, int(opts["is_train"]),
+                                              _lib.ptr(u_coarse), _lib.ptr(u_fine), int(opts["seed"]),
+                                              int(opts["ray_index0"]), out, ws.data_ptr(), _stream()))
         ctx.mark_non_differentiable(depth)
         if need_grad:
             ctx.model, ctx.opts, ctx.n = model, opts, n
@@ -90,7 +96,7 @@ class _VolumeRender(torch.autograd.Function):
                                            ws.data_ptr(), _lib.ptr(d_rgb), _lib.ptr(d_bg), _lib.ptr(d_env),
                                            _lib.ptr(d_alpha), d_tables.data_ptr(), G, _stream()))
         _lib.check(lib.egn_unpack_table_grads(cfg, d_tables.data_ptr(), G, _stream()))
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 class EgoNeRF(torch.nn.Module):
@@ -312,6 +318,23 @@ class EgoNeRF(torch.nn.Module):
             return F.softplus(density_features + self.density_shift)
         return F.relu(density_features)
 
+    def sample_depths(self, rays_chunk, is_train=False, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True,
+                      u_coarse=None, u_fine=None, seed=0, ray_index0=0):
+        """Sorted sample depths (N,S): sample_ray_exp + coarse pass + sample_pdf + sort (EgoNeRF.py:507-542)."""
+        _need_cuda(rays_chunk, "rays_chunk")
+        lib = _lib.load()
+        opts = dict(is_train=bool(is_train), n_coarse=n_coarse, n_fine=n_fine if resampling else 0,
+                    resampling=bool(resampling), use_coarse_sample=bool(use_coarse_sample))
+        cfg = self._config(opts)
+        rays = rays_chunk.detach().contiguous().float()
+        n, S = rays.shape[0], lib.egn_samples_per_ray(cfg)
+        z = torch.empty(n, S, device=rays.device)
+        uc = u_coarse.contiguous().float() if u_coarse is not None else None
+        uf = u_fine.contiguous().float() if u_fine is not None else None
+        _lib.check(lib.egn_sample_rays(cfg, self._render_tables().data_ptr(), rays.data_ptr(), n, int(is_train),
+                                       _lib.ptr(uc), _lib.ptr(uf), int(seed), int(ray_index0), z.data_ptr(), _stream()))
+        return z
+
     def _gather(self, coords_sampled, coarse=False, want_app=False):
         _need_cuda(coords_sampled, "coords_sampled")
         lib = _lib.load()
@@ -376,10 +399,12 @@ class EgoNeRF(torch.nn.Module):
     # ---- forward --------------------------------------------------------------------------------------
     def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, n_coarse=-1, n_fine=0,
                 exp_sampling=False, pretrain_envmap=False, pivotal_sample_th=0., resampling=False,
-                use_coarse_sample=True, interval_th=False, u_coarse=None, u_fine=None, seed=None, ray_index0=0):
+                use_coarse_sample=True, interval_th=False, u_coarse=None, u_fine=None, seed=None, ray_index0=0,
+                z_vals=None):
         """Same signature and return tuple as the reference (EgoNeRF.py:491-602).  Extra keyword-only extensions:
         `u_coarse` / `u_fine` inject the train-mode uniforms (reproducible parity tests), `seed` / `ray_index0` key
-        the in-kernel generator so that ray-sharded runs draw disjoint streams."""
+        the in-kernel generator so that ray-sharded runs draw disjoint streams, `z_vals` (N,S) supplies the sorted sample
+        depths and skips the sampler (the reference's sampler / renderer split)."""
         _need_cuda(rays_chunk, "rays_chunk")
         if pretrain_envmap:
             return self.envmap.get_radiance(rays_chunk[:, 3:6])
@@ -398,7 +423,8 @@ class EgoNeRF(torch.nn.Module):
                     ray_index0=ray_index0)
         uc = u_coarse.contiguous().float() if u_coarse is not None else None
         uf = u_fine.contiguous().float() if u_fine is not None else None
-        outs = _VolumeRender.apply(self, opts, rays, uc, uf, *self._param_list())
+        zv = z_vals.detach().contiguous().float() if z_vals is not None else None
+        outs = _VolumeRender.apply(self, opts, rays, uc, uf, zv, *self._param_list())
         if self.envmap is not None:
             rgb, depth, bg, env, alpha = outs
             return rgb, depth, bg, env, alpha

@@ -59,8 +59,14 @@ class Scene:
 def make_scene(n_voxels=128 ** 3, near_far=(0.01, 15.0), r0=0.03, density_shift=-8.0, distance_scale=25.0,
                sigma_std=0.7, app_std=0.1, n_lamb_sigma=(16, 16, 16), n_lamb_sh=(48, 48, 48), app_dim=27,
                shading='MLP_Fea', view_pe=2, fea_pe=2, featureC=128, envmap_h=None, traj_radius=0.5,
-               seed=20221028) -> Scene:
-    """aabb = ±(traj_radius + far) cube around the origin (dataset_omniblender.py:24-32)."""
+               seed=20221028, smooth=8) -> Scene:
+    """aabb = ±(traj_radius + far) cube around the origin (dataset_omniblender.py:24-32).
+
+    `smooth` = correlation length (texels) of the random factor fields: noise is drawn on a grid `smooth` times
+    coarser and bilinearly upsampled, then rescaled to the requested std.  smooth=1 gives white noise — a stress
+    case in which a 1e-4 shift of a sample depth already moves rgb by >1e-4 (the reference's own inverse-CDF
+    resampling is that sensitive to 1-ulp differences in exp(), see tests/test_gpu_parity.py); trained fields
+    are spatially coherent, which `smooth=8` imitates."""
     g = torch.Generator().manual_seed(seed)
     half = traj_radius + near_far[1]
     aabb = torch.tensor([[-half] * 3, [half] * 3], dtype=torch.float32)
@@ -68,7 +74,17 @@ def make_scene(n_voxels=128 ** 3, near_far=(0.01, 15.0), r0=0.03, density_shift=
     sd = OrderedDict()
 
     def rn(*shape, std):
-        return std * torch.randn(*shape, generator=g, dtype=torch.float32)
+        if smooth <= 1 or len(shape) != 4:
+            return std * torch.randn(*shape, generator=g, dtype=torch.float32)
+        _, c, hh, ww = shape
+        lo = torch.randn(1, c, -(-hh // smooth) + 1, (-(-ww // smooth) + 1) if ww > 1 else 1, generator=g,
+                         dtype=torch.float32)
+        if ww == 1:
+            lo = lo.expand(-1, -1, -1, 2)
+            f = torch.nn.functional.interpolate(lo, size=(hh, 2), mode='bilinear', align_corners=True)[..., :1]
+        else:
+            f = torch.nn.functional.interpolate(lo, size=(hh, ww), mode='bilinear', align_corners=True)
+        return (f * (std / f.std())).contiguous()
 
     def uni(*shape, bound):
         return (torch.rand(*shape, generator=g, dtype=torch.float32) * 2 - 1) * bound

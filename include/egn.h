@@ -138,6 +138,17 @@ int32_t egn_render_forward(const EgnConfig* cfg, const EgnParams* params, const 
                            const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
                            const EgnOutputs* out, void* workspace, void* stream);
 
+/* The two halves of egn_render_forward, for callers that keep the reference's sampler / renderer split:
+ *   egn_sample_rays    = sample_ray_exp + coarse density + raw2alpha + sample_pdf + sort  -> z_out (n,S) sorted depths
+ *                        (EgoNeRF.py:507-542)
+ *   egn_render_samples = everything after the depths are known (EgoNeRF.py:544-602); z_vals (n,S) is copied into
+ *                        the workspace (NULL: the workspace already holds the depths). */
+int32_t egn_sample_rays(const EgnConfig* cfg, const float* tables, const float* rays, int64_t n_rays, int32_t is_train,
+                        const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
+                        float* z_out, void* stream);
+int32_t egn_render_samples(const EgnConfig* cfg, const EgnParams* params, const float* tables, const float* rays,
+                           int64_t n_rays, const float* z_vals, const EgnOutputs* out, void* workspace, void* stream);
+
 /* Backward of the above w.r.t. every parameter that receives a gradient in the reference (SURVEY.md
  * Appendix A10): fine density/appearance planes+lines, both basis matrices, the MLP, the envmap —
  * through rgb, bg, env and alpha; not through depth, the coarse pass, coordinates or rays.

@@ -129,6 +129,15 @@ def main():
             u_f = torch.rand(N, 128)            # ray_utils.py:169
             torch.manual_seed(seed)
         store = dict(rays=rays, is_train=int(is_train), u_coarse=u_c, u_fine=u_f)
+        # the reference does not return its sorted sample depths (EgoNeRF.py:537): capture them from torch.sort
+        captured = []
+        real_sort = torch.sort
+
+        def spy_sort(*a, **k):
+            r = real_sort(*a, **k)
+            captured.append(r[0].detach().clone())
+            return r
+        torch.sort = spy_sort
         if grads:
             out = ref_render(model, rays, is_train, **kw)
             g2 = torch.Generator().manual_seed(seed + 1)
@@ -149,6 +158,9 @@ def main():
         else:
             with torch.no_grad():
                 out = ref_render(model, rays, is_train, **kw)
+        torch.sort = real_sort
+        if captured:
+            store["z_vals"] = captured[0]
         store.update(rgb=out[0], depth=out[1], bg=out[2], env=out[3], alpha=out[4],
                      checksum=sd_checksum(scene.state_dict))
         npz(name, **store)
@@ -166,6 +178,7 @@ def main():
     render_case("render_tiny_fineonly.npz", tiny, r64, False, use_coarse_sample=False)
     # BASELINE.json configs[1] / configs[2] shapes: scene regenerated from its seed, checksum pinned
     render_case("render_128_eval.npz", make_scene(n_voxels=128 ** 3), make_rays(256, 'isotropic', seed=31), False)
+    render_case("render_128_white_eval.npz", make_scene(n_voxels=128 ** 3, smooth=1), make_rays(256, 'isotropic', seed=34), False)
     render_case("render_300_eval.npz", make_scene(n_voxels=27e6), make_rays(128, 'isotropic', seed=32), False)
     render_case("render_300_train.npz", make_scene(n_voxels=27e6), make_rays(128, 'isotropic', seed=33), True)
     # other decoders that work through EgoNeRF.forward in the reference: MLP, RGB

@@ -21,6 +21,7 @@ RENDER_CASES = {
     "render_tiny_noresample": (TINY, dict(resampling=False, n_fine=0)),
     "render_tiny_fineonly": (TINY, dict(use_coarse_sample=False)),
     "render_128_eval": (dict(n_voxels=128 ** 3), {}),
+    "render_128_white_eval": (dict(n_voxels=128 ** 3, smooth=1), {}),
     "render_300_eval": (dict(n_voxels=27e6), {}),
     "render_300_train": (dict(n_voxels=27e6), {}),
     "render_tiny_mlp": (dict(n_voxels=40 ** 3, seed=9, shading='MLP'), {}),
