@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — rays/s of the EgoNeRF volume-rendering path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--mode render|train] [--impl reference]
+
+A "step" = one pass of the hot path (EgoNeRF.forward through the C ABI of libegn_b200; `--mode train` adds the backward
+pass and, for N > 1, the NCCL all-reduce of the gradients) over one batch of synthetic rays per GPU.  Rays shard
+across ranks with the parameters replicated (weak scaling: every rank renders `rays` rays per step).
+
+  value      device-resident throughput: rays already in HBM, CUDA events around exactly K steps, max over ranks
+  e2e        same metric through the public API (`renderer.volume_renderer`) from PINNED HOST rays: H2D of the rays
+             and D2H of the result (rgb + depth; loss in train mode) inside the timed region
+  roofline   dominant kernel, algorithmic bytes (SURVEY.md §8d tap model) / its CUDA-event duration, vs the measured
+             HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (port of the reference's algorithm, oracle/egn_oracle.py) on a bounded sample of the
+             same workload on this box's host cores (rank 0, N = 1 only)
+
+`--impl reference` times that CPU port alone (the reference itself is a Python program that cannot travel to the GPU
+box; the oracle is pinned to it by tests/golden).  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE.json configs restated as synthetic inputs
+WORKLOADS = {
+    "cfg1": dict(desc="synthetic 360 scene, 128^3 Yin-Yang grid [64,72,216], 4096 rays/batch", n_voxels=128 ** 3, rays=4096,
+                 scene={}),
+    "cfg2": dict(desc="OmniBlender-shape synthetic, 300^3 grid [150,172,516] VM-decomp, 65536 rays/batch", n_voxels=27e6,
+                 rays=65536, scene={}),
+    "cfg3": dict(desc="Ricoh360-shape synthetic, 300^3 grid + envmap h=1920, 16384 rays/GPU", n_voxels=27e6, rays=16384,
+                 scene=dict(near_far=(0.1, 300.), r0=0.05, density_shift=-10., envmap_h=1920)),
+}
+N_COARSE, N_FINE = 128, 128
+
+
+def algorithmic_bytes_per_ray(S, n_coarse, elem=4, env=False):
+    """SURVEY.md §8(d) tap model: every bilinear/linear tap reads C contiguous elements."""
+    io = 24 + 16 + 4 * S + (28 + 48 if env else 0)
+    return elem * (n_coarse * 288 + S * 1152) + io
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML; nvidia-smi as fallback)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        import torch
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = device.index or 0, [], set(), False, None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:        # CUDA_VISIBLE_DEVICES may renumber: resolve through the UUID
+                self.h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(device).uuid))
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        if self.h is not None:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        else:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                  "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip().split(",")
+            self.samples.append(int(out[0]))
+            self.max_mhz = int(out[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:]):
+                if v.strip() == "Active":
+                    self.reasons.add(name)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def oracle_rays_per_s(scene, n_rays, repeats, warmup, seed=5):
+    """CPU port of the reference path (checker code, used here only as the reported CPU baseline)."""
+    import torch
+    from oracle import egn_oracle as O
+    from egonerf_b200.synthetic import make_rays
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.OracleCfg(aabb=scene.aabb, grid=tuple(scene.grid), r0=scene.r0, near=scene.near_far[0], far=scene.near_far[1],
+                      density_shift=scene.density_shift, distance_scale=scene.distance_scale, n_coarse=N_COARSE,
+                      n_fine=N_FINE)
+    rays = make_rays(n_rays, 'isotropic', seed=seed)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            O.render(scene.state_dict, cfg, rays, False, emission=scene.emission)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return n_rays * len(times) / sum(times), sum(times) / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (default: the workload's batch)")
+    ap.add_argument("--mode", default="render", choices=["render", "train"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    n_rays = args.rays or wl["rays"]
+    S = N_COARSE + N_FINE
+    config = {"workload": wl["desc"], "rays_per_gpu_per_step": n_rays, "samples_per_ray": f"{N_COARSE} coarse + {S} fine",
+              "mode": args.mode, "sharding": f"rays x{world}, grid replicated", "l2": "inputs exceed L2 (factor tables "
+              "99 MB + >2 GB per-sample workspace streamed every step)"}
+    metric = "rays/sec (render)" if args.mode == "render" else "rays/sec (train step: fwd+bwd)"
+
+    import torch
+    from egonerf_b200.synthetic import make_scene, make_rays
+
+    # ---------------------------------------------------------------- reference arm: CPU port on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        scene = make_scene(n_voxels=wl["n_voxels"], **wl["scene"])
+        per_step = 512
+        rps, sec = oracle_rays_per_s(scene, per_step, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"{per_step} rays/step of the same scene, eval forward, torch CPU"},
+                "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from egonerf_b200 import _lib
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.renderer import volume_renderer
+    lib = _lib.load()
+
+    scene = make_scene(n_voxels=wl["n_voxels"], **wl["scene"])
+    model = model_from_scene(scene, dev)
+    rays_host = make_rays(n_rays, 'isotropic', seed=1000 + rank).pin_memory()
+    rays_dev = rays_host.to(dev)
+    ray0 = rank * n_rays
+    kw = dict(RENDER_KW)
+    train = args.mode == "train"
+    if train:
+        target = torch.rand(n_rays, 3, device=dev)
+        params = [p for p in model.parameters()] + ([model.envmap.emission] if model.envmap is not None else [])
+
+    def step_device():
+        if not train:
+            with torch.no_grad():
+                return model(rays_dev, is_train=False, ray_index0=ray0, **kw)[0]
+        for p in params:
+            p.grad = None
+        rgb = model(rays_dev, is_train=True, seed=1234, ray_index0=ray0, **kw)[0]
+        loss = torch.mean((rgb - target) ** 2)
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
+        model.update_coarse_sigma_grid()
+        return loss
+
+    out_rgb = torch.empty(n_rays, 3).pin_memory()
+    out_depth = torch.empty(n_rays).pin_memory()
+
+    def step_e2e():
+        if not train:
+            with torch.no_grad():
+                rgb, depth, _, _, _ = volume_renderer(rays_host, model, chunk=n_rays, is_train=False, device=dev, **kw)
+            out_rgb.copy_(rgb, non_blocking=True)
+            out_depth.copy_(depth, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return
+        for p in params:
+            p.grad = None
+        rgb = volume_renderer(rays_host, model, chunk=n_rays, is_train=True, device=dev, **kw)[0]
+        loss = torch.mean((rgb - target) ** 2)
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
+        model.update_coarse_sigma_grid()
+        loss.item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, clocks=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if clocks is not None:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # the volume_renderer mirror prints the reference's "elapsed time per image" line (renderer.py:75): keep stdout clean
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sampler = ClockSampler(dev)
+        ms = timed(step_device, args.steps, args.warmup, sampler)
+        clocks = sampler.result()
+        ms_e2e = timed(step_e2e, args.steps, 2)
+
+    total_rays = n_rays * world * args.steps
+    value = total_rays / (ms * 1e-3)
+    e2e_value = total_rays / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-stage CUDA-event times over the same workload (render stages) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    stage_names = ["sampler(coarse+cdf+sort)", "fine_gather+basis", "mlp_decode", "composite"]
+    stage_alg_bytes = [n_rays * (N_COARSE * 288 * 4 + 24 + 4 * S), n_rays * (S * 1152 * 4 + 4 * S),
+                       n_rays * S * (28 + 3) * 4, n_rays * (S * (4 + 4 + 12) + 16 + 4 * S)]
+    stage_ms = model.stage_times(rays_dev, repeats=max(3, min(args.steps, 10)), **kw)
+    dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
+    achieved = stage_alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "stage_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
+                "whole_path": {"bytes_per_ray": algorithmic_bytes_per_ray(S, N_COARSE, 4, scene.emission is not None),
+                               "achieved": value / world * algorithmic_bytes_per_ray(S, N_COARSE, 4, scene.emission is not None) / 1e9,
+                               "frac": value / world * algorithmic_bytes_per_ray(S, N_COARSE, 4, scene.emission is not None) / 1e9 / peak}}
+
+    line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
+                    "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world},
+            "gpu_launches": model.launches_per_forward() * args.steps * (1 if not train else 1) if not train
+            else model.launches_per_train_step() * args.steps,
+            "roofline": roofline}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            rps, _ = oracle_rays_per_s(scene, args.cpu_rays, 3, 1)
+            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{args.cpu_rays} rays of the same scene x 3 repeats, eval forward, "
+                                              f"torch CPU fp32 ({os.cpu_count()} threads)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

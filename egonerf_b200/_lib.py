@@ -61,6 +61,9 @@ PROTOTYPES = {
     "egn_render_forward": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64,
                                        C.POINTER(EgnOutputs), C.c_void_p, C.c_void_p]),
+    "egn_render_forward_timed": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p,
+                                             C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64,
+                                             C.POINTER(EgnOutputs), C.c_void_p, C.c_void_p, c_float_p]),
     "egn_sample_rays": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "egn_render_samples": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,

@@ -142,12 +142,13 @@ extern "C" int32_t egn_sample_rays(const EgnConfig* c, const float* tables, cons
     return e ? cuda_fail("egn_sample_rays", e) : 0;
 }
 
-extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
-                                      int64_t n, const float* z_vals, const EgnOutputs* out, void* workspace,
-                                      void* stream) {
-    if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
-    if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
+// stage boundaries recorded when a caller asks for per-stage device times (egn_render_forward_timed)
+struct StageEvents { cudaEvent_t ev[EGN_N_STAGES + 1]; bool on; };
+static inline void mark(StageEvents* se, int i, cudaStream_t st) { if (se && se->on) cudaEventRecord(se->ev[i], st); }
+
+static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays, int64_t n,
+                               const float* z_vals, const EgnOutputs* out, void* workspace, cudaStream_t st,
+                               StageEvents* se) {
     EgnKernelCfg k = make_kcfg(c, tables);
     WsPlan w = plan_ws(c, n);
     char* base = (char*)workspace;
@@ -160,11 +161,34 @@ extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, co
     int e;
     if (z_vals && z_vals != z)
         if ((e = (int)cudaMemcpyAsync(z, z_vals, sizeof(float) * n * k.S, cudaMemcpyDeviceToDevice, st))) return cuda_fail("z copy", e);
+    mark(se, 1, st);
     if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
+    mark(se, 2, st);
     if (c->shading <= EGN_SHADE_MLP)
         if ((e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st))) return cuda_fail("mlp", e);
+    mark(se, 3, st);
     if ((e = egn_launch_composite(k, p, rays, n, z, fsig, feat, rgbs, out, wgt, bgw, st))) return cuda_fail("composite", e);
+    mark(se, 4, st);
     return 0;
+}
+
+extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                      int64_t n, const float* z_vals, const EgnOutputs* out, void* workspace,
+                                      void* stream) {
+    if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
+    if (n <= 0) return 0;
+    return render_samples_impl(c, p, tables, rays, n, z_vals, out, workspace, (cudaStream_t)stream, nullptr);
+}
+
+static int render_forward_impl(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                               int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
+                               int64_t ray0, const EgnOutputs* out, void* workspace, cudaStream_t st, StageEvents* se) {
+    float* z = (float*)((char*)workspace + plan_ws(c, n).z);
+    EgnKernelCfg k = make_kcfg(c, tables);
+    mark(se, 0, st);
+    int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z, st);
+    if (e) return cuda_fail("egn_sample_rays", e);
+    return render_samples_impl(c, p, tables, rays, n, nullptr, out, workspace, st, se);
 }
 
 extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
@@ -172,9 +196,30 @@ extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, co
                                       int64_t ray0, const EgnOutputs* out, void* workspace, void* stream) {
     if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
     if (n <= 0) return 0;
-    float* z = (float*)((char*)workspace + plan_ws(c, n).z);
-    if (egn_sample_rays(c, tables, rays, n, is_train, u_c, u_f, seed, ray0, z, stream)) return 1;
-    return egn_render_samples(c, p, tables, rays, n, nullptr, out, workspace, stream);
+    return render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace,
+                               (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int32_t egn_render_forward_timed(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                            int64_t n, int32_t is_train, const float* u_c, const float* u_f,
+                                            uint64_t seed, int64_t ray0, const EgnOutputs* out, void* workspace,
+                                            void* stream, float* stage_ms) {
+    if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
+    if (!stage_ms) return fail("stage_ms is required");
+    for (int i = 0; i < EGN_N_STAGES; ++i) stage_ms[i] = 0.f;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    StageEvents se;
+    se.on = true;
+    for (int i = 0; i <= EGN_N_STAGES; ++i) cudaEventCreate(&se.ev[i]);
+    int rc = render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace, st, &se);
+    if (!rc) {
+        int e = (int)cudaEventSynchronize(se.ev[EGN_N_STAGES]);
+        if (e) rc = cuda_fail("egn_render_forward_timed", e);
+        else for (int i = 0; i < EGN_N_STAGES; ++i) cudaEventElapsedTime(&stage_ms[i], se.ev[i], se.ev[i + 1]);
+    }
+    for (int i = 0; i <= EGN_N_STAGES; ++i) cudaEventDestroy(se.ev[i]);
+    return rc;
 }
 
 extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,

@@ -396,6 +396,37 @@ class EgoNeRF(torch.nn.Module):
     def updateAlphaMask(self, gridSize=None):
         raise NotImplementedError("alpha-mask update is disabled in every shipped config (common.txt:13); SURVEY.md §8 f4")
 
+    # ---- measurement hooks (bench.py) ------------------------------------------------------------------
+    def launches_per_forward(self):
+        """Kernels of libegn_b200 launched by one `forward` (sampler, gather, [MLP], composite)."""
+        return 4 if isinstance(self.renderModule, torch.nn.Module) else 3
+
+    def stage_times(self, rays_chunk, repeats=3, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, **_):
+        """Mean device time (ms) of each stage of the eval forward, from CUDA events recorded between the launches
+        (egn_render_forward_timed)."""
+        _need_cuda(rays_chunk, "rays_chunk")
+        lib = _lib.load()
+        opts = dict(is_train=False, n_coarse=n_coarse, n_fine=n_fine if resampling else 0, resampling=bool(resampling),
+                    use_coarse_sample=bool(use_coarse_sample))
+        cfg = self._config(opts)
+        rays = rays_chunk.detach().contiguous().float()
+        n, S, dev = rays.shape[0], lib.egn_samples_per_ray(cfg), rays.device
+        has_env = cfg.env_h > 0
+        rgb, depth = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
+        alpha = torch.empty(n, S + (1 if has_env else 0), device=dev)
+        bg = torch.empty(n, 3, device=dev) if has_env else None
+        env = torch.empty(n, 3, device=dev) if has_env else None
+        ws = torch.empty(int(lib.egn_workspace_bytes_eval(cfg, n)), dtype=torch.uint8, device=dev)
+        out = _lib.EgnOutputs(rgb.data_ptr(), depth.data_ptr(), _lib.ptr(bg), _lib.ptr(env), alpha.data_ptr())
+        ms = (C.c_float * 4)()
+        tot = [0.0] * 4
+        P, tables = self._params_struct(), self._render_tables()
+        for _ in range(repeats):
+            _lib.check(lib.egn_render_forward_timed(cfg, P, tables.data_ptr(), rays.data_ptr(), n, 0, None, None, 0, 0,
+                                                    out, ws.data_ptr(), _stream(), ms))
+            tot = [a + b for a, b in zip(tot, ms)]
+        return [t / repeats for t in tot]
+
     # ---- forward --------------------------------------------------------------------------------------
     def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, n_coarse=-1, n_fine=0,
                 exp_sampling=False, pretrain_envmap=False, pivotal_sample_th=0., resampling=False,

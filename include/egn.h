@@ -138,6 +138,15 @@ int32_t egn_render_forward(const EgnConfig* cfg, const EgnParams* params, const 
                            const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
                            const EgnOutputs* out, void* workspace, void* stream);
 
+/* Same call with per-stage device times (CUDA events on `stream`; the call synchronises on the last one).
+ * stage_ms (host, EGN_N_STAGES floats): 0 sampler (coarse pass + inverse CDF + sort), 1 fine gather + basis,
+ * 2 colour decode (MLP), 3 compositing.  Used by bench.py for the roofline of the dominant kernel. */
+#define EGN_N_STAGES 4
+int32_t egn_render_forward_timed(const EgnConfig* cfg, const EgnParams* params, const float* tables,
+                                 const float* rays, int64_t n_rays, int32_t is_train,
+                                 const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
+                                 const EgnOutputs* out, void* workspace, void* stream, float* stage_ms /*host*/);
+
 /* The two halves of egn_render_forward, for callers that keep the reference's sampler / renderer split:
  *   egn_sample_rays    = sample_ray_exp + coarse density + raw2alpha + sample_pdf + sort  -> z_out (n,S) sorted depths
  *                        (EgoNeRF.py:507-542)

@@ -1,0 +1,121 @@
+"""CPU: the C-ABI library builds/loads, exports every symbol include/egn.h declares, validates its arguments without a
+GPU, and its host helpers reproduce the oracle's ladders.  No compute entry point is executed here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from egonerf_b200 import _lib
+from oracle import egn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.isfile(_lib.LIB_PATH):
+        from egonerf_b200.build import build
+        build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "egn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(egn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/egn.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype in egonerf_b200/_lib.py"
+    assert set(_lib.PROTOTYPES) <= set(names), "ctypes binds symbols the header does not declare"
+    assert lib.egn_abi_version() == _lib.ABI_VERSION
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def _cfg(**kw):
+    cfg = _lib.EgnConfig()
+    cfg.grid[:] = [20, 22, 64]
+    cfg.c_sigma, cfg.c_app, cfg.app_dim, cfg.shading = 16, 48, 27, 0
+    cfg.view_pe, cfg.fea_pe, cfg.feature_c = 2, 2, 128
+    cfg.n_coarse, cfg.n_fine, cfg.use_coarse_sample, cfg.resampling = 128, 128, 1, 1
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def test_sizes_and_validation(lib):
+    cfg = _cfg()
+    assert lib.egn_samples_per_ray(cfg) == 256
+    assert lib.egn_samples_per_ray(_cfg(use_coarse_sample=0)) == 128
+    assert lib.egn_samples_per_ray(_cfg(resampling=0)) == 128
+    nfl = lib.egn_table_floats(cfg)
+    G = [20, 22, 64]
+    fine = 2 * 64 * (G[0] * G[1] + G[0] * G[2] + G[1] * G[2] + sum(G))
+    coarse = 2 * 16 * (10 * 11 + 10 * 32 + 11 * 32 + 10 + 11 + 32)
+    assert fine + coarse <= nfl <= fine + coarse + 24 * 64          # sections padded to 256 B
+    assert lib.egn_workspace_bytes(cfg, 1000) > lib.egn_workspace_bytes_eval(cfg, 1000) > 0
+    # errors are reported through the status code + egn_last_error, never by crashing
+    assert lib.egn_table_floats(_cfg(c_sigma=8)) == -1
+    assert b"n_lamb_sigma" in lib.egn_last_error()
+    bad = _cfg(n_coarse=100)
+    z = (C.c_float * 4)()
+    assert lib.egn_sample_rays(bad, C.addressof(z), C.addressof(z), 1, 0, None, None, 0, 0, C.addressof(z), None) != 0
+    assert b"n_coarse" in lib.egn_last_error()
+    with pytest.raises(RuntimeError, match="libegn_b200"):
+        _lib.check(1)
+
+
+@pytest.mark.parametrize("near,far,r0,n", [(0.01, 15., 0.03, 128), (0.1, 300., 0.05, 128), (0.01, 15., 0.03, 256)])
+def test_host_sample_schedule_matches_oracle(lib, near, far, r0, n):
+    out = (C.c_float * n)()
+    assert lib.egn_host_sample_schedule(near, far, r0, n, out) == 0
+    ref = O.sample_schedule(near, far, r0, n).numpy()
+    assert np.abs(np.array(out) - ref).max() <= 4e-6 * ref.max()      # powf vs torch pow: <= a few ulp
+
+
+@pytest.mark.parametrize("half,r0,n_r", [(15.5, 0.03, 150), (15.5, 0.03, 64), (300.5, 0.05, 150)])
+def test_host_r_knots_matches_oracle(lib, half, r0, n_r):
+    aabb = torch.tensor([[-half] * 3, [half] * 3])
+    far_r = O.max_corner_radius(aabb)
+    out = (C.c_float * (n_r + 1))()
+    assert lib.egn_host_r_knots(float(far_r), r0, n_r, out) == 0
+    ref = O.r_reference_grid(far_r, r0, n_r).numpy()
+    assert np.abs(np.array(out) - ref).max() <= 4e-6 * ref.max()
+
+
+def test_python_mirror_ladders_are_bit_exact():
+    """The drop-in modules feed the kernels the ladders built by the host mirror: these must equal the oracle's."""
+    from egonerf_b200.models.coordinates import YinYangSphericalCoords, sample_schedule
+    for half, r0, nvox, nf in ((15.5, 0.03, 27e6, (0.01, 15.)), (300.5, 0.05, 27e6, (0.1, 300.)), (15.5, 0.03, 128 ** 3, (0.01, 15.))):
+        aabb = torch.tensor([[-half] * 3, [half] * 3])
+        co = YinYangSphericalCoords("cpu", aabb, exp_r=True, N_voxel=nvox, r0=r0, interval_th=True)
+        grid = O.yinyang_resolution(nvox)
+        assert [co.N_r, co.N_theta, co.N_phi] == grid
+        assert torch.equal(co.r_knots(), O.r_reference_grid(O.max_corner_radius(aabb), r0, grid[0]))
+        assert torch.equal(sample_schedule(nf[0], nf[1], r0, 128), O.sample_schedule(nf[0], nf[1], r0, 128))
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing somewhere else."""
+    from egonerf_b200.scene_io import model_from_scene
+    from egonerf_b200.synthetic import make_scene, make_rays
+    scene = make_scene(n_voxels=40 ** 3, seed=7)
+    model = model_from_scene(scene, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(make_rays(4), n_coarse=128, n_fine=128, exp_sampling=True, resampling=True)
+    import egonerf_b200
+    src = open(os.path.join(os.path.dirname(egonerf_b200.__file__), "models", "EgoNeRF.py")).read()
+    assert "oracle" not in src

@@ -1,0 +1,150 @@
+"""CPU: the oracle (oracle/egn_oracle.py) held to the frozen outputs of the UNMODIFIED reference (tests/golden/*.npz,
+made by oracle/make_golden.py).  This is the parity pin of the oracle — the reference ships no tests of its own.
+
+Tolerances: the oracle is an independent fp32 restatement (explicit taps instead of F.grid_sample, gathers instead of
+boolean-mask compaction), so sums are associated differently: 2e-6 on O(1) quantities, 1e-5 on rgb after 256-term sums.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import egn_oracle as O
+from tests.helpers import RENDER_CASES, T, checksum, load_golden, oracle_cfg, scene_for, stable_rays
+
+FAST = [n for n in RENDER_CASES if "tiny" in n]
+SLOW = [n for n in RENDER_CASES if "tiny" not in n]
+
+
+@pytest.mark.parametrize("tag", ["indoor300", "indoor128", "outdoor300"])
+def test_schedule_and_coordinates(tag):
+    g = load_golden("kat_coords_" + tag)
+    aabb, r0 = T(g["aabb"]), float(g["r0"])
+    near, far = [float(x) for x in g["near_far"]]
+    grid = g["grid"].tolist()
+    nvox = {"indoor300": 27e6, "indoor128": 128 ** 3, "outdoor300": 27e6}[tag]
+    assert O.yinyang_resolution(nvox) == grid
+    far_r = O.max_corner_radius(aabb)
+    assert float(far_r) == float(g["far_r"])
+    z = near + O.sample_schedule(near, far, r0, 128)
+    assert np.array_equal(z.numpy(), g["z_coarse"]), "sample schedule must be bit-exact (EgoNeRF.py:68-76)"
+    knots = O.r_reference_grid(far_r, r0, grid[0])
+    pts = T(g["points"])
+    r, a, b, is_yang, _ = O.cart_to_yinyang(pts, O.scene_center(aabb))
+    ref_u, ref_n = g["unnormalized"], g["normalized"]
+    assert np.array_equal(is_yang.numpy(), ref_u[:, 6] != 0)
+    col = np.where(is_yang.numpy(), 3, 0)
+    rows = np.arange(len(col))
+    assert np.array_equal(r.numpy(), ref_u[rows, col])
+    assert np.array_equal(a.numpy(), ref_u[rows, col + 1])
+    assert np.array_equal(b.numpy(), ref_u[rows, col + 2])
+    an, bn = O.normalize_angles(a, b)
+    rn = O.normalize_radius(r, knots)
+    assert np.abs(rn.numpy() - ref_n[rows, col]).max() <= 2e-7
+    assert np.array_equal(an.numpy(), ref_n[rows, col + 1])
+    assert np.array_equal(bn.numpy(), ref_n[rows, col + 2])
+
+
+def test_known_answer_values():
+    """SURVEY.md §8c KATs (aabb = ±15.5 cube, N_voxel 27e6, r0 .03, interval_th)."""
+    aabb = torch.tensor([[-15.5] * 3, [15.5] * 3])
+    far_r = O.max_corner_radius(aabb)
+    assert abs(float(far_r) - 26.84678840637207) < 1e-6
+    r = O.sample_schedule(0.01, 15., 0.03, 128)
+    z = 0.01 + r
+    assert np.allclose(z[:4].numpy(), [.01, .04, .07, .10], atol=1e-7)
+    assert np.allclose(z[-4:].numpy(), [13.6022606, 14.2203226, 14.8693781, 15.5509796], atol=2e-6)
+    knots = O.r_reference_grid(far_r, 0.03, 150)
+    iv = knots[1:] - knots[:-1]
+    assert int((torch.abs(iv - 0.03) < 1e-6).sum()) == 69
+    c, yang, _ = O._coords(torch.tensor([[.3, -.2, .1], [-5., .5, 7.], [10., 10., 10.]]), O.scene_center(aabb), knots)
+    assert np.allclose(c[0].numpy(), [-0.8337041, -0.3444746, -0.2495561], atol=2e-6) and not yang[0]
+    assert np.allclose(c[1].numpy(), [0.6158372, -0.0739223, 0.4034245], atol=2e-6) and yang[1]
+    assert np.allclose(c[2].numpy(), [0.8471348, -0.7836531, 0.3333334], atol=2e-6) and not yang[2]
+
+
+def test_operators():
+    g = load_golden("ops_small")
+    scene = scene_for(dict(n_voxels=40 ** 3, seed=7))
+    assert np.allclose(checksum(scene.state_dict), g["checksum"], rtol=1e-6)
+    sd = dict(scene.state_dict)
+    c7 = T(g["coords7"])
+    yang = c7[:, 6] != 0
+    c3 = torch.where(yang[:, None], c7[:, 3:6], c7[:, 0:3])
+    assert np.abs(O.density_feature(sd, c3, yang).numpy() - g["sigma_feature"]).max() <= 1e-5
+    sd.update(O.avg_pool_factors(sd))
+    assert np.abs(O.density_feature(sd, c3, yang, coarse=True).numpy() - g["coarse_sigma_feature"]).max() <= 1e-5
+    app = O.app_feature(sd, c3, yang)
+    assert np.abs(app.numpy() - g["app_feature"]).max() <= 1e-5
+    rgb = O.decode_color(sd, oracle_cfg(scene), T(g["app_feature"]), T(g["dirs"]))
+    assert np.abs(rgb.numpy() - g["rgb"]).max() <= 2e-6
+
+
+def test_composite_and_inverse_cdf():
+    g = load_golden("composite_pdf")
+    a, w, bg = O.alpha_composite_weights(T(g["sigma"]), T(g["dist"]))
+    assert np.array_equal(a.numpy(), g["alpha"])
+    assert np.abs(w.numpy() - g["weight"]).max() <= 1e-7 and np.abs(bg.numpy() - g["bg"]).max() <= 1e-7
+    bins, wgt = T(g["bins"]), T(g["weight"])[:, 1:-1]
+    ze, _ = O.inverse_cdf(bins, wgt, torch.linspace(0., 1., 128).expand(16, 128))
+    zt, _ = O.inverse_cdf(bins, wgt, T(g["u_train"]))
+    assert np.abs(ze.numpy() - g["fine_eval"]).max() <= 1e-5
+    assert np.abs(zt.numpy() - g["fine_train"]).max() <= 1e-5
+
+
+def _run_case(name):
+    skw, okw = RENDER_CASES[name]
+    g = load_golden(name)
+    scene = scene_for(skw)
+    assert np.allclose(checksum(scene.state_dict), g["checksum"], rtol=1e-6), "synthetic scene drifted from the fixture"
+    rays = T(g["rays"])
+    is_train = bool(g["is_train"])
+    u_c = T(g["u_coarse"]) if "u_coarse" in g else None
+    u_f = T(g["u_fine"]) if "u_fine" in g else None
+    cfg = oracle_cfg(scene, **okw)
+    with torch.no_grad():
+        out = O.render(scene.state_dict, cfg, rays, is_train, u_c, u_f, emission=scene.emission)
+    e_rgb = np.abs(out[0].numpy() - g["rgb"]).max()
+    e_dep = np.abs(out[1].numpy() - g["depth"]).max()
+    assert out[4].shape == g["alpha"].shape
+    print(f"{name}: oracle vs reference rgb {e_rgb:.2e} depth {e_dep:.2e}")
+    assert e_rgb <= 1e-5
+    assert e_dep <= 1e-4 * scene.near_far[1]
+    if "bg" in g:
+        assert np.abs(out[2].numpy() - g["bg"]).max() <= 1e-5
+        assert np.abs(out[3].numpy() - g["env"]).max() <= 2e-6
+    else:
+        assert out[2] is None and out[3] is None
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_render_tiny(name):
+    _run_case(name)
+
+
+@pytest.mark.parametrize("name", SLOW)
+def test_render_baseline_shapes(name):
+    _run_case(name)
+
+
+@pytest.mark.parametrize("name", ["render_tiny_train_grad", "render_tiny_env_train_grad"])
+def test_gradients(name):
+    """autograd through the oracle against the reference's own .grad (all 38/39 parameter tensors)."""
+    skw, okw = RENDER_CASES[name]
+    g = load_golden(name)
+    scene = scene_for(skw)
+    sd = {k: v.clone().requires_grad_(True) for k, v in scene.state_dict.items()}
+    em = scene.emission.clone().requires_grad_(True) if scene.emission is not None else None
+    out = O.render(sd, oracle_cfg(scene, **okw), T(g["rays"]), True, T(g["u_coarse"]), T(g["u_fine"]), emission=em)
+    loss = (out[0] * T(g["w_rgb"])).sum() + (out[4] * T(g["w_alpha"])).sum()
+    if em is not None:
+        loss = loss + (out[2] * T(g["w_bg"])).sum() + (out[3] * T(g["w_env"])).sum()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * max(1., abs(float(g["loss"])))
+    for k, v in sd.items():
+        ref = g["grad:" + k]
+        got = v.grad.numpy() if v.grad is not None else np.zeros_like(ref)
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= 2e-4 * scale, k
+    if em is not None:
+        ref = g["grad:envmap.emission"]
+        assert np.abs(em.grad.numpy() - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-6)
