@@ -293,8 +293,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
                     "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world},
-            "gpu_launches": model.launches_per_forward() * args.steps * (1 if not train else 1) if not train
-            else model.launches_per_train_step() * args.steps,
+            "gpu_launches": (model.launches_per_forward() if not train else model.launches_per_train_step(n_rays)) * args.steps,
             "roofline": roofline}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

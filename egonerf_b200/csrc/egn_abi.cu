@@ -94,17 +94,22 @@ extern "C" int32_t egn_unpack_table_grads(const EgnConfig* c, const float* d_tab
 
 // ---- workspace ----------------------------------------------------------------------------------
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
-struct WsPlan { long long z, fsig, feat, rgbs, wgt, bgw, h1, h2, d_rgbs, d_fsig, d_feat, dz1, dz2, total; };
+// backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
+#define EGN_BWD_SUB_RAYS 4096
+struct WsPlan { long long z, fsig, feat, rgbs, wgt, bgw, rgbpre, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, total; };
 static WsPlan plan_ws(const EgnConfig* c, long long n) {
-    const long long M = n * egn_samples_per_ray(c);
+    const long long S = egn_samples_per_ray(c);
+    const long long M = n * S;
     WsPlan w;
     long long off = 0;
     auto take = [&](long long floats) { long long o = off; off += align256(floats * 4); return o; };
     w.z = take(M); w.fsig = take(M); w.feat = take(M * EGN_FEAT_STRIDE); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n);
+    w.rgbpre = take(n * 3);
     w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
     const bool mlp = c->shading <= EGN_SHADE_MLP;
-    w.h1 = take(mlp ? M * EGN_HID : 0); w.h2 = take(mlp ? M * EGN_HID : 0);
-    w.dz1 = take(mlp ? M * EGN_HID : 0); w.dz2 = take(mlp ? M * EGN_HID : 0);
+    const long long Ms = (n < EGN_BWD_SUB_RAYS ? n : EGN_BWD_SUB_RAYS) * S;
+    w.h1 = take(mlp ? Ms * EGN_HID : 0); w.h2 = take(mlp ? Ms * EGN_HID : 0);
+    w.dz1 = take(mlp ? Ms * EGN_HID : 0); w.dz2 = take(mlp ? Ms * EGN_HID : 0);
     w.total = off;
     return w;
 }
@@ -158,6 +163,7 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     float* rgbs = (float*)(base + w.rgbs);
     float* wgt = (float*)(base + w.wgt);
     float* bgw = (float*)(base + w.bgw);
+    float* rgbpre = (float*)(base + w.rgbpre);
     int e;
     if (z_vals && z_vals != z)
         if ((e = (int)cudaMemcpyAsync(z, z_vals, sizeof(float) * n * k.S, cudaMemcpyDeviceToDevice, st))) return cuda_fail("z copy", e);
@@ -167,7 +173,7 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     if (c->shading <= EGN_SHADE_MLP)
         if ((e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st))) return cuda_fail("mlp", e);
     mark(se, 3, st);
-    if ((e = egn_launch_composite(k, p, rays, n, z, fsig, feat, rgbs, out, wgt, bgw, st))) return cuda_fail("composite", e);
+    if ((e = egn_launch_composite(k, p, rays, n, z, fsig, feat, rgbs, out, wgt, bgw, rgbpre, st))) return cuda_fail("composite", e);
     mark(se, 4, st);
     return 0;
 }
@@ -226,9 +232,42 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
                                        int64_t n, const void* workspace, const float* d_rgb, const float* d_bg,
                                        const float* d_env, const float* d_alpha, float* d_tables, const EgnGrads* g,
                                        void* stream) {
-    (void)c; (void)p; (void)tables; (void)rays; (void)n; (void)workspace; (void)d_rgb; (void)d_bg; (void)d_env;
-    (void)d_alpha; (void)d_tables; (void)g; (void)stream;
-    return fail("egn_render_backward: not built yet");
+    if (validate(c, true)) return 1;
+    if (!p || !tables || !rays || !workspace || !d_tables || !g) return fail("null argument");
+    if (!g->basis[0] || !g->basis[1]) return fail("basis gradient buffers missing");
+    const bool mlp = c->shading <= EGN_SHADE_MLP;
+    if (mlp)
+        for (int l = 0; l < 3; ++l)
+            if (!p->mlp_w[l] || !p->mlp_b[l] || !g->mlp_w[l] || !g->mlp_b[l]) return fail("MLP weights / gradient buffers missing");
+    if (c->env_h > 0 && (!p->emission || !g->emission)) return fail("envmap configured but emission / its gradient missing");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    EgnKernelCfg k = make_kcfg(c, tables);
+    WsPlan w = plan_ws(c, n);
+    char* base = (char*)workspace;
+    const float* z = (const float*)(base + w.z);
+    const float* fsig = (const float*)(base + w.fsig);
+    const float* feat = (const float*)(base + w.feat);
+    const float* rgbs = (const float*)(base + w.rgbs);
+    const float* rgbpre = (const float*)(base + w.rgbpre);
+    float* d_rgbs = (float*)(base + w.d_rgbs);
+    float* d_fsig = (float*)(base + w.d_fsig);
+    float* d_feat = (float*)(base + w.d_feat);
+    int e;
+    if ((e = egn_launch_composite_bwd(k, p, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs,
+                                      d_fsig, d_feat, g->emission, st))) return cuda_fail("composite backward", e);
+    if (mlp) {
+        float* h1 = (float*)(base + w.h1); float* h2 = (float*)(base + w.h2);
+        float* dz1 = (float*)(base + w.dz1); float* dz2 = (float*)(base + w.dz2);
+        for (long long r0 = 0; r0 < n; r0 += EGN_BWD_SUB_RAYS) {
+            const long long ns = (n - r0 < EGN_BWD_SUB_RAYS) ? (n - r0) : EGN_BWD_SUB_RAYS;
+            const long long m0 = r0 * k.S;
+            if ((e = egn_launch_mlp_bwd(k, p, rays + r0 * 6, ns, feat + m0 * EGN_FEAT_STRIDE, rgbs + m0 * 3, d_rgbs + m0 * 3,
+                                        d_feat + m0 * EGN_FEAT_STRIDE, h1, h2, dz1, dz2, g, st))) return cuda_fail("mlp backward", e);
+        }
+    }
+    if ((e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st))) return cuda_fail("gather backward", e);
+    return 0;
 }
 
 // ---- stand-alone operators ---------------------------------------------------------------------------

@@ -1,0 +1,374 @@
+// Backward kernels of the render path (sm_100a): gradients w.r.t. every parameter that receives one in the reference
+//  — fine density / appearance planes + lines, both basis matrices, the envmap — through rgb,
+// bg, env and alpha.  Nothing flows through depth (no_grad, EgoNeRF.py:595), the coarse pass (detached resampling,
+// :534), the coordinates (detach, :247,255) or the rays.
+//   egn_composite_bwd_kernel  d(rgb, bg, env, alpha) -> d(sample colour), d(sigma feature), d(envmap)
+//   egn_gather_bwd_kernel     d(sigma feature), d(app feature) -> d(render tables) [vector atomics], d(basis)
+// The MLP backward lives in egn_mlp_bwd.cu.
+#include "egn_device.cuh"
+#include "egn_host.h"
+#include "egn_shared.cuh"
+
+// =================================================================================================
+// Compositing backward.  One warp per ray, lane owns S/32 consecutive samples (same partition as the forward).
+//   w_j = a_j T_j,  T_{j+1} = T_j m_j,  m_j = 1 - a_j + 1e-10,  bgw = T_S        (tensorBase.py:22-27)
+//   dL/da_j = dw_j T_j + dalpha_j - R_j / m_j,   R_j = sum_{i>j} dw_i w_i + dbgw T_S
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ emission,
+                         const float* __restrict__ rays, long long n, const float* __restrict__ zs,
+                         const float* __restrict__ fsig, const float* __restrict__ feat, const float* __restrict__ rgbs,
+                         const float* __restrict__ rgbpre, const float* __restrict__ d_rgb, const float* __restrict__ d_bg,
+                         const float* __restrict__ d_env, const float* __restrict__ d_alpha, float* __restrict__ d_rgbs,
+                         float* __restrict__ d_fsig, float* __restrict__ d_feat, float* __restrict__ d_emission) {
+    const int lane = threadIdx.x & 31;
+    const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n) return;
+    const int S = k.S, cnt = S >> 5;
+    const float dx = rays[ray * 6 + 3], dy = rays[ray * 6 + 4], dz = rays[ray * 6 + 5];
+    float sh[9];
+    if (k.shading == EGN_SHADE_SH) egn_sh_basis(dx, dy, dz, sh);
+    const long long base = ray * S;
+    const int acols = S + (k.env_h > 0 ? 1 : 0);
+    // upstream gradient of the unclamped colour: torch.clamp passes the gradient where min <= x <= max (EgoNeRF.py:593)
+    float g[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float pre = rgbpre[ray * 3 + ch];
+        g[ch] = (d_rgb && pre >= 0.f && pre <= 1.f) ? d_rgb[ray * 3 + ch] : 0.f;
+    }
+    float a_loc[K4_MAXE], m_loc[K4_MAXE], k_loc[K4_MAXE], dw_loc[K4_MAXE], T_loc[K4_MAXE];
+    float prodl = 1.f;
+#pragma unroll
+    for (int q = 0; q < K4_MAXE; ++q) {
+        if (q < cnt) {
+            const int j = lane * cnt + q;
+            const float zj = zs[base + j];
+            const float dist = ((j + 1 < S) ? (zs[base + j + 1] - zj) : (zj - zs[base + j - 1])) * k.distance_scale;
+            const float f = fsig[base + j];
+            const float sigma = egn_density_act(f, k.density_shift, k.fea2dense);
+            const float e = expf(-sigma * dist);
+            const float alpha = 1.f - e;
+            a_loc[q] = alpha;
+            m_loc[q] = 1.f - alpha + 1e-10f;
+            float dact;                                        // d sigma / d f
+            if (k.fea2dense == EGN_ACT_SOFTPLUS) {
+                const float x = f + k.density_shift;
+                dact = x > 20.f ? 1.f : egn_sigmoid(x);
+            } else {
+                dact = f > 0.f ? 1.f : 0.f;
+            }
+            k_loc[q] = e * dist * dact;                        // d alpha / d f
+            prodl *= m_loc[q];
+        }
+    }
+    float incl = prodl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl *= o;
+    }
+    float T = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) T = 1.f;
+    const float Tend = __shfl_sync(FULL, incl, 31);
+    // envmap: rgb += bgw * env; bg = bgw * env; env is an output too (EgoNeRF.py:586-590)
+    float dbgw = 0.f;
+    if (k.env_h > 0) {
+        float e[3];
+        egn_env_radiance(emission, k.env_h, dx, dy, dz, e);
+        float de[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float gb = g[ch] + (d_bg ? d_bg[ray * 3 + ch] : 0.f);
+            dbgw = fmaf(gb, e[ch], dbgw);
+            de[ch] = gb * Tend + (d_env ? d_env[ray * 3 + ch] : 0.f);
+        }
+        if (lane == 0 && d_emission) {
+            const EnvTap t = egn_env_tap(dx, dy, dz, k.env_h);
+            const int W = k.env_h, H = 2 * k.env_h;
+            const float w[4] = {(1.f - t.fx) * (1.f - t.fy), t.fx * (1.f - t.fy), (1.f - t.fx) * t.fy, t.fx * t.fy};
+            for (int ch = 0; ch < 3; ++ch) {
+                const float gg = de[ch] * e[ch] * (1.f - e[ch]);
+                for (int q = 0; q < 4; ++q) {
+                    const int x = t.x0 + (q & 1), y = t.y0 + (q >> 1);
+                    if (x >= 0 && x < W && y >= 0 && y < H) atomicAdd(d_emission + ((long long)ch * H + y) * W + x, w[q] * gg);
+                }
+            }
+        }
+    }
+    // forward walk: weights, d(colour), lane-local sum of dw * w
+    float sl = 0.f;
+#pragma unroll
+    for (int q = 0; q < K4_MAXE; ++q) {
+        if (q < cnt) {
+            const int j = lane * cnt + q;
+            const long long m = base + j;
+            const float w = a_loc[q] * T;
+            T_loc[q] = T;
+            T *= m_loc[q];
+            float c[3];
+            egn_sample_color(k, feat, rgbs, m, sh, c);
+            const float dw = g[0] * c[0] + g[1] * c[1] + g[2] * c[2];
+            dw_loc[q] = dw;
+            sl = fmaf(dw, w, sl);
+            if (k.shading == EGN_SHADE_RGB) {
+                d_feat[m * EGN_FEAT_STRIDE] = w * g[0]; d_feat[m * EGN_FEAT_STRIDE + 1] = w * g[1];
+                d_feat[m * EGN_FEAT_STRIDE + 2] = w * g[2];
+                for (int b = 3; b < EGN_FEAT_STRIDE; ++b) d_feat[m * EGN_FEAT_STRIDE + b] = 0.f;
+            } else if (k.shading == EGN_SHADE_SH) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float da = (c[ch] > 0.f) ? w * g[ch] : 0.f;      // relu(a + 0.5)
+#pragma unroll
+                    for (int b = 0; b < 9; ++b) d_feat[m * EGN_FEAT_STRIDE + ch * 9 + b] = sh[b] * da;
+                }
+                d_feat[m * EGN_FEAT_STRIDE + 27] = 0.f;
+            } else {
+                d_rgbs[m * 3] = w * g[0]; d_rgbs[m * 3 + 1] = w * g[1]; d_rgbs[m * 3 + 2] = w * g[2];
+            }
+        }
+    }
+    // exclusive suffix over lanes
+    float suf = sl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float o = __shfl_down_sync(FULL, suf, d);
+        if (lane + d < 32) suf += o;
+    }
+    float R = suf - sl + dbgw * Tend;
+#pragma unroll
+    for (int q = K4_MAXE - 1; q >= 0; --q) {
+        if (q < cnt) {
+            const int j = lane * cnt + q;
+            const float da = dw_loc[q] * T_loc[q] + (d_alpha ? d_alpha[ray * acols + j] : 0.f) - R / m_loc[q];
+            d_fsig[base + j] = da * k_loc[q];
+            R = fmaf(dw_loc[q], a_loc[q] * T_loc[q], R);
+        }
+    }
+}
+
+int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                             const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,
+                             const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
+                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, cudaStream_t st) {
+    long long threads = n * 32;
+    egn_composite_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        k, p->emission, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs, d_fsig, d_feat, d_emission);
+    return (int)cudaGetLastError();
+}
+
+// =================================================================================================
+// Gather backward.  Mirrors egn_gather_kernel: a warp handles 16 samples per round, a half-warp (16 lanes x float4 =
+// the 64 interleaved channels of one texel) handles one sample at a time.  Per sample the taps are gathered again
+// (recompute instead of saving 1152 values), dv = B_h^T dfeat is formed from the basis in shared memory, and
+// d(plane) = dv * L, d(line) = dv * P are scattered with 128-bit vector reductions into the table-layout gradient.
+// d(basis) needs a reduction over all samples: every round the 256 samples of the CTA stage v = P*L in shared memory and
+// all 512 threads accumulate a fixed 4 x 2 tile of d(basis_yin) and d(basis_yang) in registers.
+// =================================================================================================
+#define GB_WARPS 16
+#define GB_VT 148
+#define GB_K (3 * EGN_CA)
+
+struct GbSmem {
+    float Bo[2][EGN_FEAT_STRIDE][GB_K];       // basis, output-major (the weight's own layout), rows >= app_dim zero
+    float vt[GB_WARPS][16][GB_VT];            // v = P * L of the round's samples
+    float df[GB_WARPS][16][EGN_FEAT_STRIDE];  // d(app feature) of the round's samples
+    int yang[GB_WARPS][16];                   // hemisphere of each sample, -1 = no sample
+    float knots[EGN_MAX_KNOTS + 1];
+};
+
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+    atomicAdd(reinterpret_cast<float4*>(addr), v);           // red.global.add.v4.f32 on sm_90+
+}
+__device__ __forceinline__ float4 f4scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+
+__global__ void __launch_bounds__(GB_WARPS * 32, 1)
+egn_gather_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
+                      const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
+                      const float* __restrict__ zs, const float* __restrict__ d_fsig, const float* __restrict__ d_feat,
+                      float* __restrict__ d_tab, float* __restrict__ d_basis0, float* __restrict__ d_basis1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GbSmem& sm = *reinterpret_cast<GbSmem*>(smem_raw);
+    for (int i = threadIdx.x; i < 2 * EGN_FEAT_STRIDE * GB_K; i += blockDim.x) {
+        const int h = i / (EGN_FEAT_STRIDE * GB_K), o = (i / GB_K) % EGN_FEAT_STRIDE, kk = i % GB_K;
+        const float* B = h ? basis1 : basis0;
+        sm.Bo[h][o][kk] = (o < k.app_dim) ? B[o * GB_K + kk] : 0.f;
+    }
+    for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) sm.knots[i] = k.r_knots[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane & 15;
+    float(*vt)[GB_VT] = sm.vt[warp];
+    float(*df)[EGN_FEAT_STRIDE] = sm.df[warp];
+    // d(basis) tile of this thread: outputs 4*og .. 4*og+3, inputs 2*kp, 2*kp+1 (both hemispheres)
+    const int og = threadIdx.x / (GB_K / 2), kp = threadIdx.x % (GB_K / 2);
+    const bool has_tile = og < EGN_FEAT_STRIDE / 4;
+    float accB[2][4][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) accB[h][a][0] = accB[h][a][1] = 0.f;
+
+    const long long rounds = (M + 15) / 16;
+    const long long cta_rounds = (rounds + GB_WARPS - 1) / GB_WARPS;
+    for (long long cr = blockIdx.x; cr < cta_rounds; cr += gridDim.x) {
+        const long long r = cr * GB_WARPS + warp;
+        // ---- a. coordinates, upstream gradients of the warp's 16 samples ----
+        const long long m = r * 16 + (lane & 15);
+        YYCoord cc;
+        cc.c[0] = cc.c[1] = cc.c[2] = -3.f;
+        cc.yang = 0;
+        float dfs = 0.f;
+        const bool live = (r < rounds) && (m < M);
+        if (live) {
+            const long long ray = m / k.S;
+            const float z = zs[m];
+            const float* ry = rays + ray * 6;
+            cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, sm.knots);
+            dfs = d_fsig[m];
+        }
+        if (lane < 16) sm.yang[warp][lane] = live ? cc.yang : -1;
+        for (int i = lane; i < 16 * (EGN_FEAT_STRIDE / 4); i += 32) {          // 16 x 28 floats, float4 granules
+            const int s = i / (EGN_FEAT_STRIDE / 4), q = i % (EGN_FEAT_STRIDE / 4);
+            const long long mm = r * 16 + s;
+            float4 v = f4zero();
+            if (r < rounds && mm < M) v = *reinterpret_cast<const float4*>(d_feat + mm * EGN_FEAT_STRIDE + q * 4);
+            *reinterpret_cast<float4*>(&df[s][q * 4]) = v;
+        }
+        __syncwarp();
+        // ---- b. per sample pair: regather, local gradients, scatter ----
+        for (int it = 0; it < 8; ++it) {
+            const int src = 2 * it + (lane >> 4);
+            float c[3];
+            c[0] = __shfl_sync(FULL, cc.c[0], src);
+            c[1] = __shfl_sync(FULL, cc.c[1], src);
+            c[2] = __shfl_sync(FULL, cc.c[2], src);
+            const int yang = __shfl_sync(FULL, cc.yang, src);
+            const float dsig = __shfl_sync(FULL, dfs, src);
+            int i0[3];
+            float fr[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float ix = egn_unnorm(c[a], k.lay.G[a]);
+                float fl = floorf(ix);
+                fr[a] = ix - fl;
+                i0[a] = (int)fminf(fmaxf(fl, -2.f), (float)k.lay.G[a] + 1.f);
+            }
+            // dv for this lane's 4 channels of each of the 3 products
+            float4 dv[3] = {f4zero(), f4zero(), f4zero()};
+            if (sub >= EGN_CS / 4) {
+                const int kc = (sub - EGN_CS / 4) * 4;
+#pragma unroll 3
+                for (int o = 0; o < EGN_FEAT_STRIDE - 1; ++o) {
+                    const float x = df[src][o];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float4 b = *reinterpret_cast<const float4*>(&sm.Bo[yang][o][i * EGN_CA + kc]);
+                        dv[i] = f4fma(x, b, dv[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+                const int W = k.lay.G[ax], H = k.lay.G[ay], L = k.lay.G[al];
+                const int x0 = i0[ax], y0 = i0[ay], q0 = i0[al];
+                const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+                const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
+                const bool vq0 = (q0 >= 0) & (q0 < L), vq1 = (q0 + 1 >= 0) & (q0 + 1 < L);
+                const long long po = k.lay.pf[yang][i] + ((long long)y0 * W + x0) * EGN_CF + sub * 4;
+                const long long lo = k.lay.lf[yang][i] + (long long)q0 * EGN_CF + sub * 4;
+                const float* pb = k.tables + po;
+                const float* lb = k.tables + lo;
+                const float4 t0 = (vx0 & vy0) ? ldg4(pb) : f4zero();
+                const float4 t1 = (vx1 & vy0) ? ldg4(pb + EGN_CF) : f4zero();
+                const float4 t2 = (vx0 & vy1) ? ldg4(pb + (long long)W * EGN_CF) : f4zero();
+                const float4 t3 = (vx1 & vy1) ? ldg4(pb + (long long)W * EGN_CF + EGN_CF) : f4zero();
+                const float4 l0 = vq0 ? ldg4(lb) : f4zero();
+                const float4 l1 = vq1 ? ldg4(lb + EGN_CF) : f4zero();
+                const float fx = fr[ax], fy = fr[ay], fq = fr[al];
+                const float gx = 1.f - fx, gy = 1.f - fy;
+                const float w0 = gx * gy, w1 = fx * gy, w2 = gx * fy, w3 = fx * fy;
+                float4 P = f4zero();
+                P = f4fma(w0, t0, P); P = f4fma(w1, t1, P); P = f4fma(w2, t2, P); P = f4fma(w3, t3, P);
+                float4 Lv = f4zero();
+                Lv = f4fma(1.f - fq, l0, Lv); Lv = f4fma(fq, l1, Lv);
+                const float4 prod = f4mul(P, Lv);
+                // density lanes: s_i = sum over the 16 density channels (4 lanes); d s_i = dsig * [s_i > 0]  (relu, EgoNeRF.py:346)
+                float s = hsum4(prod);
+                s += __shfl_xor_sync(FULL, s, 1);
+                s += __shfl_xor_sync(FULL, s, 2);
+                float4 up;                                       // upstream gradient of this lane's 4 product channels
+                if (sub < EGN_CS / 4) {
+                    const float ds = (s > 0.f) ? dsig : 0.f;
+                    up = make_float4(ds, ds, ds, ds);
+                } else {
+                    up = dv[i];
+                    *reinterpret_cast<float4*>(&vt[src][i * EGN_CA + (sub - EGN_CS / 4) * 4]) = prod;
+                }
+                const float4 dP = f4mul(up, Lv), dL = f4mul(up, P);
+                float* gp = d_tab + po;
+                float* gl = d_tab + lo;
+                if (vx0 & vy0) red_add4(gp, f4scale(w0, dP));
+                if (vx1 & vy0) red_add4(gp + EGN_CF, f4scale(w1, dP));
+                if (vx0 & vy1) red_add4(gp + (long long)W * EGN_CF, f4scale(w2, dP));
+                if (vx1 & vy1) red_add4(gp + (long long)W * EGN_CF + EGN_CF, f4scale(w3, dP));
+                if (vq0) red_add4(gl, f4scale(1.f - fq, dL));
+                if (vq1) red_add4(gl + EGN_CF, f4scale(fq, dL));
+            }
+        }
+        // ---- c. d(basis) += dfeat^T v over the CTA's 256 samples ----
+        __syncthreads();
+        if (has_tile) {
+            for (int w = 0; w < GB_WARPS; ++w) {
+#pragma unroll 4
+                for (int s = 0; s < 16; ++s) {
+                    const int yy = sm.yang[w][s];              // CTA-uniform
+                    if (yy < 0) continue;
+                    const float4 d4 = *reinterpret_cast<const float4*>(&sm.df[w][s][og * 4]);
+                    const float2 v2 = *reinterpret_cast<const float2*>(&sm.vt[w][s][kp * 2]);
+                    if (yy == 0) {
+                        accB[0][0][0] = fmaf(d4.x, v2.x, accB[0][0][0]); accB[0][0][1] = fmaf(d4.x, v2.y, accB[0][0][1]);
+                        accB[0][1][0] = fmaf(d4.y, v2.x, accB[0][1][0]); accB[0][1][1] = fmaf(d4.y, v2.y, accB[0][1][1]);
+                        accB[0][2][0] = fmaf(d4.z, v2.x, accB[0][2][0]); accB[0][2][1] = fmaf(d4.z, v2.y, accB[0][2][1]);
+                        accB[0][3][0] = fmaf(d4.w, v2.x, accB[0][3][0]); accB[0][3][1] = fmaf(d4.w, v2.y, accB[0][3][1]);
+                    } else {
+                        accB[1][0][0] = fmaf(d4.x, v2.x, accB[1][0][0]); accB[1][0][1] = fmaf(d4.x, v2.y, accB[1][0][1]);
+                        accB[1][1][0] = fmaf(d4.y, v2.x, accB[1][1][0]); accB[1][1][1] = fmaf(d4.y, v2.y, accB[1][1][1]);
+                        accB[1][2][0] = fmaf(d4.z, v2.x, accB[1][2][0]); accB[1][2][1] = fmaf(d4.z, v2.y, accB[1][2][1]);
+                        accB[1][3][0] = fmaf(d4.w, v2.x, accB[1][3][0]); accB[1][3][1] = fmaf(d4.w, v2.y, accB[1][3][1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (has_tile) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float* dB = h ? d_basis1 : d_basis0;
+            if (!dB) continue;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int o = og * 4 + a;
+                if (o < k.app_dim) {
+                    atomicAdd(dB + o * GB_K + kp * 2, accB[h][a][0]);
+                    atomicAdd(dB + o * GB_K + kp * 2 + 1, accB[h][a][1]);
+                }
+            }
+        }
+    }
+}
+
+int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                          const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st) {
+    const long long M = n * k.S;
+    const long long rounds = (M + 15) / 16;
+    long long blocks = (rounds + GB_WARPS - 1) / GB_WARPS;
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    cudaFuncSetAttribute(egn_gather_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GbSmem));
+    egn_gather_bwd_kernel<<<(unsigned)blocks, GB_WARPS * 32, sizeof(GbSmem), st>>>(
+        k, p->basis[0], p->basis[1], rays, M, z, d_fsig, d_feat, d_tables, g->basis[0], g->basis[1]);
+    return (int)cudaGetLastError();
+}

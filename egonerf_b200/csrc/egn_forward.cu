@@ -5,8 +5,7 @@
 // Reference semantics: SURVEY.md Appendix A; citations are into changwoonchoi/EgoNeRF.
 #include "egn_device.cuh"
 #include "egn_host.h"
-
-#define FULL 0xffffffffu
+#include "egn_shared.cuh"
 
 // -------------------------------------------------------------------------------------------------
 // One lane's float4 slice of P_i * L_i (i < 3) for one sample: EgoNeRF.compute_densityfeature /
@@ -60,7 +59,6 @@ __device__ __forceinline__ void egn_gather_products(const float* __restrict__ ta
         prod[i] = f4mul(P, Lv);
     }
 }
-__device__ __forceinline__ float hsum4(float4 v) { return (v.x + v.y) + (v.z + v.w); }
 
 // =================================================================================================
 // K1: coarse pass + resampling.  One warp per ray.
@@ -480,34 +478,6 @@ int egn_launch_coords(const EgnKernelCfg& k, const float* xyz, long long m, floa
 // =================================================================================================
 // Envmap (models/envmap.py:6-34): equirect (3, 2h, h) bilinear + sigmoid.
 // =================================================================================================
-struct EnvTap { int x0, y0; float fx, fy; };
-__device__ __forceinline__ EnvTap egn_env_tap(float dx, float dy, float dz, int h) {
-    const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);     // F.normalize eps
-    dx /= nrm; dy /= nrm; dz /= nrm;
-    const float u = (dz + 1.f) * 0.5f;
-    const float v = (atan2f(dy, dx) + 3.14159265358979323846f) / 6.28318530717958647692f;
-    const float ix = egn_unnorm(2.f * u - 1.f, h), iy = egn_unnorm(2.f * v - 1.f, 2 * h);
-    EnvTap t;
-    const float flx = floorf(ix), fly = floorf(iy);
-    t.x0 = (int)flx; t.y0 = (int)fly; t.fx = ix - flx; t.fy = iy - fly;
-    return t;
-}
-__device__ __forceinline__ void egn_env_radiance(const float* __restrict__ em, int h, float dx, float dy, float dz, float out[3]) {
-    const EnvTap t = egn_env_tap(dx, dy, dz, h);
-    const int W = h, H = 2 * h;
-    const float w[4] = {(1.f - t.fx) * (1.f - t.fy), t.fx * (1.f - t.fy), (1.f - t.fx) * t.fy, t.fx * t.fy};
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int x = t.x0 + (q & 1), y = t.y0 + (q >> 1);
-            if (x >= 0 && x < W && y >= 0 && y < H) acc = fmaf(w[q], __ldg(em + ((long long)ch * H + y) * W + x), acc);
-        }
-        out[ch] = egn_sigmoid(acc);
-    }
-}
-
 __global__ void __launch_bounds__(256)
 egn_envmap_kernel(int h, const float* __restrict__ em, const float* __restrict__ dirs, long long n, float* __restrict__ out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -550,38 +520,11 @@ int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, l
 // K4: compositing (tensorBase.py:22-27, EgoNeRF.py:579-598).  One warp per ray, lane owns S/32
 // consecutive samples; transmittance = warp-shuffle product scan.
 // =================================================================================================
-#define K4_MAXE 16
-
-__device__ __forceinline__ void egn_sample_color(const EgnKernelCfg& k, const float* __restrict__ feat,
-                                                 const float* __restrict__ rgbs, long long m, const float sh[9], float c[3]) {
-    if (k.shading == EGN_SHADE_RGB) {              // RGBRender (tensorBase.py:37-39)
-        c[0] = feat[m * EGN_FEAT_STRIDE]; c[1] = feat[m * EGN_FEAT_STRIDE + 1]; c[2] = feat[m * EGN_FEAT_STRIDE + 2];
-    } else if (k.shading == EGN_SHADE_SH) {        // SHRender (tensorBase.py:30-34)
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float a = 0.f;
-#pragma unroll
-            for (int b = 0; b < 9; ++b) a += sh[b] * feat[m * EGN_FEAT_STRIDE + ch * 9 + b];
-            c[ch] = fmaxf(a + 0.5f, 0.f);
-        }
-    } else {
-        c[0] = rgbs[m * 3]; c[1] = rgbs[m * 3 + 1]; c[2] = rgbs[m * 3 + 2];
-    }
-}
-__device__ __forceinline__ void egn_sh_basis(float x, float y, float z, float sh[9]) {   // models/sh.py:87-116
-    sh[0] = 0.28209479177387814f;
-    sh[1] = -0.4886025119029199f * y; sh[2] = 0.4886025119029199f * z; sh[3] = -0.4886025119029199f * x;
-    const float xx = x * x, yy = y * y, zz = z * z;
-    sh[4] = 1.0925484305920792f * (x * y); sh[5] = -1.0925484305920792f * (y * z);
-    sh[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-    sh[7] = -1.0925484305920792f * (x * z); sh[8] = 0.5462742152960396f * (xx - yy);
-}
-
 __global__ void __launch_bounds__(256)
 egn_composite_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ emission,
                      const float* __restrict__ rays, long long n, const float* __restrict__ zs,
                      const float* __restrict__ fsig, const float* __restrict__ feat, const float* __restrict__ rgbs,
-                     EgnOutputs out, float* __restrict__ wgt, float* __restrict__ bgw) {
+                     EgnOutputs out, float* __restrict__ wgt, float* __restrict__ bgw, float* __restrict__ rgbpre) {
     const int lane = threadIdx.x & 31;
     const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (ray >= n) return;
@@ -645,6 +588,7 @@ egn_composite_kernel(const __grid_constant__ EgnKernelCfg k, const float* __rest
             cr += b0; cg += b1; cb += b2;
             out.alpha[ray * acols + S] = 1.f;       // EgoNeRF.py:587
         }
+        if (rgbpre) { rgbpre[ray * 3] = cr; rgbpre[ray * 3 + 1] = cg; rgbpre[ray * 3 + 2] = cb; }   // clamp mask for backward
         out.rgb[ray * 3] = fminf(fmaxf(cr, 0.f), 1.f);
         out.rgb[ray * 3 + 1] = fminf(fmaxf(cg, 0.f), 1.f);
         out.rgb[ray * 3 + 2] = fminf(fmaxf(cb, 0.f), 1.f);
@@ -655,9 +599,9 @@ egn_composite_kernel(const __grid_constant__ EgnKernelCfg k, const float* __rest
 
 int egn_launch_composite(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                          const float* fsig, const float* feat, const float* rgbs, const EgnOutputs* out, float* wgt,
-                         float* bgw, cudaStream_t st) {
+                         float* bgw, float* rgbpre, cudaStream_t st) {
     long long threads = n * 32;
     egn_composite_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(k, p->emission, rays, n, z, fsig, feat, rgbs,
-                                                                           *out, wgt, bgw);
+                                                                           *out, wgt, bgw, rgbpre);
     return (int)cudaGetLastError();
 }

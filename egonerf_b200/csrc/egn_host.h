@@ -9,8 +9,9 @@ struct EgnWorkspace {
     float* fsig;     // (n,S)      density feature before feature2density
     float* feat;     // (n,S,28)   appearance feature (27 used)
     float* rgbs;     // (n,S,3)    decoded sample colours
-    float* wgt;      // (n,S)      compositing weights (saved for backward)
+    float* wgt;      // (n,S)      compositing weights
     float* bgw;      // (n)        background weight T_S
+    float* rgbpre;   // (n,3)      unclamped rgb (clamp mask of the backward pass)
     float* d_rgbs;   // (n,S,3)    backward scratch
     float* d_fsig;   // (n,S)
     float* d_feat;   // (n,S,28)
@@ -30,7 +31,7 @@ int egn_launch_mlp(const EgnKernelCfg& k, const EgnParams* p, const float* rays,
                    float* rgbs, cudaStream_t st);
 int egn_launch_composite(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                          const float* fsig, const float* feat, const float* rgbs, const EgnOutputs* out, float* wgt,
-                         float* bgw, cudaStream_t st);
+                         float* bgw, float* rgbpre, cudaStream_t st);
 int egn_launch_coords(const EgnKernelCfg& k, const float* xyz, long long m, float* coords7, cudaStream_t st);
 int egn_launch_envmap(int env_h, const float* emission, const float* dirs, long long n, float* out, cudaStream_t st);
 int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, long long n, const float* d_out,
@@ -38,10 +39,14 @@ int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, l
 
 // backward
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
-                             const float* fsig, const float* feat, const float* rgbs, const float* wgt, const float* bgw,
+                             const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,
                              const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
                              float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, cudaStream_t st);
+// MLP backward of a sub-chunk of n rays: recomputes the hidden activations into scratch (h1, h2, dz1, dz2: n*S x 128 floats)
 int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
-                       const float* rgbs, const float* d_rgbs, float* d_feat, const EgnGrads* g, cudaStream_t st);
+                       const float* rgbs, const float* d_rgbs, float* d_feat, float* h1, float* h2, float* dz1,
+                       float* dz2, const EgnGrads* g, cudaStream_t st);
+int egn_launch_mlp_save(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
+                        float* h1, float* h2, cudaStream_t st);
 int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                           const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st);

@@ -42,7 +42,7 @@ class _VolumeRender(torch.autograd.Function):
         S = lib.egn_samples_per_ray(cfg)
         has_env = cfg.env_h > 0
         dev = rays.device
-        need_grad = opts["is_train"] and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = bool(opts["is_train"]) and any(ctx.needs_input_grad[6:])
         rgb = torch.empty(n, 3, device=dev)
         depth = torch.empty(n, device=dev)
         alpha = torch.empty(n, S + (1 if has_env else 0), device=dev)
@@ -400,6 +400,21 @@ class EgoNeRF(torch.nn.Module):
     def launches_per_forward(self):
         """Kernels of libegn_b200 launched by one `forward` (sampler, gather, [MLP], composite)."""
         return 4 if isinstance(self.renderModule, torch.nn.Module) else 3
+
+    def launches_per_train_step(self, n_rays):
+        """forward + backward (composite, per-sub-chunk MLP chain, gather) + gradient unpack + table re-pack."""
+        mlp = isinstance(self.renderModule, torch.nn.Module)
+        sub = -(-int(n_rays) // 4096)
+        return self.launches_per_forward() + 1 + (6 * sub if mlp else 0) + 1 + 1 + 1
+
+    def allreduce_gradients(self, group=None):
+        """Ray-sharded data parallelism: one NCCL all-reduce (sum) over all parameter gradients."""
+        import torch.distributed as dist
+        ps = [p for p in self._param_list() if p.grad is not None]
+        flat = torch._utils._flatten_dense_tensors([p.grad for p in ps])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        for p, g in zip(ps, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in ps])):
+            p.grad.copy_(g)
 
     def stage_times(self, rays_chunk, repeats=3, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, **_):
         """Mean device time (ms) of each stage of the eval forward, from CUDA events recorded between the launches

@@ -1,10 +1,12 @@
 #!/bin/bash
-# One GPU-box session: parity tests, bench lines, ncu launch list (+ optional full capture of the top kernel).
+# One GPU-box session: parity tests, bench lines, ncu launch list.  Usage: gpu_round.sh [quick]
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest.log
+tail -15 gpurun_out/pytest.log
+if [ "$1" != "quick" ]; then
 python bench.py > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err
-python bench.py --workload cfg1 --steps 50 --no-cpu-baseline > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --rays 16384 > gpurun_out/ncu_bench.log 2>&1
-tail -5 gpurun_out/pytest.log; cat gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
+python bench.py --mode train --rays 16384 --steps 5 --no-cpu-baseline > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_train.csv \
+    python bench.py --mode train --steps 1 --warmup 3 --no-cpu-baseline --rays 8192 > gpurun_out/ncu_bench.log 2>&1
+cat gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err; cat gpurun_out/bench_train.json; tail -3 gpurun_out/bench_train.err
+fi
