@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mlp", default="tc_split", choices=["fp32", "tc_split", "tc_bf16"],
+                    help="arithmetic of the colour-decode MLP: exact fp32 FFMA, tcgen05 3-term bf16 split (fp32-equivalent), tcgen05 bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -187,6 +189,8 @@ def main():
 
     scene = make_scene(n_voxels=wl["n_voxels"], **wl["scene"])
     model = model_from_scene(scene, dev)
+    model.mlp_mode = args.mlp
+    config["mlp"] = args.mlp
     rays_host = make_rays(n_rays, 'isotropic', seed=1000 + rank).pin_memory()
     rays_dev = rays_host.to(dev)
     ray0 = rank * n_rays
@@ -290,7 +294,7 @@ def main():
 
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "dtype": "f32" if args.mlp != "tc_bf16" else "f32 tables + bf16 MLP", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
                     "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world},
             "gpu_launches": (model.launches_per_forward() if not train else model.launches_per_train_step(n_rays)) * args.steps,

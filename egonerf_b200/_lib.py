@@ -47,6 +47,7 @@ class EgnOutputs(C.Structure):
 
 SHADING = {"MLP_Fea": 0, "MLP": 1, "RGB": 2, "SH": 3}
 ACT = {"softplus": 0, "relu": 1}
+MLP_MODE = {"fp32": 0, "tc_split": 1, "tc_bf16": 2}   # EGN_MLP_* (include/egn.h)
 
 # name -> (restype, argtypes); every symbol include/egn.h declares
 PROTOTYPES = {

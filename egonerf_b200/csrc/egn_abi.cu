@@ -41,6 +41,9 @@ static int validate(const EgnConfig* c, bool need_schedule) {
         if (c->feature_c != EGN_HID) return fail("featureC=%d unsupported (%d)", c->feature_c, EGN_HID);
         int in_dim = c->app_dim + 3 + 6 * c->view_pe + (c->shading == EGN_SHADE_MLP_FEA ? 2 * c->fea_pe * c->app_dim : 0);
         if (in_dim > 152) return fail("MLP input width %d exceeds 152", in_dim);
+        if (c->mlp_mode < EGN_MLP_FP32 || c->mlp_mode > EGN_MLP_TC_BF16) return fail("unknown mlp_mode %d", c->mlp_mode);
+        if (c->mlp_mode != EGN_MLP_FP32 && !(c->shading == EGN_SHADE_MLP_FEA && c->view_pe == 2 && c->fea_pe == 2))
+            return fail("tensor-core MLP modes need shadingMode MLP_Fea with view_pe = fea_pe = 2 (use EGN_MLP_FP32)");
     }
     if (need_schedule) {
         if (c->n_coarse < 32 || c->n_coarse > 256 || c->n_coarse % 32) return fail("n_coarse=%d must be a multiple of 32 in [32,256]", c->n_coarse);
@@ -66,6 +69,7 @@ static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables) {
     k.use_coarse_sample = c->use_coarse_sample; k.resampling = c->resampling;
     k.fea2dense = c->fea2dense; k.shading = c->shading; k.app_dim = c->app_dim;
     k.view_pe = c->view_pe; k.fea_pe = c->fea_pe; k.env_h = c->env_h;
+    k.mlp_mode = c->mlp_mode;
     return k;
 }
 
@@ -170,8 +174,11 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     mark(se, 1, st);
     if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
     mark(se, 2, st);
-    if (c->shading <= EGN_SHADE_MLP)
-        if ((e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st))) return cuda_fail("mlp", e);
+    if (c->shading <= EGN_SHADE_MLP) {
+        if (c->mlp_mode == EGN_MLP_FP32) e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st);
+        else e = egn_launch_mlp_tc(k, p, rays, n, feat, rgbs, c->mlp_mode == EGN_MLP_TC_SPLIT, nullptr, st);
+        if (e) return cuda_fail("mlp", e);
+    }
     mark(se, 3, st);
     if ((e = egn_launch_composite(k, p, rays, n, z, fsig, feat, rgbs, out, wgt, bgw, rgbpre, st))) return cuda_fail("composite", e);
     mark(se, 4, st);

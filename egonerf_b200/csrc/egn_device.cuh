@@ -59,6 +59,7 @@ struct EgnKernelCfg {
     float density_shift, distance_scale;
     int n_coarse, n_fine, S, use_coarse_sample, resampling;
     int fea2dense, shading, app_dim, view_pe, fea_pe, env_h;
+    int mlp_mode;             // EGN_MLP_*
 };
 
 #ifdef __CUDACC__

@@ -37,6 +37,10 @@ int egn_launch_envmap(int env_h, const float* emission, const float* dirs, long 
 int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, long long n, const float* d_out,
                           float* d_emission, cudaStream_t st);
 
+// tensor-core colour decode (egn_mlp_tc.cu): split = 1 -> 3-term bf16 split (fp32-equivalent), 0 -> plain bf16
+bool egn_mlp_tc_supported(const EgnKernelCfg& k);
+int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
+                      float* rgbs, int split, int* err_flag, cudaStream_t st);
 // backward
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,

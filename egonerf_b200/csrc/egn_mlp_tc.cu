@@ -1,0 +1,337 @@
+// Colour decode on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Same function as egn_mlp.cu (MLPRender_Fea, models/tensorBase.py:54-78 with fea_pe = view_pe = 2): per 128-sample tile
+//     X[128 x 160] (bf16)  --tcgen05.mma-->  D1 (TMEM, fp32)  --+b1, relu-->  H1[128 x 128] (bf16, shared memory)
+//     --tcgen05.mma-->  D2 (TMEM)  --+b2, relu, . W3 (fp32 FFMA), sigmoid-->  rgb
+// Two arithmetic modes (EgnConfig.mlp_mode):
+//   EGN_MLP_TC_SPLIT  every operand is split x = hi + lo (two bf16), D += A_lo B_hi + A_hi B_lo + A_hi B_hi with fp32
+//                     accumulation: products carry ~2^-17 relative error — fp32-equivalent for the 1e-4 parity bound
+//   EGN_MLP_TC_BF16   plain bf16 operands (throughput mode, PSNR-gated)
+//
+// Operand layout in shared memory: canonical K-major, no swizzle (UMMA "interleave"): 8 x 8 core matrices of 128 B,
+// element (row, k) at (k / 8) * 2048 + row * 16 + (k % 8) * 2 for 128-row tiles, i.e. LBO (K step) = 2048 B,
+// SBO (8-row step) = 128 B.  A thread that owns a row writes 16-byte chunks; consecutive rows are consecutive 16 B
+// -> conflict-free st.shared.v4.  The K order of X is OURS to choose (W1's columns are permuted to match when the
+// weights are staged): element e contributes [x, sin x, cos x, sin 2x, cos 2x] at k = 5e .. 5e+4 (e < app_dim: feature,
+// then the 3 view-direction components), so that a thread produces whole 16-byte chunks from 8 elements.
+//
+// 256 threads: thread t owns row (t & 127) and column half (t >> 7) — warps w and w+4 share TMEM lane quadrant w & 3.
+// One elected thread issues the MMAs; completion comes back through tcgen05.commit -> mbarrier.
+#include <cuda_bf16.h>
+#include "egn_device.cuh"
+#include "egn_host.h"
+
+#define TC_THREADS 256
+#define TC_TM 128
+#define TC_K1 160                      // 32 elements x 5 values
+#define TC_CHUNK 2048                  // bytes of one 8-wide K chunk of a 128-row operand
+#define TC_IDESC_128x128 0x08200490u   // kind::f16: D fp32, A/B bf16, both K-major, N = 128, M = 128
+
+// ---- shared-memory carve-up (bytes) --------------------------------------------------------------------------------
+template <bool SPLIT>
+struct TcLayout {
+    static constexpr int W1 = 0;                                             // [hi | lo] 20 chunks each
+    static constexpr int W1_BYTES = (TC_K1 / 8) * TC_CHUNK;
+    static constexpr int W2 = W1 + W1_BYTES * (SPLIT ? 2 : 1);               // 16 chunks each
+    static constexpr int W2_BYTES = (EGN_HID / 8) * TC_CHUNK;
+    static constexpr int A = W2 + W2_BYTES * (SPLIT ? 2 : 1);                // X (20 chunks) / H1 (16 chunks)
+    static constexpr int A_BYTES = (TC_K1 / 8) * TC_CHUNK;
+    static constexpr int MBAR = A + A_BYTES * (SPLIT ? 2 : 1);               // 2 x 8 bytes
+    static constexpr int TMEM = MBAR + 16;                                   // 4 bytes
+    static constexpr int TOTAL = TMEM + 16;
+    // bf16 mode: 114 720 B -> two CTAs per SM (the second CTA's CUDA-core phases hide the first one's MMAs);
+    // split mode: 229 408 B -> one CTA per SM
+    // layer-3 partial sums of column half 1, 128 x 4 floats: aliases K chunks 16.. of the A buffer, which the
+    // layer-2 operand (16 chunks) never touches
+    static constexpr int PART = A + 16 * TC_CHUNK;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+    // start address >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(TC_CHUNK >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+// bounded wait: a lost arrive must not hang the GPU — after ~2^28 polls the CTA flags an error and carries on
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); two values per 32-bit word, first value in the low half
+__device__ __forceinline__ uint32_t pack_hi(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    return pack_hi(a - ha, b - hb);
+}
+template <bool SPLIT>
+__device__ __forceinline__ void store_chunk(unsigned char* hi_base, unsigned char* lo_base, int chunk, int row, const float* v) {
+    uint4 h;
+    h.x = pack_hi(v[0], v[1]); h.y = pack_hi(v[2], v[3]); h.z = pack_hi(v[4], v[5]); h.w = pack_hi(v[6], v[7]);
+    *reinterpret_cast<uint4*>(hi_base + chunk * TC_CHUNK + row * 16) = h;
+    if (SPLIT) {
+        uint4 l;
+        l.x = pack_lo(v[0], v[1], h.x); l.y = pack_lo(v[2], v[3], h.y); l.z = pack_lo(v[4], v[5], h.z); l.w = pack_lo(v[6], v[7], h.w);
+        *reinterpret_cast<uint4*>(lo_base + chunk * TC_CHUNK + row * 16) = l;
+    }
+}
+__device__ __forceinline__ void store_elem(unsigned char* hi_base, unsigned char* lo_base, bool split, int row, int kk, float x) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const int off = (kk >> 3) * TC_CHUNK + row * 16 + (kk & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
+    if (split) *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+// original input index (tensorBase.py:68-74 order) of our K position kk; -1 = padding; -2 = the constant-1 column that
+// carries the layer-1 bias (first value of the first padding element)
+__device__ __forceinline__ int tc_input_index(int kk, int AD) {
+    const int e = kk / 5, r = kk % 5;
+    if (e == AD + 3 && r == 0) return -2;
+    if (e >= AD + 3) return -1;
+    const int off_fs = AD + 3, off_fc = off_fs + 2 * AD, off_vs = off_fc + 2 * AD, off_vc = off_vs + 6;
+    if (e < AD) return r == 0 ? e : ((r & 1) ? off_fs : off_fc) + e * 2 + ((r - 1) >> 1);
+    const int d = e - AD;
+    return r == 0 ? AD + d : ((r & 1) ? off_vs : off_vc) + d * 2 + ((r - 1) >> 1);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(TC_THREADS, SPLIT ? 1 : 2)
+egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                  const float* __restrict__ b3, const float* __restrict__ rays, long long M,
+                  const float* __restrict__ feat, float* __restrict__ rgbs, int* __restrict__ err_flag) {
+    using L = TcLayout<SPLIT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, half = tid >> 7;
+    const int AD = k.app_dim;
+    const int in_dim = AD + 3 + 4 * AD + 12;
+    unsigned char* w1hi = smem + L::W1; unsigned char* w1lo = w1hi + L::W1_BYTES;
+    unsigned char* w2hi = smem + L::W2; unsigned char* w2lo = w2hi + L::W2_BYTES;
+    unsigned char* ahi = smem + L::A;   unsigned char* alo = ahi + L::A_BYTES;
+    float* part = reinterpret_cast<float*>(smem + L::PART);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
+    const uint32_t bar0 = smem_u32(smem + L::MBAR), bar1 = bar0 + 8;
+
+    // ---- one-time setup: TMEM, barriers, weights ----
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < EGN_HID * TC_K1; i += TC_THREADS) {          // W1[n][kk], columns permuted to our K order
+        const int n = i / TC_K1, kk = i % TC_K1;
+        const int src = tc_input_index(kk, AD);
+        store_elem(w1hi, w1lo, SPLIT, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
+    }
+    for (int i = tid; i < EGN_HID * EGN_HID; i += TC_THREADS) {
+        const int n = i / EGN_HID, kk = i % EGN_HID;
+        store_elem(w2hi, w2lo, SPLIT, n, kk, w2[i]);
+    }
+    const float bias3[3] = {__ldg(b3), __ldg(b3 + 1), __ldg(b3 + 2)};
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);      // this warp's lane quadrant
+    const uint32_t a_hi = smem_u32(ahi), a_lo = smem_u32(alo);
+    const uint32_t w1_hi = smem_u32(w1hi), w1_lo = smem_u32(w1lo), w2_hi = smem_u32(w2hi), w2_lo = smem_u32(w2lo);
+
+    const long long tiles = (M + TC_TM - 1) / TC_TM;
+    uint32_t it = 0;
+    bool ok = true;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const long long gm = tile * TC_TM + row;
+        const bool live = gm < M;
+        // ---- A. input rows: 16 elements per thread -> 10 chunks of [x, sin x, cos x, sin 2x, cos 2x] ----
+        {
+            float el[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) el[j] = 0.f;
+            if (live) {
+                const float4* f4 = reinterpret_cast<const float4*>(feat + gm * EGN_FEAT_STRIDE);
+                if (half == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float4 v = __ldg(f4 + q); el[4 * q] = v.x; el[4 * q + 1] = v.y; el[4 * q + 2] = v.z; el[4 * q + 3] = v.w; }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { const float4 v = __ldg(f4 + 4 + q); el[4 * q] = v.x; el[4 * q + 1] = v.y; el[4 * q + 2] = v.z; el[4 * q + 3] = v.w; }
+                }
+                // elements >= app_dim are the view direction (then padding)
+                const float* dir = rays + (gm / k.S) * 6 + 3;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int e = 16 * half + j;
+                    if (e >= AD) el[j] = (e < AD + 3) ? dir[e - AD] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[40];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = 16 * half + 8 * pass + j;
+                    const float x = el[8 * pass + j];
+                    float s1, c1;
+                    if (SPLIT) sincosf(x, &s1, &c1); else __sincosf(x, &s1, &c1);   // bf16 operands keep 8 bits: MUFU is ample
+                    const float s2 = 2.f * s1 * c1, c2 = 1.f - 2.f * s1 * s1;          // sin 2x, cos 2x by the double-angle identities
+                    const bool valid = e < AD + 3;           // padding elements must contribute exact zeros (cos 0 = 1!)
+                    v[5 * j] = (e == AD + 3) ? 1.f : x;      // constant-1 column: layer-1 bias rides in W1
+                    v[5 * j + 1] = valid ? s1 : 0.f; v[5 * j + 2] = valid ? c1 : 0.f;
+                    v[5 * j + 3] = valid ? s2 : 0.f; v[5 * j + 4] = valid ? c2 : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 5; ++c) store_chunk<SPLIT>(ahi, alo, 10 * half + 5 * pass + c, row, v + 8 * c);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- B. layer 1: D1 (TMEM columns 0..127) = X . W1^T ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < TC_K1 / 16; ++ks) {
+                const uint32_t o = ks * 2 * TC_CHUNK;
+                if (SPLIT) {
+                    tc_mma(tmem, tc_desc(a_lo + o), tc_desc(w1_hi + o), TC_IDESC_128x128, ks > 0);
+                    tc_mma(tmem, tc_desc(a_hi + o), tc_desc(w1_lo + o), TC_IDESC_128x128, 1);
+                    tc_mma(tmem, tc_desc(a_hi + o), tc_desc(w1_hi + o), TC_IDESC_128x128, 1);
+                } else {
+                    tc_mma(tmem, tc_desc(a_hi + o), tc_desc(w1_hi + o), TC_IDESC_128x128, ks > 0);
+                }
+            }
+            tc_commit(bar0);
+        }
+        // ---- C. H1 = relu(D1 + b1) -> bf16 operand of layer 2 (overwrites X: its MMAs have completed) ----
+        ok &= mbar_wait(bar0, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int col = 64 * half + 32 * cc;
+            uint32_t r[32];
+            tmem_ld32(tmem_lane + col, r);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]), 0.f);        // b1 is already inside D1
+#pragma unroll
+            for (int c = 0; c < 4; ++c) store_chunk<SPLIT>(ahi, alo, (col >> 3) + c, row, v + 8 * c);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- D. layer 2: D2 (TMEM columns 128..255) = H1 . W2^T ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < EGN_HID / 16; ++ks) {
+                const uint32_t o = ks * 2 * TC_CHUNK;
+                if (SPLIT) {
+                    tc_mma(tmem + 128, tc_desc(a_lo + o), tc_desc(w2_hi + o), TC_IDESC_128x128, ks > 0);
+                    tc_mma(tmem + 128, tc_desc(a_hi + o), tc_desc(w2_lo + o), TC_IDESC_128x128, 1);
+                    tc_mma(tmem + 128, tc_desc(a_hi + o), tc_desc(w2_hi + o), TC_IDESC_128x128, 1);
+                } else {
+                    tc_mma(tmem + 128, tc_desc(a_hi + o), tc_desc(w2_hi + o), TC_IDESC_128x128, ks > 0);
+                }
+            }
+            tc_commit(bar1);
+        }
+        // ---- E. H2 = relu(D2 + b2); rgb = sigmoid(W3 H2 + b3) in fp32 ----
+        ok &= mbar_wait(bar1, it & 1);
+        tc_fence_after();
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int col = 64 * half + 32 * cc;
+            uint32_t r[32];
+            tmem_ld32(tmem_lane + 128 + col, r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {                 // warp-uniform addresses: one L1 transaction per load
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + q);
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + q);
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + q);
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + q);
+                const float h0 = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
+                const float h2 = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
+                p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
+                p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
+                p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
+            }
+        }
+        tc_fence_before();
+        if (half == 1) *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, 0.f);
+        __syncthreads();
+        if (half == 0 && live) {
+            const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
+            rgbs[gm * 3 + 0] = egn_sigmoid(p0 + q.x + bias3[0]);
+            rgbs[gm * 3 + 1] = egn_sigmoid(p1 + q.y + bias3[1]);
+            rgbs[gm * 3 + 2] = egn_sigmoid(p2 + q.z + bias3[2]);
+        }
+        __syncthreads();                                  // the next tile's X overwrites the partial-sum scratch
+    }
+    if (!ok) { if (err_flag) atomicExch(err_flag, 1); __trap(); }      // a lost tcgen05.commit arrive: fail loudly, never hang
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+}
+
+bool egn_mlp_tc_supported(const EgnKernelCfg& k) {
+    return k.shading == EGN_SHADE_MLP_FEA && k.view_pe == 2 && k.fea_pe == 2 && k.app_dim >= 1 && k.app_dim <= 27;
+}
+
+int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
+                      float* rgbs, int split, int* err_flag, cudaStream_t st) {
+    const long long M = n * k.S;
+    const long long tiles = (M + TC_TM - 1) / TC_TM;
+    const int blocks = (int)(tiles < 148 * (split ? 1 : 2) ? tiles : 148 * (split ? 1 : 2));
+    if (split) {
+        cudaFuncSetAttribute(egn_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<true>::TOTAL);
+        egn_mlp_tc_kernel<true><<<blocks, TC_THREADS, TcLayout<true>::TOTAL, st>>>(
+            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs, err_flag);
+    } else {
+        cudaFuncSetAttribute(egn_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<false>::TOTAL);
+        egn_mlp_tc_kernel<false><<<blocks, TC_THREADS, TcLayout<false>::TOTAL, st>>>(
+            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs, err_flag);
+    }
+    return (int)cudaGetLastError();
+}

@@ -7,6 +7,7 @@ No CPU path: every compute entry point raises if the tensors are not on a CUDA d
 from __future__ import annotations
 
 import ctypes as C
+import os
 from math import pi
 
 import numpy as np
@@ -140,6 +141,9 @@ class EgoNeRF(torch.nn.Module):
         self._tables = None
         self._tables_key = None
         self._sched = {}
+        # arithmetic of the colour-decode MLP inside libegn_b200: "fp32" (exact FFMA), "tc_split" (tcgen05, 3-term bf16
+        # split: fp32-equivalent) or "tc_bf16" (tcgen05, plain bf16).  Not a reference kwarg: set the attribute.
+        self.mlp_mode = os.environ.get("EGN_MLP_MODE", "tc_split")
 
     # ---- parameters (EgoNeRF.py:96-122) -------------------------------------------------------------
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
@@ -291,6 +295,8 @@ class EgoNeRF(torch.nn.Module):
         cfg.shading = _lib.SHADING[self.shadingMode]
         cfg.view_pe, cfg.fea_pe, cfg.feature_c = self.view_pe, self.fea_pe, self.featureC
         cfg.fea2dense = _lib.ACT[self.fea2denseAct]
+        tc_ok = self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
+        cfg.mlp_mode = _lib.MLP_MODE[self.mlp_mode] if tc_ok else 0
         cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0
         cfg.center[:] = co.center.cpu().tolist()
         cfg.near_plane = self.near_far[0]

@@ -1,0 +1,82 @@
+"""GPU: the tcgen05 colour-decode kernel (egn_mlp_tc.cu) against the exact-fp32 FFMA kernel and the reference goldens.
+
+  tc_split (3-term bf16 split, fp32 accumulate in TMEM): must stay inside the 1e-4 rgb parity bound on every golden case
+            (reference depths) and within 2e-5 of the FFMA kernel;
+  tc_bf16  (plain bf16 operands): throughput mode — bounded at 2e-2 in rgb and 0.05 dB in PSNR against the fp32 render.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import RENDER_CASES, T, load_golden, scene_for
+
+pytestmark = pytest.mark.gpu
+MLP_FEA_CASES = [n for n in RENDER_CASES if "mlp" not in n and "rgb" not in n and "noresample" not in n]
+
+
+def _model(name):
+    from egonerf_b200.scene_io import model_from_scene
+    skw, okw = RENDER_CASES[name]
+    return model_from_scene(scene_for(skw)), okw, load_golden(name)
+
+
+def _render(model, g, okw, mode, use_ref_depths=True):
+    from egonerf_b200.scene_io import RENDER_KW
+    kw = dict(RENDER_KW)
+    kw.update(okw)
+    model.mlp_mode = mode
+    dev = "cuda:0"
+    cu = lambda k: T(g[k]).to(dev) if k in g else None
+    with torch.no_grad():
+        out = model(cu("rays"), is_train=bool(g["is_train"]), u_coarse=cu("u_coarse"), u_fine=cu("u_fine"),
+                    z_vals=cu("z_vals") if use_ref_depths else None, **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("name", MLP_FEA_CASES)
+def test_tc_split_matches_fp32_and_reference(name):
+    model, okw, g = _model(name)
+    ref = _render(model, g, okw, "fp32")
+    out = _render(model, g, okw, "tc_split")
+    d = (out[0] - ref[0]).abs().max().item()
+    e = np.abs(out[0].cpu().numpy() - g["rgb"]).max()
+    print(f"{name}: tc_split vs fp32 kernel {d:.2e}; vs reference {e:.2e}")
+    assert d <= 2e-5
+    assert e <= 1e-4 or "white" in name
+
+
+@pytest.mark.parametrize("name", ["render_128_eval", "render_300_eval"])
+def test_tc_bf16_is_psnr_safe(name):
+    model, okw, g = _model(name)
+    ref = _render(model, g, okw, "fp32")[0]
+    out = _render(model, g, okw, "tc_bf16")[0]
+    d = (out - ref).abs().max().item()
+    mse = ((out - ref) ** 2).mean().item()
+    psnr_between = -10 * np.log10(max(mse, 1e-20))
+    print(f"{name}: tc_bf16 vs fp32 kernel Linf {d:.2e}, PSNR between the two renders {psnr_between:.1f} dB")
+    assert d <= 2e-2
+    assert psnr_between >= 50.0          # a 0.05 dB change at 30 dB needs the two renders > ~50 dB apart
+
+
+def test_tc_ragged_tile_and_many_tiles():
+    """M not a multiple of 128 and more tiles than CTAs (persistent loop + mbarrier phase toggling)."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays
+    model = model_from_scene(scene_for(dict(n_voxels=40 ** 3, seed=7)))
+    rays = make_rays(333, 'isotropic', seed=5).cuda()
+    kw = dict(RENDER_KW)
+    kw.update(use_coarse_sample=False)                 # S = 128 -> M = 333 * 128: 333 tiles over 148 CTAs
+    outs = {}
+    for mode in ("fp32", "tc_split"):
+        model.mlp_mode = mode
+        with torch.no_grad():
+            outs[mode] = model(rays, is_train=False, **kw)[0]
+    assert (outs["fp32"] - outs["tc_split"]).abs().max().item() <= 2e-5
+    kw = dict(RENDER_KW)
+    rays = rays[:7]                                      # M = 7 * 256 = 1792 = 14 tiles; then 3 rays with S = 128 + ragged
+    for mode in ("fp32", "tc_split"):
+        model.mlp_mode = mode
+        with torch.no_grad():
+            outs[mode] = model(rays, is_train=False, **kw)[0]
+    assert (outs["fp32"] - outs["tc_split"]).abs().max().item() <= 2e-5
