@@ -413,14 +413,15 @@ class EgoNeRF(torch.nn.Module):
         sub = -(-int(n_rays) // 4096)
         return self.launches_per_forward() + 1 + (6 * sub if mlp else 0) + 1 + 1 + 1
 
-    def allreduce_gradients(self, group=None):
-        """Ray-sharded data parallelism: one NCCL all-reduce (sum) over all parameter gradients."""
-        import torch.distributed as dist
-        ps = [p for p in self._param_list() if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors([p.grad for p in ps])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        for p, g in zip(ps, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in ps])):
-            p.grad.copy_(g)
+    def allreduce_gradients(self, group=None, average=False):
+        """Ray-sharded data parallelism: ONE all-reduce (sum) over all parameter gradients, through a
+        persistent flat bucket (egonerf_b200/sharding.py)."""
+        from ..sharding import GradientBucket
+        ps = self._param_list()
+        if getattr(self, "_bucket", None) is None or [id(p) for p in self._bucket.params] != [id(p) for p in ps]:
+            self._bucket = GradientBucket(ps)
+        self._bucket.gather_from_params()
+        self._bucket.allreduce(group, average)
 
     def stage_times(self, rays_chunk, repeats=3, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, **_):
         """Mean device time (ms) of each stage of the eval forward, from CUDA events recorded between the launches

@@ -1,0 +1,67 @@
+"""CPU, world_size 2 over gloo: the host-side logic of ray-sharded data parallelism — shard ranges,
+the flat gradient bucket and its single all-reduce.  The device side (per-ray RNG keyed by the global ray index, shard
+additivity of gradients) is covered on the GPU by tests/test_gpu_grad.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from egonerf_b200.sharding import GradientBucket, row_tiles, shard_range
+
+
+def test_shard_ranges_partition_exactly():
+    for n in (0, 1, 7, 4096, 65536, 131072, 4096 * 2048 + 3):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    assert row_tiles(2048, 3, 8) == (768, 1024)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(s)) for s in ((1, 16, 22, 20), (1, 48, 64, 1), (27, 144), (128,), (3, 8, 4))]
+        bucket = GradientBucket(params)
+        # every rank computes the gradient of its own ray shard of a toy "render": loss = sum_r w_r * <p, x_r>
+        n = 1001
+        a, b = shard_range(n, rank, world)
+        g = torch.Generator().manual_seed(5)
+        coeff = torch.rand(n, generator=g)
+        for p in params:
+            p.grad = None
+        loss = sum((p * p).sum() for p in params) * coeff[a:b].sum()
+        loss.backward()                                   # autograd allocates its own .grad tensors
+        bucket.gather_from_params()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views))
+        bucket.allreduce()
+        expect = [2 * p.detach() * coeff.sum() for p in params]
+        err = max(float((p.grad - e).abs().max() / e.abs().max()) for p, e in zip(params, expect))
+        out[rank] = err
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_bucket_allreduce_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world and all(e < 1e-5 for e in out.values()), dict(out)
