@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tables", default="f32", choices=["f32", "bf16"], help="dtype of the fine render tables (bf16 needs --mlp tc_bf16)")
     ap.add_argument("--mlp", default="tc_split", choices=["fp32", "tc_split", "tc_bf16"],
                     help="arithmetic of the colour-decode MLP: exact fp32 FFMA, tcgen05 3-term bf16 split (fp32-equivalent), tcgen05 bf16")
     args = ap.parse_args()
@@ -190,7 +191,9 @@ def main():
     scene = make_scene(n_voxels=wl["n_voxels"], **wl["scene"])
     model = model_from_scene(scene, dev)
     model.mlp_mode = args.mlp
+    model.table_dtype = args.tables
     config["mlp"] = args.mlp
+    config["tables"] = args.tables
     rays_host = make_rays(n_rays, 'isotropic', seed=1000 + rank).pin_memory()
     rays_dev = rays_host.to(dev)
     ray0 = rank * n_rays

@@ -24,7 +24,7 @@ class EgnConfig(C.Structure):
         ("mlp_mode", C.c_int32),
         ("center", C.c_float * 3), ("near_plane", C.c_float), ("density_shift", C.c_float),
         ("distance_scale", C.c_float), ("ang_near", C.c_float * 2), ("ang_inv", C.c_float * 2),
-        ("r_knots", C.c_void_p), ("z_coarse", C.c_void_p),
+        ("r_knots", C.c_void_p), ("z_coarse", C.c_void_p), ("tables_bf16", C.c_void_p),
     ]
 
 
@@ -56,6 +56,8 @@ PROTOTYPES = {
     "egn_samples_per_ray": (C.c_int32, [C.POINTER(EgnConfig)]),
     "egn_table_floats": (C.c_int64, [C.POINTER(EgnConfig)]),
     "egn_pack_tables": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p]),
+    "egn_table_bf16_elems": (C.c_int64, [C.POINTER(EgnConfig)]),
+    "egn_pack_tables_bf16": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     "egn_unpack_table_grads": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.POINTER(EgnGrads), C.c_void_p]),
     "egn_workspace_bytes": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),
     "egn_workspace_bytes_eval": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),

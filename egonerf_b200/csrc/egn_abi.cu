@@ -70,6 +70,7 @@ static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables) {
     k.fea2dense = c->fea2dense; k.shading = c->shading; k.app_dim = c->app_dim;
     k.view_pe = c->view_pe; k.fea_pe = c->fea_pe; k.env_h = c->env_h;
     k.mlp_mode = c->mlp_mode;
+    k.tables_bf16 = c->tables_bf16;
     return k;
 }
 
@@ -87,6 +88,18 @@ extern "C" int32_t egn_pack_tables(const EgnConfig* c, const EgnParams* p, float
                 return fail("missing factor tensor h=%d i=%d", h, i);
     int e = egn_launch_pack(c, p, tables, (cudaStream_t)stream);
     return e ? cuda_fail("egn_pack_tables", e) : 0;
+}
+
+extern "C" int64_t egn_table_bf16_elems(const EgnConfig* c) {
+    if (validate(c, false)) return -1;
+    return egn_make_layout(c->grid).pc[0][0];
+}
+
+extern "C" int32_t egn_pack_tables_bf16(const EgnConfig* c, const float* tables, void* tables_bf16, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!tables || !tables_bf16) return fail("null argument");
+    int e = egn_launch_pack_bf16(c, tables, tables_bf16, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_pack_tables_bf16", e) : 0;
 }
 
 extern "C" int32_t egn_unpack_table_grads(const EgnConfig* c, const float* d_tables, const EgnGrads* g, void* stream) {
@@ -157,7 +170,7 @@ static inline void mark(StageEvents* se, int i, cudaStream_t st) { if (se && se-
 
 static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays, int64_t n,
                                const float* z_vals, const EgnOutputs* out, void* workspace, cudaStream_t st,
-                               StageEvents* se) {
+                               StageEvents* se, bool save_feat) {
     EgnKernelCfg k = make_kcfg(c, tables);
     WsPlan w = plan_ws(c, n);
     char* base = (char*)workspace;
@@ -172,9 +185,17 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     if (z_vals && z_vals != z)
         if ((e = (int)cudaMemcpyAsync(z, z_vals, sizeof(float) * n * k.S, cudaMemcpyDeviceToDevice, st))) return cuda_fail("z copy", e);
     mark(se, 1, st);
-    if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
-    mark(se, 2, st);
-    if (c->shading <= EGN_SHADE_MLP) {
+    const bool fused = c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_BF16;
+    if (fused) {
+        // throughput mode: one warp-specialised kernel for gather + basis + MLP; the app feature is only written
+        // when a backward pass will read it (full training workspace)
+        if ((e = egn_launch_fused_fine(k, p, rays, n, z, fsig, save_feat ? feat : nullptr, rgbs, st))) return cuda_fail("fused fine pass", e);
+        mark(se, 2, st);
+    } else {
+        if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
+        mark(se, 2, st);
+    }
+    if (!fused && c->shading <= EGN_SHADE_MLP) {
         if (c->mlp_mode == EGN_MLP_FP32) e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st);
         else e = egn_launch_mlp_tc(k, p, rays, n, feat, rgbs, c->mlp_mode == EGN_MLP_TC_SPLIT, nullptr, st);
         if (e) return cuda_fail("mlp", e);
@@ -190,7 +211,7 @@ extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, co
                                       void* stream) {
     if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
     if (n <= 0) return 0;
-    return render_samples_impl(c, p, tables, rays, n, z_vals, out, workspace, (cudaStream_t)stream, nullptr);
+    return render_samples_impl(c, p, tables, rays, n, z_vals, out, workspace, (cudaStream_t)stream, nullptr, true);
 }
 
 static int render_forward_impl(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
@@ -201,7 +222,7 @@ static int render_forward_impl(const EgnConfig* c, const EgnParams* p, const flo
     mark(se, 0, st);
     int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z, st);
     if (e) return cuda_fail("egn_sample_rays", e);
-    return render_samples_impl(c, p, tables, rays, n, nullptr, out, workspace, st, se);
+    return render_samples_impl(c, p, tables, rays, n, nullptr, out, workspace, st, se, is_train != 0);
 }
 
 extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,

@@ -41,6 +41,10 @@ int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, l
 bool egn_mlp_tc_supported(const EgnKernelCfg& k);
 int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                       float* rgbs, int split, int* err_flag, cudaStream_t st);
+// fused fine pass (egn_fused.cu): gather + basis + MLP in one warp-specialised tcgen05 kernel (bf16 operands)
+int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                          float* fsig, float* feat_out, float* rgbs, cudaStream_t st);
+int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st);
 // backward
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,

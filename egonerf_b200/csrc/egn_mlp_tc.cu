@@ -17,15 +17,9 @@
 //
 // 256 threads: thread t owns row (t & 127) and column half (t >> 7) — warps w and w+4 share TMEM lane quadrant w & 3.
 // One elected thread issues the MMAs; completion comes back through tcgen05.commit -> mbarrier.
-#include <cuda_bf16.h>
-#include "egn_device.cuh"
+#include "egn_tc.cuh"
 #include "egn_host.h"
 
-#define TC_THREADS 256
-#define TC_TM 128
-#define TC_K1 160                      // 32 elements x 5 values
-#define TC_CHUNK 2048                  // bytes of one 8-wide K chunk of a 128-row operand
-#define TC_IDESC_128x128 0x08200490u   // kind::f16: D fp32, A/B bf16, both K-major, N = 128, M = 128
 
 // ---- shared-memory carve-up (bytes) --------------------------------------------------------------------------------
 template <bool SPLIT>
@@ -45,89 +39,6 @@ struct TcLayout {
     // layer-2 operand (16 chunks) never touches
     static constexpr int PART = A + 16 * TC_CHUNK;
 };
-
-// ---- PTX wrappers --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
-    // start address >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(TC_CHUNK >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-           (1ull << 46);
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-// bounded wait: a lost arrive must not hang the GPU — after ~2^28 polls the CTA flags an error and carries on
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return true;
-    }
-    return false;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); two values per 32-bit word, first value in the low half
-__device__ __forceinline__ uint32_t pack_hi(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
-    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
-    return pack_hi(a - ha, b - hb);
-}
-template <bool SPLIT>
-__device__ __forceinline__ void store_chunk(unsigned char* hi_base, unsigned char* lo_base, int chunk, int row, const float* v) {
-    uint4 h;
-    h.x = pack_hi(v[0], v[1]); h.y = pack_hi(v[2], v[3]); h.z = pack_hi(v[4], v[5]); h.w = pack_hi(v[6], v[7]);
-    *reinterpret_cast<uint4*>(hi_base + chunk * TC_CHUNK + row * 16) = h;
-    if (SPLIT) {
-        uint4 l;
-        l.x = pack_lo(v[0], v[1], h.x); l.y = pack_lo(v[2], v[3], h.y); l.z = pack_lo(v[4], v[5], h.z); l.w = pack_lo(v[6], v[7], h.w);
-        *reinterpret_cast<uint4*>(lo_base + chunk * TC_CHUNK + row * 16) = l;
-    }
-}
-__device__ __forceinline__ void store_elem(unsigned char* hi_base, unsigned char* lo_base, bool split, int row, int kk, float x) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const int off = (kk >> 3) * TC_CHUNK + row * 16 + (kk & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
-    if (split) *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = __float2bfloat16_rn(x - __bfloat162float(h));
-}
-
-// original input index (tensorBase.py:68-74 order) of our K position kk; -1 = padding; -2 = the constant-1 column that
-// carries the layer-1 bias (first value of the first padding element)
-__device__ __forceinline__ int tc_input_index(int kk, int AD) {
-    const int e = kk / 5, r = kk % 5;
-    if (e == AD + 3 && r == 0) return -2;
-    if (e >= AD + 3) return -1;
-    const int off_fs = AD + 3, off_fc = off_fs + 2 * AD, off_vs = off_fc + 2 * AD, off_vc = off_vs + 6;
-    if (e < AD) return r == 0 ? e : ((r & 1) ? off_fs : off_fc) + e * 2 + ((r - 1) >> 1);
-    const int d = e - AD;
-    return r == 0 ? AD + d : ((r & 1) ? off_vs : off_vc) + d * 2 + ((r - 1) >> 1);
-}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 1 : 2)

@@ -2,6 +2,7 @@
 // the 2x average-pooled density tables of the coarse pass (replaces EgoNeRF.update_coarse_sigma_grid,
 // models/EgoNeRF.py:124-133), and the inverse scatter of table gradients back to NCHW.
 #include "egn_device.cuh"
+#include <cuda_bf16.h>
 #include "egn_host.h"
 
 struct PackJob {
@@ -112,5 +113,20 @@ int egn_launch_unpack(const EgnConfig* cfg, const float* d_tables, const EgnGrad
     int n = fill_jobs(cfg, nullptr, grads, jobs, false);
     dim3 grid(148 * 2, n);
     egn_unpack_kernel<<<grid, 256, 0, st>>>(jobs, d_tables);
+    return (int)cudaGetLastError();
+}
+
+// bf16 copy of the fine sections (same element offsets) for the throughput-mode gather: one texel = 128 bytes
+__global__ void __launch_bounds__(256) egn_pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat162* __restrict__ dst, long long n4) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[t];
+        dst[2 * t] = __floats2bfloat162_rn(v.x, v.y);
+        dst[2 * t + 1] = __floats2bfloat162_rn(v.z, v.w);
+    }
+}
+int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st) {
+    const EgnLayout L = egn_make_layout(cfg->grid);
+    const long long n4 = L.pc[0][0] / 4;                    // the fine sections come first
+    egn_pack_bf16_kernel<<<148 * 4, 256, 0, st>>>(tables, reinterpret_cast<__nv_bfloat162*>(tables_bf16), n4);
     return (int)cudaGetLastError();
 }

@@ -39,6 +39,7 @@ class _VolumeRender(torch.autograd.Function):
     def forward(ctx, model, opts, rays, u_coarse, u_fine, z_vals, *params):
         lib = _lib.load()
         n = rays.shape[0]
+        tables = model._render_tables()          # (re)packs fp32 / bf16 tables if the parameters changed; before _config
         cfg = model._config(opts)
         S = lib.egn_samples_per_ray(cfg)
         has_env = cfg.env_h > 0
@@ -54,7 +55,6 @@ class _VolumeRender(torch.autograd.Function):
         out = _lib.EgnOutputs(rgb.data_ptr(), depth.data_ptr(), bg.data_ptr() if has_env else None,
                               env.data_ptr() if has_env else None, alpha.data_ptr())
         P = model._params_struct()
-        tables = model._render_tables()
         if z_vals is not None:
             if tuple(z_vals.shape) != (n, S):
                 raise ValueError(f"z_vals must be ({n}, {S})")
@@ -144,6 +144,9 @@ class EgoNeRF(torch.nn.Module):
         # arithmetic of the colour-decode MLP inside libegn_b200: "fp32" (exact FFMA), "tc_split" (tcgen05, 3-term bf16
         # split: fp32-equivalent) or "tc_bf16" (tcgen05, plain bf16).  Not a reference kwarg: set the attribute.
         self.mlp_mode = os.environ.get("EGN_MLP_MODE", "tc_split")
+        # "bf16": the fused fine pass of mlp_mode "tc_bf16" gathers from a bf16 copy of the render tables (half the bytes)
+        self.table_dtype = os.environ.get("EGN_TABLE_DTYPE", "f32")
+        self._tables_bf16 = None
 
     # ---- parameters (EgoNeRF.py:96-122) -------------------------------------------------------------
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
@@ -283,6 +286,13 @@ class EgoNeRF(torch.nn.Module):
                 self._tables = torch.empty_like(self._tables)     # saved-for-backward tables must not be overwritten
             _lib.check(lib.egn_pack_tables(cfg, self._params_struct(), self._tables.data_ptr(), _stream()))
             self._tables_key = key
+            self._tables_bf16 = None
+        if self.table_dtype == "bf16" and self.mlp_mode == "tc_bf16" and self._tables_bf16 is None:
+            lib = _lib.load()
+            cfg = self._config(None)
+            ne = int(lib.egn_table_bf16_elems(cfg))
+            self._tables_bf16 = torch.empty(ne, device=fp[0].device, dtype=torch.bfloat16)
+            _lib.check(lib.egn_pack_tables_bf16(cfg, self._tables.data_ptr(), self._tables_bf16.data_ptr(), _stream()))
         return self._tables
 
     def _config(self, opts):
@@ -297,6 +307,8 @@ class EgoNeRF(torch.nn.Module):
         cfg.fea2dense = _lib.ACT[self.fea2denseAct]
         tc_ok = self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
         cfg.mlp_mode = _lib.MLP_MODE[self.mlp_mode] if tc_ok else 0
+        use_bf16 = self.table_dtype == "bf16" and self.mlp_mode == "tc_bf16" and self._tables_bf16 is not None
+        cfg.tables_bf16 = self._tables_bf16.data_ptr() if use_bf16 else None
         cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0
         cfg.center[:] = co.center.cpu().tolist()
         cfg.near_plane = self.near_far[0]
@@ -430,6 +442,7 @@ class EgoNeRF(torch.nn.Module):
         lib = _lib.load()
         opts = dict(is_train=False, n_coarse=n_coarse, n_fine=n_fine if resampling else 0, resampling=bool(resampling),
                     use_coarse_sample=bool(use_coarse_sample))
+        tables = self._render_tables()
         cfg = self._config(opts)
         rays = rays_chunk.detach().contiguous().float()
         n, S, dev = rays.shape[0], lib.egn_samples_per_ray(cfg), rays.device
@@ -442,7 +455,7 @@ class EgoNeRF(torch.nn.Module):
         out = _lib.EgnOutputs(rgb.data_ptr(), depth.data_ptr(), _lib.ptr(bg), _lib.ptr(env), alpha.data_ptr())
         ms = (C.c_float * 4)()
         tot = [0.0] * 4
-        P, tables = self._params_struct(), self._render_tables()
+        P = self._params_struct()
         for _ in range(repeats):
             _lib.check(lib.egn_render_forward_timed(cfg, P, tables.data_ptr(), rays.data_ptr(), n, 0, None, None, 0, 0,
                                                     out, ws.data_ptr(), _stream(), ms))

@@ -30,7 +30,9 @@ extern "C" {
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
 /* TensorBase.feature2density (models/tensorBase.py:415-419) */
 enum { EGN_ACT_SOFTPLUS = 0, EGN_ACT_RELU = 1 };
-/* MLP arithmetic: exact fp32 FFMA, or tcgen05 tensor cores with a 3-term bf16 split (fp32-equivalent) */
+/* MLP arithmetic: EGN_MLP_FP32 exact fp32 FFMA; EGN_MLP_TC_SPLIT tcgen05 tensor cores with a 3-term bf16 split
+ * (fp32-equivalent, inside the 1e-4 parity bound); EGN_MLP_TC_BF16 throughput mode: gather + basis + MLP fused into one
+ * warp-specialised tcgen05 kernel with bf16 operands (PSNR-gated, not bit-parity) */
 enum { EGN_MLP_FP32 = 0, EGN_MLP_TC_SPLIT = 1, EGN_MLP_TC_BF16 = 2 };
 
 /* Static description of one model / scene.  Scalars mirror the constructor arguments of
@@ -60,6 +62,8 @@ typedef struct EgnConfig {
     const float* r_knots;     /* device, N_r+1 : reference r ladder of normalize_r (coordinates.py:118-124) */
     const float* z_coarse;    /* device, n_coarse : r schedule of sample_ray_exp WITHOUT near (EgoNeRF.py:69-76);
                                  the kernels add near_plane and, in train mode, the interval jitter (:78-82) */
+    const void*  tables_bf16; /* device, optional: bf16 copy of the fine render tables (egn_pack_tables_bf16), read by the
+                                 fused fine pass of EGN_MLP_TC_BF16 instead of the fp32 tables; NULL = gather from fp32 */
 } EgnConfig;
 
 /* Parameters in the REFERENCE layout (contiguous NCHW fp32, shapes of EgoNeRF.init_one_svd,
@@ -112,6 +116,9 @@ int32_t egn_samples_per_ray(const EgnConfig* cfg);
  * re-run whenever the parameters change (once per optimiser step in training). */
 int64_t egn_table_floats(const EgnConfig* cfg);
 int32_t egn_pack_tables(const EgnConfig* cfg, const EgnParams* params, float* tables /*device*/, void* stream);
+/* bf16 copy of the fine sections (same element offsets; egn_table_bf16_elems elements of 2 bytes) for the throughput mode */
+int64_t egn_table_bf16_elems(const EgnConfig* cfg);
+int32_t egn_pack_tables_bf16(const EgnConfig* cfg, const float* tables /*device*/, void* tables_bf16 /*device*/, void* stream);
 /* inverse scatter for training: writes d(tables) (table layout) into the reference-layout factor grads
  * (overwrites grads->{density,app}_{plane,line}; the other members are untouched) */
 int32_t egn_unpack_table_grads(const EgnConfig* cfg, const float* d_tables /*device*/, const EgnGrads* grads,

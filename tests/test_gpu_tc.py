@@ -80,3 +80,24 @@ def test_tc_ragged_tile_and_many_tiles():
         with torch.no_grad():
             outs[mode] = model(rays, is_train=False, **kw)[0]
     assert (outs["fp32"] - outs["tc_split"]).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("tables", ["f32", "bf16"])
+@pytest.mark.parametrize("name", ["render_tiny_eval", "render_tiny_env_eval", "render_128_eval", "render_300_eval"])
+def test_fused_fine_pass_is_psnr_safe(name, tables):
+    """EGN_MLP_TC_BF16 = gather + basis + MLP fused into one warp-specialised tcgen05 kernel (bf16 operands; optionally
+    bf16 tables): bounded against the exact fp32 render of the same scene."""
+    model, okw, g = _model(name)
+    ref = _render(model, g, okw, "fp32")
+    model.table_dtype = tables
+    out = _render(model, g, okw, "tc_bf16")
+    model.table_dtype = "f32"
+    d = (out[0] - ref[0]).abs().max().item()
+    da = (out[4] - ref[4]).abs().max().item()
+    mse = ((out[0] - ref[0]) ** 2).mean().item()
+    psnr_between = -10 * np.log10(max(mse, 1e-20))
+    print(f"{name} fused/{tables}: rgb Linf {d:.2e}, alpha Linf {da:.2e}, PSNR between the renders {psnr_between:.1f} dB")
+    assert d <= (3e-2 if tables == "bf16" else 5e-3)
+    assert psnr_between >= (45.0 if tables == "bf16" else 55.0)
+    if tables == "f32":
+        assert da <= 1e-5          # the density path of the fused kernel is fp32 end to end
