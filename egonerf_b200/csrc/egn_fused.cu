@@ -42,16 +42,7 @@ static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared me
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-// one lane's share of a tap, kept as loaded (4 registers): 8 bf16 channels or 4 fp32 channels; zero outside the grid
-template <bool BF16>
-__device__ __forceinline__ uint4 load_tap(const void* __restrict__ tab, long long elem_off, bool valid) {
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (valid) {
-        if constexpr (BF16) q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(tab) + elem_off));
-        else q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(tab) + elem_off));
-    }
-    return q;
-}
+// one lane's share of a tap is kept as loaded (4 registers): 8 bf16 channels or 4 fp32 channels
 template <bool BF16>
 __device__ __forceinline__ float tap_val(const uint4& q, int ch) {
     if constexpr (BF16) {
@@ -96,39 +87,45 @@ __device__ __forceinline__ void fused_gather_rows(const EgnKernelCfg& k, const v
         c[1] = __shfl_sync(FULL, cc.c[1], src);
         c[2] = __shfl_sync(FULL, cc.c[2], src);
         const int yang = __shfl_sync(FULL, cc.yang, src);
-        int i0[3];
-        float fr[3];
+        // per axis: clamped texel indices and tap weights with the zero padding of F.grid_sample folded in — an
+        // out-of-range tap gets weight 0 and reads a clamped in-range texel, so every load is unconditional
+        unsigned j0[3], j1[3];
+        float wa0[3], wa1[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float ix = egn_unnorm(c[a], k.lay.G[a]);
+            const int G = k.lay.G[a];
+            const float ix = egn_unnorm(c[a], G);
             const float fl = floorf(ix);
-            fr[a] = ix - fl;
-            i0[a] = (int)fminf(fmaxf(fl, -2.f), (float)k.lay.G[a] + 1.f);
+            const float fr = ix - fl;
+            const int i0 = (int)fminf(fmaxf(fl, -2.f), (float)G + 1.f);
+            wa0[a] = ((i0 >= 0) & (i0 < G)) ? 1.f - fr : 0.f;
+            wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G)) ? fr : 0.f;
+            j0[a] = (unsigned)min(max(i0, 0), G - 1);
+            j1[a] = (unsigned)min(max(i0 + 1, 0), G - 1);
         }
+        constexpr unsigned ES = BF16 ? 2u : 4u;                 // bytes per table element
+        const char* tabc = reinterpret_cast<const char*>(tab);
         uint4 t[3][4], l[3][2];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
-            const int W = k.lay.G[ax], H = k.lay.G[ay], L = k.lay.G[al];
-            const int x0 = i0[ax], y0 = i0[ay], q0 = i0[al];
-            const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
-            const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
-            const long long po = k.lay.pf[yang][i] + ((long long)y0 * W + x0) * EGN_CF + sub * NCH;
-            t[i][0] = load_tap<BF16>(tab, po, vx0 & vy0);
-            t[i][1] = load_tap<BF16>(tab, po + EGN_CF, vx1 & vy0);
-            t[i][2] = load_tap<BF16>(tab, po + (long long)W * EGN_CF, vx0 & vy1);
-            t[i][3] = load_tap<BF16>(tab, po + (long long)W * EGN_CF + EGN_CF, vx1 & vy1);
-            const long long lo = k.lay.lf[yang][i] + (long long)q0 * EGN_CF + sub * NCH;
-            l[i][0] = load_tap<BF16>(tab, lo, (q0 >= 0) & (q0 < L));
-            l[i][1] = load_tap<BF16>(tab, lo + EGN_CF, (q0 + 1 >= 0) & (q0 + 1 < L));
+            const unsigned W = (unsigned)k.lay.G[ax];
+            const unsigned pbase = (unsigned)k.lay.pf[yang][i] + sub * NCH, lbase = (unsigned)k.lay.lf[yang][i] + sub * NCH;
+            const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
+            t[i][0] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (ra + j0[ax]) * EGN_CF) * ES));
+            t[i][1] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (ra + j1[ax]) * EGN_CF) * ES));
+            t[i][2] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (rb + j0[ax]) * EGN_CF) * ES));
+            t[i][3] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (rb + j1[ax]) * EGN_CF) * ES));
+            l[i][0] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(lbase + j0[al] * EGN_CF) * ES));
+            l[i][1] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(lbase + j1[al] * EGN_CF) * ES));
         }
         float f = 0.f;
         const int row = row0 + src;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const float fx = fr[egn_mx(i)], fy = fr[egn_my(i)], fq = fr[egn_vl(i)];
-            const float gx = 1.f - fx, gy = 1.f - fy;
-            const float w0 = gx * gy, w1 = fx * gy, w2 = gx * fy, w3 = fx * fy, u0 = 1.f - fq;
+            const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+            const float w0 = wa0[ax] * wa0[ay], w1 = wa1[ax] * wa0[ay], w2 = wa0[ax] * wa1[ay], w3 = wa1[ax] * wa1[ay];
+            const float u0 = wa0[al], u1 = wa1[al];
             float prod[NCH];
             float s = 0.f;
 #pragma unroll
@@ -137,7 +134,7 @@ __device__ __forceinline__ void fused_gather_rows(const EgnKernelCfg& k, const v
                 P = fmaf(w1, tap_val<BF16>(t[i][1], ch), P);
                 P = fmaf(w2, tap_val<BF16>(t[i][2], ch), P);
                 P = fmaf(w3, tap_val<BF16>(t[i][3], ch), P);
-                const float Lv = fmaf(fq, tap_val<BF16>(l[i][1], ch), u0 * tap_val<BF16>(l[i][0], ch));
+                const float Lv = fmaf(u1, tap_val<BF16>(l[i][1], ch), u0 * tap_val<BF16>(l[i][0], ch));
                 prod[ch] = P * Lv;
                 s += prod[ch];
             }

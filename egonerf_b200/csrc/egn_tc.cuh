@@ -36,10 +36,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // bounded wait: a lost arrive must not hang the GPU — after ~2^28 polls the CTA flags an error and carries on
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return true;
+        if (spin > 4) __nanosleep(spin > 64 ? 256 : 32);          // back off: a spinning warp steals issue slots from the working ones
     }
     return false;
 }
