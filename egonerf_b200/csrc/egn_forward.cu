@@ -17,45 +17,48 @@ template <int C>
 __device__ __forceinline__ void egn_gather_products(const float* __restrict__ tab, const long long pofs[3],
                                                     const long long lofs[3], const int G[3], const float c[3],
                                                     int sub, float4 prod[3]) {
-    int i0[3];
-    float fr[3];
+    // per axis: clamped texel indices and tap weights with the zero padding folded in — an out-of-range tap gets
+    // weight 0 and reads a clamped in-range texel, so every load is unconditional (no predication, no divergence);
+    // the arithmetic on in-range taps is unchanged
+    unsigned j0[3], j1[3];
+    float wa0[3], wa1[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float ix = egn_unnorm(c[a], G[a]);
-        float fl = floorf(ix);
-        fr[a] = ix - fl;
+        const float ix = egn_unnorm(c[a], G[a]);
+        const float fl = floorf(ix);
+        const float fr = ix - fl;
         // clamp before the int conversion so far-out-of-range samples stay "invalid" instead of wrapping
-        i0[a] = (int)fminf(fmaxf(fl, -2.f), (float)G[a] + 1.f);
+        const int i0 = (int)fminf(fmaxf(fl, -2.f), (float)G[a] + 1.f);
+        wa0[a] = ((i0 >= 0) & (i0 < G[a])) ? 1.f - fr : 0.f;
+        wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G[a])) ? fr : 0.f;
+        j0[a] = (unsigned)min(max(i0, 0), G[a] - 1);
+        j1[a] = (unsigned)min(max(i0 + 1, 0), G[a] - 1);
     }
     float4 t[3][4], l[3][2];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
-        const int W = G[ax], H = G[ay], L = G[al];
-        const int x0 = i0[ax], y0 = i0[ay], q0 = i0[al];
-        const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
-        const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
-        const float* pb = tab + pofs[i] + ((long long)y0 * W + x0) * C + sub * 4;
-        t[i][0] = (vx0 & vy0) ? ldg4(pb) : f4zero();
-        t[i][1] = (vx1 & vy0) ? ldg4(pb + C) : f4zero();
-        t[i][2] = (vx0 & vy1) ? ldg4(pb + (long long)W * C) : f4zero();
-        t[i][3] = (vx1 & vy1) ? ldg4(pb + (long long)W * C + C) : f4zero();
-        const float* lb = tab + lofs[i] + (long long)q0 * C + sub * 4;
-        l[i][0] = (q0 >= 0 && q0 < L) ? ldg4(lb) : f4zero();
-        l[i][1] = (q0 + 1 >= 0 && q0 + 1 < L) ? ldg4(lb + C) : f4zero();
+        const unsigned W = (unsigned)G[ax];
+        const unsigned pbase = (unsigned)pofs[i] + sub * 4, lbase = (unsigned)lofs[i] + sub * 4;
+        const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
+        t[i][0] = ldg4(tab + (size_t)(pbase + (ra + j0[ax]) * C));
+        t[i][1] = ldg4(tab + (size_t)(pbase + (ra + j1[ax]) * C));
+        t[i][2] = ldg4(tab + (size_t)(pbase + (rb + j0[ax]) * C));
+        t[i][3] = ldg4(tab + (size_t)(pbase + (rb + j1[ax]) * C));
+        l[i][0] = ldg4(tab + (size_t)(lbase + j0[al] * C));
+        l[i][1] = ldg4(tab + (size_t)(lbase + j1[al] * C));
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float fx = fr[egn_mx(i)], fy = fr[egn_my(i)], fq = fr[egn_vl(i)];
-        const float gx = 1.f - fx, gy = 1.f - fy;
+        const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
         float4 P = f4zero();
-        P = f4fma(gx * gy, t[i][0], P);
-        P = f4fma(fx * gy, t[i][1], P);
-        P = f4fma(gx * fy, t[i][2], P);
-        P = f4fma(fx * fy, t[i][3], P);
+        P = f4fma(wa0[ax] * wa0[ay], t[i][0], P);
+        P = f4fma(wa1[ax] * wa0[ay], t[i][1], P);
+        P = f4fma(wa0[ax] * wa1[ay], t[i][2], P);
+        P = f4fma(wa1[ax] * wa1[ay], t[i][3], P);
         float4 Lv = f4zero();
-        Lv = f4fma(1.f - fq, l[i][0], Lv);
-        Lv = f4fma(fq, l[i][1], Lv);
+        Lv = f4fma(wa0[al], l[i][0], Lv);
+        Lv = f4fma(wa1[al], l[i][1], Lv);
         prod[i] = f4mul(P, Lv);
     }
 }
