@@ -69,7 +69,7 @@ __device__ __forceinline__ void egn_gather_products(const float* __restrict__ ta
 #define K1_WARPS 8
 #define K1_MAXC 256
 
-__global__ void __launch_bounds__(K1_WARPS * 32)
+__global__ void __launch_bounds__(K1_WARPS * 32, 2)
 egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ rays, long long n, int is_train,
                   const float* __restrict__ u_c, const float* __restrict__ u_f, unsigned long long seed,
                   long long ray0, float near_plane, float* __restrict__ z_out) {
@@ -226,29 +226,46 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             zn[i] = b0 + tt * (b1 - b0);
         }
         __syncwarp();
-        // ---- 6. sort(cat(coarse, new)) (EgoNeRF.py:536-539) as a rank sort; ties broken by position ----
+        // ---- 6. sort(cat(coarse, new)) (EgoNeRF.py:536-539).  Only the sorted VALUES are observable, so: the coarse
+        // depths are already increasing (monotone schedule; the jitter stays inside its own interval), the fine draws are
+        // rank-sorted among themselves (ties broken by position), and the two sorted lists are merged by binary search:
+        // position = own rank + number of elements of the other list that come first. ----
         const int na = k.use_coarse_sample ? nc : 0;
         const int S = na + nf;
-        float v[2 * K1_MAXC / 32];
-        int rk[2 * K1_MAXC / 32];
-        const int E = S >> 5;
+        const int EF = nf >> 5;
+        float vf[K1_MAXC / 32];
+        int rf[K1_MAXC / 32];
 #pragma unroll
-        for (int e = 0; e < 2 * K1_MAXC / 32; ++e) {
-            rk[e] = 0;
-            if (e < E) { const int a = e * 32 + lane; v[e] = (a < na) ? zc[a] : zn[a - na]; }
-            else v[e] = 0.f;
+        for (int e = 0; e < K1_MAXC / 32; ++e) {
+            rf[e] = 0;
+            vf[e] = (e < EF) ? zn[e * 32 + lane] : 0.f;
         }
-        for (int b = 0; b < S; ++b) {
-            const float vb = (b < na) ? zc[b] : zn[b - na];
+        for (int b = 0; b < nf; ++b) {
+            const float vb = zn[b];
 #pragma unroll
-            for (int e = 0; e < 2 * K1_MAXC / 32; ++e) {
-                const int a = e * 32 + lane;
-                rk[e] += (vb < v[e]) || (vb == v[e] && b < a);
+            for (int e = 0; e < K1_MAXC / 32; ++e)
+                if (e < EF) rf[e] += (vb < vf[e]) || (vb == vf[e] && b < e * 32 + lane);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < K1_MAXC / 32; ++e)
+            if (e < EF) sw[rf[e]] = vf[e];          // sw (the cdf) is dead: it now holds the fine draws in increasing order
+        __syncwarp();
+        float* zo = z_out + ray * S;
+#pragma unroll
+        for (int e = 0; e < K1_MAXC / 32; ++e) {
+            if (e < EF) {                            // fine element: coarse depths <= it come first
+                int lo = 0, hi = na;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= vf[e]) lo = mid + 1; else hi = mid; }
+                zo[rf[e] + lo] = vf[e];
             }
         }
-#pragma unroll
-        for (int e = 0; e < 2 * K1_MAXC / 32; ++e)
-            if (e < E) z_out[ray * S + rk[e]] = v[e];
+        for (int i = lane; i < na; i += 32) {        // coarse element: fine draws strictly below it come first
+            const float v = zc[i];
+            int lo = 0, hi = nf;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sw[mid] < v) lo = mid + 1; else hi = mid; }
+            zo[i + lo] = v;
+        }
         __syncwarp();
     }
 }
