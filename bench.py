@@ -19,6 +19,8 @@ across ranks with the parameters replicated (weak scaling: every rank renders `r
 box; the oracle is pinned to it by tests/golden).  Nothing here reads /root/reference.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import sys
@@ -42,7 +44,8 @@ N_COARSE, N_FINE = 128, 128
 
 
 def algorithmic_bytes_per_ray(S, n_coarse, elem=4, env=False):
-    """SURVEY.md §8(d) tap model: every bilinear/linear tap reads C contiguous elements."""
+    """SURVEY.md §8(d) tap model: every bilinear/linear tap reads C contiguous elements of `elem` bytes
+    (1 328 168 B/ray fp32, 664 616 B/ray bf16 at 128 coarse + 256 fine samples)."""
     io = 24 + 16 + 4 * S + (28 + 48 if env else 0)
     return elem * (n_coarse * 288 + S * 1152) + io
 
@@ -138,8 +141,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tables", default="f32", choices=["f32", "bf16"], help="dtype of the fine render tables (bf16 needs --mlp tc_bf16)")
-    ap.add_argument("--mlp", default="tc_split", choices=["fp32", "tc_split", "tc_bf16"],
+    ap.add_argument("--no-parity-line", action="store_true", help="skip the extra fp32-parity-mode measurement")
+    ap.add_argument("--tables", default="bf16", choices=["f32", "bf16"], help="dtype of the fine render tables (bf16 needs --mlp tc_bf16)")
+    ap.add_argument("--mlp", default="tc_bf16", choices=["fp32", "tc_split", "tc_bf16"],
                     help="arithmetic of the colour-decode MLP: exact fp32 FFMA, tcgen05 3-term bf16 split (fp32-equivalent), tcgen05 bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -264,8 +268,6 @@ def main():
         return ms
 
     # the volume_renderer mirror prints the reference's "elapsed time per image" line (renderer.py:75): keep stdout clean
-    import contextlib
-    import io
     with contextlib.redirect_stdout(io.StringIO()):
         sampler = ClockSampler(dev)
         ms = timed(step_device, args.steps, args.warmup, sampler)
@@ -282,26 +284,51 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    stage_names = ["sampler(coarse+cdf+sort)", "fine_gather+basis", "mlp_decode", "composite"]
-    stage_alg_bytes = [n_rays * (N_COARSE * 288 * 4 + 24 + 4 * S), n_rays * (S * 1152 * 4 + 4 * S),
+    fused = args.mlp == "tc_bf16"
+    elem = 2 if (fused and args.tables == "bf16") else 4
+    env = scene.emission is not None
+    stage_names = ["sampler(coarse+cdf+sort)", "fused fine pass: gather+basis+mlp (egn_fused_fine_kernel)" if fused else
+                   "fine_gather+basis (egn_gather_kernel)", "mlp_decode", "composite"]
+    # algorithmic bytes per stage (tap model): coarse taps 288 values, fine taps 1152 values per sample
+    stage_alg_bytes = [n_rays * (N_COARSE * 288 * 4 + 24 + 4 * S), n_rays * (S * 1152 * elem + 4 * S + (12 * S if fused else 0)),
                        n_rays * S * (28 + 3) * 4, n_rays * (S * (4 + 4 + 12) + 16 + 4 * S)]
     stage_ms = model.stage_times(rays_dev, repeats=max(3, min(args.steps, 10)), **kw)
     dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
     achieved = stage_alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    b_ray = algorithmic_bytes_per_ray(S, N_COARSE, elem, env)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full captures
+    if os.path.isfile(tpath):
+        rec = json.load(open(tpath)).get(f"{args.workload}:{args.mlp}:{args.tables}:{stage_names[dom].split(' (')[0].split(':')[0]}")
+        if rec and rec.get("rays") == n_rays:
+            traffic = rec["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "algorithmic (tap-model) bytes; the 99 MB (fp32) / 49 MB (bf16) factor tables are L2-resident, so most "
+                        "of these bytes are served by L2, not HBM — see traffic (ncu dram bytes) and profiles/",
                 "stage_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
-                "whole_path": {"bytes_per_ray": algorithmic_bytes_per_ray(S, N_COARSE, 4, scene.emission is not None),
-                               "achieved": value / world * algorithmic_bytes_per_ray(S, N_COARSE, 4, scene.emission is not None) / 1e9,
-                               "frac": value / world * algorithmic_bytes_per_ray(S, N_COARSE, 4, scene.emission is not None) / 1e9 / peak}}
+                "whole_path": {"bytes_per_ray": b_ray, "achieved": value / world * b_ray / 1e9,
+                               "frac": value / world * b_ray / 1e9 / peak}}
 
+    dtype = {"fp32": "f32", "tc_split": "f32 (tensor-core MLP, 3-term bf16 split, fp32-equivalent)",
+             "tc_bf16": "bf16 MMA operands, fp32 accumulate; " + ("bf16" if args.tables == "bf16" else "f32") + " tables; f32 density/compositing"}[args.mlp]
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mlp != "tc_bf16" else "f32 tables + bf16 MLP", "data": "synthetic", "config": config, "clocks": clocks,
+            "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
                     "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world},
             "gpu_launches": (model.launches_per_forward() if not train else model.launches_per_train_step(n_rays)) * args.steps,
             "roofline": roofline}
+    # the same workload in the fp32-parity mode (fp32 tables, tensor-core MLP with the 3-term split), reported alongside
+    if fused and not args.no_parity_line:
+        model.mlp_mode, model.table_dtype = "tc_split", "f32"
+        with contextlib.redirect_stdout(io.StringIO()):
+            ms_p = timed(step_device, max(3, args.steps // 2), 3)
+        st_p = model.stage_times(rays_dev, repeats=3, **kw)
+        line["parity_mode"] = {"value": n_rays * world * max(3, args.steps // 2) / (ms_p * 1e-3), "unit": "rays/s",
+                               "dtype": "f32 tables, tcgen05 MLP with 3-term bf16 split (rgb within 1e-4 of the reference)",
+                               "stage_ms": dict(zip(["sampler", "gather+basis", "mlp", "composite"], [round(x, 4) for x in st_p]))}
+        model.mlp_mode, model.table_dtype = args.mlp, args.tables
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             rps, _ = oracle_rays_per_s(scene, args.cpu_rays, 3, 1)

@@ -417,7 +417,10 @@ class EgoNeRF(torch.nn.Module):
     # ---- measurement hooks (bench.py) ------------------------------------------------------------------
     def launches_per_forward(self):
         """Kernels of libegn_b200 launched by one `forward` (sampler, gather, [MLP], composite)."""
-        return 4 if isinstance(self.renderModule, torch.nn.Module) else 3
+        if not isinstance(self.renderModule, torch.nn.Module):
+            return 3
+        fused = self.mlp_mode == "tc_bf16" and self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
+        return 3 if fused else 4
 
     def launches_per_train_step(self, n_rays):
         """forward + backward (composite, per-sub-chunk MLP chain, gather) + gradient unpack + table re-pack."""

@@ -1,5 +1,3 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline --mlp tc_bf16 --tables bf16 > gpurun_out/b1.json 2> gpurun_out/b1.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/b1.json').read().strip().splitlines()[-1]); print(round(d['value']), d['ms_per_step'], d['roofline']['stage_ms'], round(d['e2e']['value']))"
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
+ncu --set full --clock-control none --import-source on -k regex:egn_fused -s 3 -c 1 -o gpurun_out/prof_fused_bf16_65536 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-line > gpurun_out/ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/launches_fused.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-parity-line > gpurun_out/ncu2.log 2>&1
