@@ -123,7 +123,7 @@ static WsPlan plan_ws(const EgnConfig* c, long long n) {
     w.z = take(M); w.fsig = take(M); w.feat = take(M * EGN_FEAT_STRIDE); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n);
     w.rgbpre = take(n * 3);
     w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
-    const bool mlp = c->shading <= EGN_SHADE_MLP;
+    const bool mlp = c->shading <= EGN_SHADE_MLP && c->mlp_mode != EGN_MLP_TC_BF16;   // the tcgen05 backward needs no scratch
     const long long Ms = (n < EGN_BWD_SUB_RAYS ? n : EGN_BWD_SUB_RAYS) * S;
     w.h1 = take(mlp ? Ms * EGN_HID : 0); w.h2 = take(mlp ? Ms * EGN_HID : 0);
     w.dz1 = take(mlp ? Ms * EGN_HID : 0); w.dz2 = take(mlp ? Ms * EGN_HID : 0);
@@ -284,7 +284,9 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
     int e;
     if ((e = egn_launch_composite_bwd(k, p, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs,
                                       d_fsig, d_feat, g->emission, st))) return cuda_fail("composite backward", e);
-    if (mlp) {
+    if (mlp && c->mlp_mode == EGN_MLP_TC_BF16) {
+        if ((e = egn_launch_mlp_bwd_tc(k, p, rays, n, feat, rgbs, d_rgbs, d_feat, g, st))) return cuda_fail("mlp backward (tcgen05)", e);
+    } else if (mlp) {
         float* h1 = (float*)(base + w.h1); float* h2 = (float*)(base + w.h2);
         float* dz1 = (float*)(base + w.dz1); float* dz2 = (float*)(base + w.dz2);
         for (long long r0 = 0; r0 < n; r0 += EGN_BWD_SUB_RAYS) {

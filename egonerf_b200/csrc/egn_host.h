@@ -54,6 +54,9 @@ int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const fl
 int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                        const float* rgbs, const float* d_rgbs, float* d_feat, float* h1, float* h2, float* dz1,
                        float* dz2, const EgnGrads* g, cudaStream_t st);
+// tensor-core MLP backward of the whole chunk (throughput mode): no scratch, weight gradients accumulated in TMEM
+int egn_launch_mlp_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
+                          const float* rgbs, const float* d_rgbs, float* d_feat, const EgnGrads* g, cudaStream_t st);
 int egn_launch_mlp_save(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                         float* h1, float* h2, cudaStream_t st);
 int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,

@@ -1,3 +1,9 @@
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
-ncu --set full --clock-control none --import-source on -k regex:egn_fused -s 3 -c 1 -o gpurun_out/prof_fused_bf16_65536 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-line > gpurun_out/ncu1.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/launches_fused.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-parity-line > gpurun_out/ncu2.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -s -k "backward" 2>&1 | grep -E "passed|failed|tc backward|Error|error|assert|\{" | tail -6
+for m in "--mlp tc_bf16 --tables bf16" "--mlp tc_split --tables f32"; do
+python bench.py --mode train --rays 16384 --steps 5 --no-cpu-baseline --no-parity-line $m > gpurun_out/bt.json 2> gpurun_out/bt.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/bt.json').read().strip().splitlines()[-1]); print('$m', round(d['value']), d['ms_per_step'], round(d['e2e']['value']))"
+tail -2 gpurun_out/bt.err
+done
+ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv --log-file gpurun_out/launches_train2.csv python bench.py --mode train --steps 2 --warmup 3 --no-cpu-baseline --no-parity-line --rays 16384 > gpurun_out/ncu_bench.log 2>&1
