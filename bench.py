@@ -39,8 +39,10 @@ WORKLOADS = {
                  rays=65536, scene={}),
     "cfg3": dict(desc="Ricoh360-shape synthetic, 300^3 grid + envmap h=1920, 16384 rays/GPU", n_voxels=27e6, rays=16384,
                  scene=dict(near_far=(0.1, 300.), r0=0.05, density_shift=-10., envmap_h=1920)),
+    "cfg5": dict(desc="one 256-row tile (1 048 576 rays / GPU) of a 4096x2048 ERP frame, 256 coarse + 512 fine samples/ray, "
+                      "rendered in chunks of 65536 rays", n_voxels=27e6, rays=256 * 4096, scene={}, n_coarse=256, n_fine=256,
+                 kind="erp", chunk=65536),
 }
-N_COARSE, N_FINE = 128, 128
 
 
 def algorithmic_bytes_per_ray(S, n_coarse, elem=4, env=False):
@@ -110,7 +112,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def oracle_rays_per_s(scene, n_rays, repeats, warmup, seed=5):
+def oracle_rays_per_s(scene, n_rays, repeats, warmup, seed=5, N_COARSE=128, N_FINE=128):
     """CPU port of the reference path (checker code, used here only as the reported CPU baseline)."""
     import torch
     from oracle import egn_oracle as O
@@ -153,6 +155,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
     n_rays = args.rays or wl["rays"]
+    N_COARSE, N_FINE = wl.get("n_coarse", 128), wl.get("n_fine", 128)
+    chunk = min(wl.get("chunk", n_rays), n_rays)
     S = N_COARSE + N_FINE
     config = {"workload": wl["desc"], "rays_per_gpu_per_step": n_rays, "samples_per_ray": f"{N_COARSE} coarse + {S} fine",
               "mode": args.mode, "sharding": f"rays x{world}, grid replicated", "l2": "inputs exceed L2 (factor tables "
@@ -168,7 +172,7 @@ def main():
             return
         scene = make_scene(n_voxels=wl["n_voxels"], **wl["scene"])
         per_step = 512
-        rps, sec = oracle_rays_per_s(scene, per_step, args.steps, args.warmup)
+        rps, sec = oracle_rays_per_s(scene, per_step, args.steps, args.warmup, N_COARSE=N_COARSE, N_FINE=N_FINE)
         line = {"impl": "reference", "metric": metric, "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -198,10 +202,14 @@ def main():
     model.table_dtype = args.tables
     config["mlp"] = args.mlp
     config["tables"] = args.tables
-    rays_host = make_rays(n_rays, 'isotropic', seed=1000 + rank).pin_memory()
+    if wl.get("kind") == "erp":          # this rank's row tile of the 2048 x 4096 equirect frame (ray_utils.py:24-40)
+        rays_host = make_rays(n_rays, 'erp', erp_hw=(2048, 4096), row0=(rank * (n_rays // 4096)) % 2048).pin_memory()
+    else:
+        rays_host = make_rays(n_rays, 'isotropic', seed=1000 + rank).pin_memory()
     rays_dev = rays_host.to(dev)
     ray0 = rank * n_rays
     kw = dict(RENDER_KW)
+    kw.update(n_coarse=N_COARSE, n_fine=N_FINE)
     train = args.mode == "train"
     if train:
         target = torch.rand(n_rays, 3, device=dev)
@@ -210,7 +218,9 @@ def main():
     def step_device():
         if not train:
             with torch.no_grad():
-                return model(rays_dev, is_train=False, ray_index0=ray0, **kw)[0]
+                for c0 in range(0, n_rays, chunk):
+                    out = model(rays_dev[c0:c0 + chunk], is_train=False, ray_index0=ray0 + c0, **kw)[0]
+                return out
         for p in params:
             p.grad = None
         rgb = model(rays_dev, is_train=True, seed=1234, ray_index0=ray0, **kw)[0]
@@ -227,7 +237,7 @@ def main():
     def step_e2e():
         if not train:
             with torch.no_grad():
-                rgb, depth, _, _, _ = volume_renderer(rays_host, model, chunk=n_rays, is_train=False, device=dev, **kw)
+                rgb, depth, _, _, _ = volume_renderer(rays_host, model, chunk=chunk, is_train=False, device=dev, **kw)
             out_rgb.copy_(rgb, non_blocking=True)
             out_depth.copy_(depth, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -292,7 +302,8 @@ def main():
     # algorithmic bytes per stage (tap model): coarse taps 288 values, fine taps 1152 values per sample
     stage_alg_bytes = [n_rays * (N_COARSE * 288 * 4 + 24 + 4 * S), n_rays * (S * 1152 * elem + 4 * S + (12 * S if fused else 0)),
                        n_rays * S * (28 + 3) * 4, n_rays * (S * (4 + 4 + 12) + 16 + 4 * S)]
-    stage_ms = model.stage_times(rays_dev, repeats=max(3, min(args.steps, 10)), **kw)
+    stage_ms = model.stage_times(rays_dev[:chunk], repeats=max(3, min(args.steps, 10)), **kw)
+    stage_ms = [x * (n_rays / chunk) for x in stage_ms]
     dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
     achieved = stage_alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
     b_ray = algorithmic_bytes_per_ray(S, N_COARSE, elem, env)
@@ -317,21 +328,21 @@ def main():
             "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
                     "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world},
-            "gpu_launches": (model.launches_per_forward() if not train else model.launches_per_train_step(n_rays)) * args.steps,
+            "gpu_launches": (model.launches_per_forward() * (-(-n_rays // chunk)) if not train else model.launches_per_train_step(n_rays)) * args.steps,
             "roofline": roofline}
     # the same workload in the fp32-parity mode (fp32 tables, tensor-core MLP with the 3-term split), reported alongside
     if fused and not args.no_parity_line:
         model.mlp_mode, model.table_dtype = "tc_split", "f32"
         with contextlib.redirect_stdout(io.StringIO()):
             ms_p = timed(step_device, max(3, args.steps // 2), 3)
-        st_p = model.stage_times(rays_dev, repeats=3, **kw)
+        st_p = [x * (n_rays / chunk) for x in model.stage_times(rays_dev[:chunk], repeats=3, **kw)]
         line["parity_mode"] = {"value": n_rays * world * max(3, args.steps // 2) / (ms_p * 1e-3), "unit": "rays/s",
                                "dtype": "f32 tables, tcgen05 MLP with 3-term bf16 split (rgb within 1e-4 of the reference)",
                                "stage_ms": dict(zip(["sampler", "gather+basis", "mlp", "composite"], [round(x, 4) for x in st_p]))}
         model.mlp_mode, model.table_dtype = args.mlp, args.tables
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            rps, _ = oracle_rays_per_s(scene, args.cpu_rays, 3, 1)
+            rps, _ = oracle_rays_per_s(scene, args.cpu_rays, 3, 1, N_COARSE=N_COARSE, N_FINE=N_FINE)
             line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{args.cpu_rays} rays of the same scene x 3 repeats, eval forward, "
                                               f"torch CPU fp32 ({os.cpu_count()} threads)"}

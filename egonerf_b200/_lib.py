@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -63,14 +63,14 @@ PROTOTYPES = {
     "egn_workspace_bytes_eval": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),
     "egn_render_forward": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64,
-                                       C.POINTER(EgnOutputs), C.c_void_p, C.c_void_p]),
+                                       C.POINTER(EgnOutputs), C.c_void_p, C.c_int32, C.c_void_p]),
     "egn_render_forward_timed": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p,
                                              C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64,
                                              C.POINTER(EgnOutputs), C.c_void_p, C.c_void_p, c_float_p]),
     "egn_sample_rays": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "egn_render_samples": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
-                                       C.c_void_p, C.POINTER(EgnOutputs), C.c_void_p, C.c_void_p]),
+                                       C.c_void_p, C.POINTER(EgnOutputs), C.c_void_p, C.c_int32, C.c_void_p]),
     "egn_render_backward": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(EgnGrads), C.c_void_p]),

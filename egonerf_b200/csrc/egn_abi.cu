@@ -113,15 +113,19 @@ extern "C" int32_t egn_unpack_table_grads(const EgnConfig* c, const float* d_tab
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
 #define EGN_BWD_SUB_RAYS 4096
-struct WsPlan { long long z, fsig, feat, rgbs, wgt, bgw, rgbpre, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, total; };
+struct WsPlan { long long z, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, eval_total, total; };
+static bool is_fused(const EgnConfig* c) { return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_BF16; }
 static WsPlan plan_ws(const EgnConfig* c, long long n) {
     const long long S = egn_samples_per_ray(c);
     const long long M = n * S;
     WsPlan w;
     long long off = 0;
     auto take = [&](long long floats) { long long o = off; off += align256(floats * 4); return o; };
-    w.z = take(M); w.fsig = take(M); w.feat = take(M * EGN_FEAT_STRIDE); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n);
-    w.rgbpre = take(n * 3);
+    w.z = take(M); w.fsig = take(M); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n); w.rgbpre = take(n * 3);
+    // the fused fine pass never materialises the app feature in eval mode: 24 B/sample instead of 136
+    const long long eval_fused = off;
+    w.feat = take(M * EGN_FEAT_STRIDE);
+    w.eval_total = is_fused(c) ? eval_fused : off;
     w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
     const bool mlp = c->shading <= EGN_SHADE_MLP && c->mlp_mode != EGN_MLP_TC_BF16;   // the tcgen05 backward needs no scratch
     const long long Ms = (n < EGN_BWD_SUB_RAYS ? n : EGN_BWD_SUB_RAYS) * S;
@@ -137,7 +141,7 @@ extern "C" int64_t egn_workspace_bytes(const EgnConfig* c, int64_t n) {
 // forward-only callers (eval) may pass a workspace of this many bytes instead: no backward scratch
 extern "C" int64_t egn_workspace_bytes_eval(const EgnConfig* c, int64_t n) {
     if (validate(c, false)) return -1;
-    return plan_ws(c, n).d_rgbs;
+    return plan_ws(c, n).eval_total;
 }
 
 static int check_render_args(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
@@ -208,29 +212,30 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
 
 extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
                                       int64_t n, const float* z_vals, const EgnOutputs* out, void* workspace,
-                                      void* stream) {
+                                      int32_t keep_for_backward, void* stream) {
     if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
     if (n <= 0) return 0;
-    return render_samples_impl(c, p, tables, rays, n, z_vals, out, workspace, (cudaStream_t)stream, nullptr, true);
+    return render_samples_impl(c, p, tables, rays, n, z_vals, out, workspace, (cudaStream_t)stream, nullptr, keep_for_backward != 0);
 }
 
 static int render_forward_impl(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
                                int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
-                               int64_t ray0, const EgnOutputs* out, void* workspace, cudaStream_t st, StageEvents* se) {
+                               int64_t ray0, const EgnOutputs* out, void* workspace, bool keep, cudaStream_t st, StageEvents* se) {
     float* z = (float*)((char*)workspace + plan_ws(c, n).z);
     EgnKernelCfg k = make_kcfg(c, tables);
     mark(se, 0, st);
     int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z, st);
     if (e) return cuda_fail("egn_sample_rays", e);
-    return render_samples_impl(c, p, tables, rays, n, nullptr, out, workspace, st, se, is_train != 0);
+    return render_samples_impl(c, p, tables, rays, n, nullptr, out, workspace, st, se, keep);
 }
 
 extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
                                       int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
-                                      int64_t ray0, const EgnOutputs* out, void* workspace, void* stream) {
+                                      int64_t ray0, const EgnOutputs* out, void* workspace, int32_t keep_for_backward,
+                                      void* stream) {
     if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
     if (n <= 0) return 0;
-    return render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace,
+    return render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace, keep_for_backward != 0,
                                (cudaStream_t)stream, nullptr);
 }
 
@@ -246,7 +251,7 @@ extern "C" int32_t egn_render_forward_timed(const EgnConfig* c, const EgnParams*
     StageEvents se;
     se.on = true;
     for (int i = 0; i <= EGN_N_STAGES; ++i) cudaEventCreate(&se.ev[i]);
-    int rc = render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace, st, &se);
+    int rc = render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace, false, st, &se);
     if (!rc) {
         int e = (int)cudaEventSynchronize(se.ev[EGN_N_STAGES]);
         if (e) rc = cuda_fail("egn_render_forward_timed", e);

@@ -59,11 +59,11 @@ class _VolumeRender(torch.autograd.Function):
             if tuple(z_vals.shape) != (n, S):
                 raise ValueError(f"z_vals must be ({n}, {S})")
             _lib.check(lib.egn_render_samples(cfg, P, tables.data_ptr(), rays.data_ptr(), n, z_vals.data_ptr(), out,
-                                              ws.data_ptr(), _stream()))
+                                              ws.data_ptr(), int(need_grad), _stream()))
         else:
             _lib.check(lib.egn_render_forward(cfg, P, tables.data_ptr(), rays.data_ptr(), n, int(opts["is_train"]),
                                               _lib.ptr(u_coarse), _lib.ptr(u_fine), int(opts["seed"]),
-                                              int(opts["ray_index0"]), out, ws.data_ptr(), _stream()))
+                                              int(opts["ray_index0"]), out, ws.data_ptr(), int(need_grad), _stream()))
         ctx.mark_non_differentiable(depth)
         if need_grad:
             ctx.model, ctx.opts, ctx.n = model, opts, n

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 1
+#define EGN_ABI_VERSION 2
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -136,14 +136,15 @@ int32_t egn_unpack_table_grads(const EgnConfig* cfg, const float* d_tables /*dev
  *   is_train  0: deterministic schedule + linspace u (EgoNeRF.py:515-516, ray_utils.py:165-167)
  *             1: jittered; the uniforms come from u_coarse (n,n_coarse) / u_fine (n,n_fine) when given,
  *                else from a counter-based generator keyed by (seed, ray_index0 + ray, sample)
- *   workspace device, egn_workspace_bytes(cfg, n) bytes; after the call it holds the per-sample
- *             state (z, sigma feature, app feature, sample rgb) that egn_render_backward consumes. */
+ *   workspace device; keep_for_backward = 1: egn_workspace_bytes(cfg, n) bytes, and after the call it holds the
+ *             per-sample state (z, sigma feature, app feature, sample rgb) that egn_render_backward consumes;
+ *             keep_for_backward = 0: egn_workspace_bytes_eval(cfg, n) bytes suffice (24 B/sample in the fused mode). */
 int64_t egn_workspace_bytes(const EgnConfig* cfg, int64_t n_rays);
 int64_t egn_workspace_bytes_eval(const EgnConfig* cfg, int64_t n_rays);   /* forward-only (no backward scratch) */
 int32_t egn_render_forward(const EgnConfig* cfg, const EgnParams* params, const float* tables,
                            const float* rays, int64_t n_rays, int32_t is_train,
                            const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
-                           const EgnOutputs* out, void* workspace, void* stream);
+                           const EgnOutputs* out, void* workspace, int32_t keep_for_backward, void* stream);
 
 /* Same call with per-stage device times (CUDA events on `stream`; the call synchronises on the last one).
  * stage_ms (host, EGN_N_STAGES floats): 0 sampler (coarse pass + inverse CDF + sort), 1 fine gather + basis,
@@ -163,7 +164,8 @@ int32_t egn_sample_rays(const EgnConfig* cfg, const float* tables, const float* 
                         const float* u_coarse, const float* u_fine, uint64_t seed, int64_t ray_index0,
                         float* z_out, void* stream);
 int32_t egn_render_samples(const EgnConfig* cfg, const EgnParams* params, const float* tables, const float* rays,
-                           int64_t n_rays, const float* z_vals, const EgnOutputs* out, void* workspace, void* stream);
+                           int64_t n_rays, const float* z_vals, const EgnOutputs* out, void* workspace,
+                           int32_t keep_for_backward, void* stream);
 
 /* Backward of the above w.r.t. every parameter that receives a gradient in the reference (SURVEY.md
  * Appendix A10): fine density/appearance planes+lines, both basis matrices, the MLP, the envmap —

@@ -1,9 +1,7 @@
-timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -s -k "backward" 2>&1 | grep -E "passed|failed|tc backward|Error|error|assert|\{" | tail -6
-for m in "--mlp tc_bf16 --tables bf16" "--mlp tc_split --tables f32"; do
-python bench.py --mode train --rays 16384 --steps 5 --no-cpu-baseline --no-parity-line $m > gpurun_out/bt.json 2> gpurun_out/bt.err
-python -c "
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err
+python bench.py --workload cfg3 --mode train --steps 5 --warmup 3 --no-cpu-baseline --no-parity-line > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
+python bench.py --workload cfg1 --steps 50 --no-cpu-baseline > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err
+for f in cfg5 cfg3 cfg1; do python -c "
 import json
-d=json.loads(open('gpurun_out/bt.json').read().strip().splitlines()[-1]); print('$m', round(d['value']), d['ms_per_step'], round(d['e2e']['value']))"
-tail -2 gpurun_out/bt.err
-done
-ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv --log-file gpurun_out/launches_train2.csv python bench.py --mode train --steps 2 --warmup 3 --no-cpu-baseline --no-parity-line --rays 16384 > gpurun_out/ncu_bench.log 2>&1
+d=json.loads(open('gpurun_out/bench_$f.json').read().strip().splitlines()[-1]); print('$f', d['metric'], round(d['value']), d['ms_per_step'], d['roofline']['stage_ms'], round(d['e2e']['value']), d.get('parity_mode',{}).get('value'))"; tail -2 gpurun_out/bench_$f.err; done

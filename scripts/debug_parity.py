@@ -38,7 +38,7 @@ off = 0
 def take(nfl):
     global off
     a = np.frombuffer(ws[off:off + nfl * 4].tobytes(), dtype=np.float32); off += al(nfl * 4); return a
-z = take(M).reshape(N, S); fs = take(M).reshape(N, S); feat = take(M * 28).reshape(N, S, 28); rgbs = take(M * 3).reshape(N, S, 3); wgt = take(M).reshape(N, S)
+z = take(M).reshape(N, S); fs = take(M).reshape(N, S); rgbs = take(M * 3).reshape(N, S, 3); wgt = take(M).reshape(N, S); take(N); take(N * 3); feat = take(M * 28).reshape(N, S, 28)
 ez = np.abs(z - aux["z"].numpy())
 print("z err max", ez.max(), "rays with z err>1e-4:", (ez.max(1) > 1e-4).sum())
 sig = torch.nn.functional.softplus(torch.from_numpy(fs) + scene.density_shift).numpy()

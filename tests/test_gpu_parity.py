@@ -162,3 +162,42 @@ def test_fresh_inputs_against_oracle():
         print(f"fresh is_train={is_train}: rgb {e:.2e}, excluded {int((~ok).sum())}")
         assert e <= RGB_TOL
         assert (depth.cpu() - ref[1]).abs()[ok].max().item() <= 2e-4 * scene.near_far[1]
+
+
+def test_erp_frame_config_512_samples_against_oracle():
+    """BASELINE.json configs[4] shape: ERP rays from one pose (ray_utils.py:24-40), 256 coarse + 256 fine draws -> S = 512
+    (the largest schedule the kernels accept), checked against the oracle; exact-parity mode."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays
+    from oracle import egn_oracle as O
+    scene = scene_for(dict(n_voxels=40 ** 3, seed=7))
+    model = model_from_scene(scene)
+    model.mlp_mode = "tc_split"
+    rays = make_rays(2 * 48, 'erp', erp_hw=(24, 48), row0=11)            # two rows of a tiny equirect frame
+    kw = dict(RENDER_KW)
+    kw.update(n_coarse=256, n_fine=256)
+    with torch.no_grad():
+        rgb, depth, _, _, alpha = model(rays.cuda(), is_train=False, **kw)
+        cfg = oracle_cfg(scene, n_coarse=256, n_fine=256)
+        ref = O.render(scene.state_dict, cfg, rays, False)
+    ok = stable_rays(scene, cfg, rays, False, None, None)
+    assert alpha.shape == (96, 512)
+    e = (rgb.cpu() - ref[0]).abs()[ok].max().item()
+    print(f"ERP S=512: rgb {e:.2e}, excluded {int((~ok).sum())}")
+    assert e <= RGB_TOL
+
+
+def test_chunked_driver_equals_single_chunk():
+    """renderer.volume_renderer's chunk loop (renderer.py:25-26) must not change results (ragged last chunk included)."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.renderer import volume_renderer
+    from egonerf_b200.synthetic import make_rays
+    scene = scene_for(dict(n_voxels=40 ** 3, seed=8, envmap_h=32, near_far=(0.1, 300.), r0=0.05, density_shift=-10.))
+    model = model_from_scene(scene)
+    rays = make_rays(1000, 'isotropic', seed=9)
+    import contextlib, io
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        a = volume_renderer(rays, model, chunk=1000, is_train=False, device="cuda:0", **RENDER_KW)
+        b = volume_renderer(rays, model, chunk=96, is_train=False, device="cuda:0", empty_gpu_cache=True, **RENDER_KW)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.cpu().numpy(), y)
