@@ -161,7 +161,7 @@ def main():
     config = {"workload": wl["desc"], "rays_per_gpu_per_step": n_rays, "samples_per_ray": f"{N_COARSE} coarse + {S} fine",
               "mode": args.mode, "sharding": f"rays x{world}, grid replicated", "l2": "inputs exceed L2 (factor tables "
               "99 MB + >2 GB per-sample workspace streamed every step)"}
-    metric = "rays/sec (render)" if args.mode == "render" else "rays/sec (train step: fwd+bwd)"
+    metric = "rays/sec (render)" if args.mode == "render" else "rays/sec (train step: fwd + bwd + grad all-reduce + Adam + table refresh)"
 
     import torch
     from egonerf_b200.synthetic import make_scene, make_rays
@@ -214,6 +214,8 @@ def main():
     if train:
         target = torch.rand(n_rays, 3, device=dev)
         params = [p for p in model.parameters()] + ([model.envmap.emission] if model.envmap is not None else [])
+        # optimiser of train.py:172-186 (Adam, betas (0.9, 0.99), per-group learning rates), fused multi-tensor implementation
+        optimizer = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
 
     def step_device():
         if not train:
@@ -227,7 +229,8 @@ def main():
         loss = torch.mean((rgb - target) ** 2)
         loss.backward()
         if world > 1:
-            model.allreduce_gradients()
+            model.allreduce_gradients(average=True)
+        optimizer.step()
         model.update_coarse_sigma_grid()
         return loss
 
@@ -248,7 +251,8 @@ def main():
         loss = torch.mean((rgb - target) ** 2)
         loss.backward()
         if world > 1:
-            model.allreduce_gradients()
+            model.allreduce_gradients(average=True)
+        optimizer.step()
         model.update_coarse_sigma_grid()
         loss.item()
 
