@@ -301,7 +301,11 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
                                         d_feat + m0 * EGN_FEAT_STRIDE, h1, h2, dz1, dz2, g, st))) return cuda_fail("mlp backward", e);
         }
     }
-    if ((e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st))) return cuda_fail("gather backward", e);
+    if (c->mlp_mode == EGN_MLP_TC_BF16 && c->shading == EGN_SHADE_MLP_FEA)
+        e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);
+    else
+        e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);
+    if (e) return cuda_fail("gather backward", e);
     return 0;
 }
 

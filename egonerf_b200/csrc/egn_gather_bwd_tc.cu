@@ -1,0 +1,264 @@
+// Gather backward, throughput mode: same function as egn_gather_bwd_kernel (egn_backward.cu) with its two dense
+// contractions moved from shared-memory FFMA loops onto the tensor cores (ncu on the FFMA version: L1/LSU pipe 80 % busy,
+// 1.1 G shared-memory wavefronts per 4 M samples for dv = B_h^T dfeat and d(basis) += dfeat^T v).
+//
+// Per 128-sample tile, one CTA per SM, 512 threads:
+//   Ph0  warp w: Yin-Yang coordinates + d(sigma feature) of rows 8w..8w+7 (kept in registers), hemisphere flags -> smem
+//   Ph1  thread (row, q): 8 values of d_feat -> bf16 tile dF2[128][64] (column block 32*hemisphere, other block zero)
+//        MMA1  dV[128 x 144] = dF2 . [B_yin ; B_yang]        (A K-major K = 64; B = MN-major view of the basis operand)
+//   Ph2  dV: TMEM -> fp32 smem tile (rows -> the gather lanes that need them)
+//   Ph3  warp w, half-warp per sample: re-gather the 18 taps (branch-free clamped loads), P, L, v = P*L;
+//        d(plane) = up*L, d(line) = up*P scattered with 128-bit reductions; v rows -> bf16 tile V[128][144]
+//        MMA2  dB[64(+64 zero) x 144] += dF2^T . V            (both operands MN-major views; accumulator stays in TMEM)
+//   end  dB: TMEM -> atomics into d(basis_mat_yin / yang)
+#include "egn_tc.cuh"
+#include "egn_host.h"
+#include "egn_shared.cuh"
+
+#define GT_THREADS 512
+#define GT_VK (3 * EGN_CA)                 // 144
+#define GT_BB_CHUNK 1024
+#define GT_DVS 148                         // dv smem row stride (floats)
+#define IDESC_DV 0x08250490u               // M128 N144, A K-major, B MN-major
+#define IDESC_DB 0x08258490u               // M128 N144, A MN-major, B MN-major
+#define GT_TM_DV 0
+#define GT_TM_DB 160
+
+struct GtLayout {
+    static constexpr int BB = 0;                                          // [64 n][144 k]      18 432
+    static constexpr int DF = BB + (GT_VK / 8) * GT_BB_CHUNK;             // [128 m][128]       32 768 (cols 64.. zero)
+    static constexpr int V = DF + 16 * TC_CHUNK;                          // [128 m][144] bf16  36 864
+    static constexpr int DV = V + (GT_VK / 8) * TC_CHUNK;                 // [128 m][148] fp32  75 776
+    static constexpr int KNOTS = DV + TC_TM * GT_DVS * 4;
+    static constexpr int YANG = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
+    static constexpr int MBAR = YANG + TC_TM;
+    static constexpr int TMEM = MBAR + 16;
+    static constexpr int TOTAL = TMEM + 16;
+};
+static_assert(GtLayout::TOTAL <= 227 * 1024, "gather backward kernel exceeds the shared memory of one SM");
+
+__device__ __forceinline__ void gt_red4(float* addr, float4 v) { atomicAdd(reinterpret_cast<float4*>(addr), v); }
+__device__ __forceinline__ float4 gt_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
+                         const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
+                         const float* __restrict__ zs, const float* __restrict__ d_fsig, const float* __restrict__ d_feat,
+                         float* __restrict__ d_tab, float* __restrict__ d_basis0, float* __restrict__ d_basis1) {
+    using L = GtLayout;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, q = tid >> 7;
+    const int AD = k.app_dim;
+    unsigned char* bbs = smem + L::BB;
+    unsigned char* dfs = smem + L::DF;
+    unsigned char* vs = smem + L::V;
+    float* dvs = reinterpret_cast<float*>(smem + L::DV);
+    float* s_knots = reinterpret_cast<float*>(smem + L::KNOTS);
+    unsigned char* s_yang = smem + L::YANG;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
+    const uint32_t bar = smem_u32(smem + L::MBAR);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 64 * GT_VK; i += GT_THREADS) {
+        const int n = i / GT_VK, kk = i % GT_VK, o = n & 31;
+        const float* B = (n >> 5) ? basis1 : basis0;
+        store_elem(bbs, nullptr, false, n, kk, o < AD ? B[o * GT_VK + kk] : 0.f, GT_BB_CHUNK);
+    }
+    for (int i = tid; i < 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i <= k.lay.G[0]; i += GT_THREADS) s_knots[i] = k.r_knots[i];
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t bb_s = smem_u32(bbs), df_s = smem_u32(dfs), v_s = smem_u32(vs);
+    const int sub = lane & 15;
+
+    const long long tiles = (M + TC_TM - 1) / TC_TM;
+    uint32_t it = 0;
+    bool ok = true;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        // ---- Ph0. coordinates of this warp's 8 samples (lane j < 8 owns row 8 * warp + j) ----
+        const long long mg = tile * TC_TM + 8 * warp + (lane & 7);
+        YYCoord cc;
+        cc.c[0] = cc.c[1] = cc.c[2] = -3.f;
+        cc.yang = 0;
+        float dsg = 0.f;
+        const bool glive = mg < M;
+        if (glive) {
+            const long long ray = mg / k.S;
+            const float z = zs[mg];
+            const float* ry = rays + ray * 6;
+            cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+            dsg = d_fsig[mg];
+        }
+        if (lane < 8) s_yang[8 * warp + lane] = (unsigned char)cc.yang;
+        if (it > 0) ok &= mbar_wait(bar + 8, (it - 1) & 1);     // MMA2 of the previous tile has finished with dF2 and V
+        __syncthreads();
+        // ---- Ph1. dF2 tile ----
+        {
+            const long long gm = tile * TC_TM + row;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            if (gm < M) {
+                const float4* f4 = reinterpret_cast<const float4*>(d_feat + gm * EGN_FEAT_STRIDE) + 2 * q;
+                const float4 a = __ldg(f4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                if (q < 3) { const float4 b = __ldg(f4 + 1); v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+            }
+            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int yang = s_yang[row];
+            store_chunk<false>(dfs, nullptr, 4 * yang + q, row, v);
+            store_chunk<false>(dfs, nullptr, 4 * (1 - yang) + q, row, zero);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)                      // K = 64 basis outputs (yin | yang)
+                tc_mma(tmem + GT_TM_DV, desc_k(df_s + ks * 2 * TC_CHUNK), desc_mn(bb_s + ks * 256, GT_BB_CHUNK), IDESC_DV, ks > 0);
+            tc_commit(bar);
+        }
+        // ---- Ph2. dV rows -> smem ----
+        ok &= mbar_wait(bar, par);
+        tc_fence_after();
+        {
+            uint32_t r[32], r4[4];
+            tmem_ld32(tmem_lane + GT_TM_DV + 36 * q, r);
+            tmem_ld4(tmem_lane + GT_TM_DV + 36 * q + 32, r4);
+            float4* dst = reinterpret_cast<float4*>(dvs + row * GT_DVS + 36 * q);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                dst[g] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+            dst[8] = make_float4(__uint_as_float(r4[0]), __uint_as_float(r4[1]), __uint_as_float(r4[2]), __uint_as_float(r4[3]));
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- Ph3. re-gather, local gradients, scatter, V rows ----
+#pragma unroll 1
+        for (int itr = 0; itr < 4; ++itr) {
+            const int src = 2 * itr + (lane >> 4);              // sample within the warp's 8
+            const int srow = 8 * warp + src;
+            float c[3];
+            c[0] = __shfl_sync(FULL, cc.c[0], src);
+            c[1] = __shfl_sync(FULL, cc.c[1], src);
+            c[2] = __shfl_sync(FULL, cc.c[2], src);
+            const int yang = __shfl_sync(FULL, cc.yang, src);
+            const float dsig = __shfl_sync(FULL, dsg, src);
+            const bool slive = __shfl_sync(FULL, (int)glive, src) != 0;
+            unsigned j0[3], j1[3];
+            float wa0[3], wa1[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int G = k.lay.G[a];
+                const float ix = egn_unnorm(c[a], G);
+                const float fl = floorf(ix);
+                const float fr = ix - fl;
+                const int i0 = (int)fminf(fmaxf(fl, -2.f), (float)G + 1.f);
+                wa0[a] = ((i0 >= 0) & (i0 < G)) ? 1.f - fr : 0.f;
+                wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G)) ? fr : 0.f;
+                j0[a] = (unsigned)min(max(i0, 0), G - 1);
+                j1[a] = (unsigned)min(max(i0 + 1, 0), G - 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+                const unsigned W = (unsigned)k.lay.G[ax];
+                const unsigned pbase = (unsigned)k.lay.pf[yang][i] + sub * 4, lbase = (unsigned)k.lay.lf[yang][i] + sub * 4;
+                const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
+                const unsigned o0 = pbase + (ra + j0[ax]) * EGN_CF, o1 = pbase + (ra + j1[ax]) * EGN_CF;
+                const unsigned o2 = pbase + (rb + j0[ax]) * EGN_CF, o3 = pbase + (rb + j1[ax]) * EGN_CF;
+                const unsigned q0 = lbase + j0[al] * EGN_CF, q1 = lbase + j1[al] * EGN_CF;
+                const float4 t0 = ldg4(k.tables + o0), t1 = ldg4(k.tables + o1), t2 = ldg4(k.tables + o2), t3 = ldg4(k.tables + o3);
+                const float4 l0 = ldg4(k.tables + q0), l1 = ldg4(k.tables + q1);
+                const float w0 = wa0[ax] * wa0[ay], w1 = wa1[ax] * wa0[ay], w2 = wa0[ax] * wa1[ay], w3 = wa1[ax] * wa1[ay];
+                const float u0 = wa0[al], u1 = wa1[al];
+                float4 P = f4zero();
+                P = f4fma(w0, t0, P); P = f4fma(w1, t1, P); P = f4fma(w2, t2, P); P = f4fma(w3, t3, P);
+                float4 Lv = f4zero();
+                Lv = f4fma(u0, l0, Lv); Lv = f4fma(u1, l1, Lv);
+                const float4 prod = f4mul(P, Lv);
+                float s = hsum4(prod);                          // density lanes: relu mask of this product (EgoNeRF.py:346)
+                s += __shfl_xor_sync(FULL, s, 1);
+                s += __shfl_xor_sync(FULL, s, 2);
+                float4 up;
+                if (sub < EGN_CS / 4) {
+                    const float ds = (s > 0.f) ? dsig : 0.f;
+                    up = make_float4(ds, ds, ds, ds);
+                } else {
+                    const int kk = i * EGN_CA + (sub - EGN_CS / 4) * 4;
+                    up = *reinterpret_cast<const float4*>(dvs + srow * GT_DVS + kk);
+                    *reinterpret_cast<uint2*>(vs + (kk >> 3) * TC_CHUNK + srow * 16 + (kk & 7) * 2) =
+                        make_uint2(pack_hi(prod.x, prod.y), pack_hi(prod.z, prod.w));
+                }
+                if (slive) {
+                    const float4 dP = f4mul(up, Lv), dL = f4mul(up, P);
+                    if (w0 != 0.f) gt_red4(d_tab + o0, gt_scale(w0, dP));
+                    if (w1 != 0.f) gt_red4(d_tab + o1, gt_scale(w1, dP));
+                    if (w2 != 0.f) gt_red4(d_tab + o2, gt_scale(w2, dP));
+                    if (w3 != 0.f) gt_red4(d_tab + o3, gt_scale(w3, dP));
+                    if (u0 != 0.f) gt_red4(d_tab + q0, gt_scale(u0, dL));
+                    if (u1 != 0.f) gt_red4(d_tab + q1, gt_scale(u1, dL));
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA2: d(basis) += dF2^T V over the tile's 128 samples ----
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t first = it > 0 ? 1u : 0u;
+#pragma unroll
+            for (int ks = 0; ks < TC_TM / 16; ++ks)
+                tc_mma(tmem + GT_TM_DB, desc_mn(df_s + ks * 256), desc_mn(v_s + ks * 256), IDESC_DB, first | (ks > 0));
+            tc_commit(bar + 8);
+        }
+    }
+    if (it > 0) ok &= mbar_wait(bar + 8, (it - 1) & 1);
+    if (!ok) __trap();
+    tc_fence_after();
+    // ---- flush d(basis): accumulator row n = 32 * hemisphere + output, column = input index ----
+    if ((warp & 3) < 2) {
+        uint32_t r[32], r4[4];
+        tmem_ld32(tmem_lane + GT_TM_DB + 36 * q, r);
+        tmem_ld4(tmem_lane + GT_TM_DB + 36 * q + 32, r4);
+        const int o = row & 31;
+        float* dB = (row >> 5) ? d_basis1 : d_basis0;
+        if (o < AD && dB != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dB + o * GT_VK + 36 * q + j, __uint_as_float(r[j]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(dB + o * GT_VK + 36 * q + 32 + j, __uint_as_float(r4[j]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
+int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                             const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st) {
+    const long long M = n * k.S;
+    if (M <= 0) return 0;
+    const long long tiles = (M + TC_TM - 1) / TC_TM;
+    const int blocks = (int)(tiles < 148 ? tiles : 148);
+    cudaFuncSetAttribute(egn_gather_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
+    egn_gather_bwd_tc_kernel<<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig, d_feat,
+                                                                           d_tables, g->basis[0], g->basis[1]);
+    return (int)cudaGetLastError();
+}

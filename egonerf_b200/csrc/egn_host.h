@@ -57,6 +57,8 @@ int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* r
 // tensor-core MLP backward of the whole chunk (throughput mode): no scratch, weight gradients accumulated in TMEM
 int egn_launch_mlp_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                           const float* rgbs, const float* d_rgbs, float* d_feat, const EgnGrads* g, cudaStream_t st);
+int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
+                             const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st);
 int egn_launch_mlp_save(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                         float* h1, float* h2, cudaStream_t st);
 int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,

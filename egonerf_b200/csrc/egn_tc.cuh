@@ -112,3 +112,24 @@ __device__ __forceinline__ int tc_input_index(int kk, int AD) {
     return r == 0 ? AD + d : ((r & 1) ? off_vs : off_vc) + d * 2 + ((r - 1) >> 1);
 }
 
+
+// ---- operand descriptors for canonical no-swizzle tiles --------------------------------------------------------------
+// K-major canonical tile read as stored (LBO = chunk stride) or as its transpose (MN-major view of the same bytes:
+// LBO = 128 B between 8-row groups, SBO = chunk stride between 8-column groups)
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr, uint32_t chunk = TC_CHUNK) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(chunk >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t chunk = TC_CHUNK) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(chunk >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
