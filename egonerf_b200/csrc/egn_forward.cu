@@ -63,6 +63,38 @@ __device__ __forceinline__ void egn_gather_products(const float* __restrict__ ta
     }
 }
 
+// Bitonic sort of 32 * EF floats held EF per lane in blocked order (element index = lane * EF + e), ascending.
+// Compare-exchange partners further than EF apart sit in another lane (one shuffle), closer ones in the same lane.
+template <int EF>
+__device__ __forceinline__ void egn_bitonic_sort(float (&v)[EF], int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= 32 * EF; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= EF) {
+                const int lm = j / EF;
+                const bool lower = (lane & lm) == 0;
+#pragma unroll
+                for (int e = 0; e < EF; ++e) {
+                    const float o = __shfl_xor_sync(FULL, v[e], lm);
+                    const bool up = ((lane * EF + e) & kk) == 0;
+                    v[e] = (lower == up) ? fminf(v[e], o) : fmaxf(v[e], o);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EF; ++e) {
+                    if ((e & j) == 0) {
+                        const float a = v[e], b = v[e ^ j];
+                        const bool up = ((lane * EF + e) & kk) == 0;
+                        v[e] = up ? fminf(a, b) : fmaxf(a, b);
+                        v[e ^ j] = up ? fmaxf(a, b) : fminf(a, b);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // =================================================================================================
 // K1: coarse pass + resampling.  One warp per ray.
 // =================================================================================================
@@ -235,16 +267,38 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         const int EF = nf >> 5;
         float vf[K1_MAXC / 32];
         int rf[K1_MAXC / 32];
+        if (EF == 4 || EF == 8) {
+            // power-of-two draw counts (128: every shipped config; 256: the ERP-frame config): already-sorted fast path
+            // (eval: u is a linspace and the inverse CDF is monotone), else a bitonic network in registers / shuffles
 #pragma unroll
-        for (int e = 0; e < K1_MAXC / 32; ++e) {
-            rf[e] = 0;
-            vf[e] = (e < EF) ? zn[e * 32 + lane] : 0.f;
-        }
-        for (int b = 0; b < nf; ++b) {
-            const float vb = zn[b];
+            for (int e = 0; e < K1_MAXC / 32; ++e) vf[e] = (e < EF) ? zn[lane * EF + e] : 0.f;
+            bool sorted_ok = true;
 #pragma unroll
             for (int e = 0; e < K1_MAXC / 32; ++e)
-                if (e < EF) rf[e] += (vb < vf[e]) || (vb == vf[e] && b < e * 32 + lane);
+                if (e < EF) { const int idx = lane * EF + e; sorted_ok &= (idx + 1 >= nf) || (vf[e] <= zn[idx + 1]); }
+            if (!__all_sync(FULL, sorted_ok)) {
+                if (EF == 4) {
+                    float w4[4] = {vf[0], vf[1], vf[2], vf[3]};
+                    egn_bitonic_sort<4>(w4, lane);
+                    vf[0] = w4[0]; vf[1] = w4[1]; vf[2] = w4[2]; vf[3] = w4[3];
+                } else {
+                    egn_bitonic_sort<8>(vf, lane);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < K1_MAXC / 32; ++e) rf[e] = lane * EF + e;
+        } else {
+#pragma unroll
+            for (int e = 0; e < K1_MAXC / 32; ++e) {
+                rf[e] = 0;
+                vf[e] = (e < EF) ? zn[e * 32 + lane] : 0.f;
+            }
+            for (int b = 0; b < nf; ++b) {
+                const float vb = zn[b];
+#pragma unroll
+                for (int e = 0; e < K1_MAXC / 32; ++e)
+                    if (e < EF) rf[e] += (vb < vf[e]) || (vb == vf[e] && b < e * 32 + lane);
+            }
         }
         __syncwarp();
 #pragma unroll
