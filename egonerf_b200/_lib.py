@@ -82,6 +82,7 @@ PROTOTYPES = {
     "egn_envmap_radiance": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "egn_envmap_backward": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "egn_erp_rays": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_float_p, C.c_void_p, C.c_void_p]),
     "egn_host_sample_schedule": (C.c_int32, [C.c_float, C.c_float, C.c_float, C.c_int32, c_float_p]),
     "egn_host_r_knots": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p]),
 }

@@ -359,6 +359,13 @@ extern "C" int32_t egn_envmap_backward(const EgnConfig* c, const float* emission
     return e ? cuda_fail("egn_envmap_backward", e) : 0;
 }
 
+extern "C" int32_t egn_erp_rays(int32_t H, int32_t W, int32_t row0, int32_t n_rows, const float* c2w, float* rays, void* stream) {
+    if (H <= 0 || W <= 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > H) return fail("bad frame / row range");
+    if (!c2w || !rays) return fail("null argument");
+    int e = egn_launch_erp_rays(H, W, row0, n_rows, c2w, rays, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_erp_rays", e) : 0;
+}
+
 // ---- host helpers -------------------------------------------------------------------------------------
 // "first K intervals forced to r0, the rest shifted" (EgoNeRF.py:72-76, coordinates.py:120-124), fp32 arithmetic
 static void force_linear_prefix(float* r, int n, float r0) {

@@ -679,3 +679,38 @@ int egn_launch_composite(const EgnKernelCfg& k, const EgnParams* p, const float*
                                                                            *out, wgt, bgw, rgbpre);
     return (int)cudaGetLastError();
 }
+
+// =================================================================================================
+// Equirectangular ray generation on the device: get_ray_directions_360 (dataLoader/ray_utils.py:24-40),
+// the normalisation of dataset_omniblender.py:43 and get_rays (ray_utils.py:85-113) for rows [row0, row0 + n_rows) of an
+// H x W frame with camera-to-world pose c2w (3 x 4, row-major).  One thread per pixel; replaces the host-side
+// meshgrid + matmul + H2D copy of a whole frame of rays (24 B/ray over PCIe) by 48 bytes of pose.
+// =================================================================================================
+struct EgnPose { float m[12]; };
+
+__global__ void __launch_bounds__(256)
+egn_erp_rays_kernel(int H, int W, int row0, long long n, const __grid_constant__ EgnPose pose, float* __restrict__ rays) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int col = (int)(idx % W), row = row0 + (int)(idx / W);
+    const float i = (float)col + 0.5f, j = (float)row + 0.5f;
+    const float phi = (1.f - 2.f * i / (float)W) * 3.14159265358979323846f;            // longitude (pi, -pi)
+    const float theta = (1.f - 2.f * j / (float)H) * 3.14159265358979323846f / 2.f;    // latitude (pi/2, -pi/2)
+    float dx = -cosf(theta) * sinf(phi), dy = sinf(theta), dz = -cosf(theta) * cosf(phi);
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= nrm; dy /= nrm; dz /= nrm;
+    float* o = rays + idx * 6;
+    o[0] = pose.m[3]; o[1] = pose.m[7]; o[2] = pose.m[11];
+    o[3] = dx * pose.m[0] + dy * pose.m[1] + dz * pose.m[2];
+    o[4] = dx * pose.m[4] + dy * pose.m[5] + dz * pose.m[6];
+    o[5] = dx * pose.m[8] + dy * pose.m[9] + dz * pose.m[10];
+}
+
+int egn_launch_erp_rays(int H, int W, int row0, int n_rows, const float* c2w_host, float* rays, cudaStream_t st) {
+    EgnPose pose;
+    for (int i = 0; i < 12; ++i) pose.m[i] = c2w_host[i];
+    const long long n = (long long)n_rows * W;
+    if (n <= 0) return 0;
+    egn_erp_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(H, W, row0, n, pose, rays);
+    return (int)cudaGetLastError();
+}

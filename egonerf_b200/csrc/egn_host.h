@@ -45,6 +45,7 @@ int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* ra
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                           float* fsig, float* feat_out, float* rgbs, cudaStream_t st);
 int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st);
+int egn_launch_erp_rays(int H, int W, int row0, int n_rows, const float* c2w_host, float* rays, cudaStream_t st);
 // backward
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,

@@ -193,6 +193,12 @@ int32_t egn_envmap_radiance(const EgnConfig* cfg, const float* emission, const f
 int32_t egn_envmap_backward(const EgnConfig* cfg, const float* emission, const float* dirs, int64_t n,
                             const float* d_out, float* d_emission, void* stream);
 
+/* Rays of rows [row0, row0 + n_rows) of an H x W equirectangular frame with pose c2w (HOST pointer, 3 x 4 row-major):
+ * get_ray_directions_360 (dataLoader/ray_utils.py:24-40) + normalisation (dataset_omniblender.py:43) + get_rays (:85-113).
+ * rays: device (n_rows * W, 6). */
+int32_t egn_erp_rays(int32_t H, int32_t W, int32_t row0, int32_t n_rows, const float* c2w /*host*/, float* rays /*device*/,
+                     void* stream);
+
 /* ---- host helpers (no GPU): the two ladders, for callers that do not build them with torch ------ */
 int32_t egn_host_sample_schedule(float near_plane, float far_plane, float r0, int32_t n, float* z_out);   /* EgoNeRF.py:69-76 */
 int32_t egn_host_r_knots(float far_r, float r0, int32_t n_r, float* knots_out /*n_r+1*/);                  /* coordinates.py:118-124 */
