@@ -333,6 +333,17 @@ int egn_launch_coarse(const EgnKernelCfg& k, const float* rays, long long n, int
     return (int)cudaGetLastError();
 }
 
+__device__ __forceinline__ uint32_t egn_pack_bf16x2(float a, float b) {        // a in the low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// D (16 x 8, fp32) += A (16 x 16, bf16, row) * B (16 x 8, bf16, col)
+__device__ __forceinline__ void egn_mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // =================================================================================================
 // K2: fine gather.  A warp handles 16 samples per round: lanes 0-15 compute their sample's Yin-Yang
 // coordinate; then 8 iterations gather 2 samples each (16 lanes x float4 = one 256-byte tap per
@@ -343,8 +354,10 @@ int egn_launch_coarse(const EgnKernelCfg& k, const float* rays, long long n, int
 #define K2_VT 148                 // v-tile row stride (floats): conflict-free float4 rows
 #define K2_K (3 * EGN_CA)         // 144
 
+#define K2_BW 76                  // basis row stride in 32-bit words (72 bf16 pairs + pad: conflict-free fragment loads)
 struct K2Smem {
-    float BT[2][K2_K][32];        // basis, k-major, outputs padded 28 -> 32
+    uint32_t Bhi[2][32][K2_BW];   // basis_mat_{yin,yang}.weight rows (output n), bf16x2 pairs along k: hi parts
+    uint32_t Blo[2][32][K2_BW];   // lo parts of the split w = hi + lo (two bf16): products carry ~2^-17 relative error
     float vt[K2_WARPS][16][K2_VT];
     float knots[EGN_MAX_KNOTS + 1];
 };
@@ -357,10 +370,13 @@ egn_gather_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
                   float* __restrict__ feat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K2Smem& sm = *reinterpret_cast<K2Smem*>(smem_raw);
-    for (int i = threadIdx.x; i < 2 * K2_K * 32; i += blockDim.x) {
-        const int h = i / (K2_K * 32), kk = (i / 32) % K2_K, o = i % 32;
+    for (int i = threadIdx.x; i < 2 * 32 * (K2_K / 2); i += blockDim.x) {
+        const int h = i / (32 * (K2_K / 2)), o = (i / (K2_K / 2)) % 32, pr = i % (K2_K / 2);
         const float* B = h ? basis1 : basis0;
-        sm.BT[h][kk][o] = (o < k.app_dim && B) ? B[o * K2_K + kk] : 0.f;
+        const float w0 = (o < k.app_dim && B) ? B[o * K2_K + 2 * pr] : 0.f, w1 = (o < k.app_dim && B) ? B[o * K2_K + 2 * pr + 1] : 0.f;
+        const uint32_t hi = egn_pack_bf16x2(w0, w1);
+        sm.Bhi[h][o][pr] = hi;
+        sm.Blo[h][o][pr] = egn_pack_bf16x2(w0 - __uint_as_float(hi << 16), w1 - __uint_as_float(hi & 0xffff0000u));
     }
     if (!FROM_COORDS)
         for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) sm.knots[i] = k.r_knots[i];
@@ -368,7 +384,6 @@ egn_gather_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float(*vt)[K2_VT] = sm.vt[warp];
     const long long rounds = (M + 15) / 16;
-    const int sg = lane & 3, og = lane >> 2;
 
     for (long long r = (long long)blockIdx.x * K2_WARPS + warp; r < rounds; r += (long long)gridDim.x * K2_WARPS) {
         // ---- a. coordinate of sample (lane & 15) ----
@@ -417,51 +432,57 @@ egn_gather_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         }
         __syncwarp();
         if (lane < 16 && m < M) fsig[m] = myf;
-        // ---- c. basis contraction: lane = (og, sg): samples sg + 4a, outputs 4og .. 4og+3 ----
+        // ---- c. basis contraction feat = B_h v (EgoNeRF.py:409,412) on the warp-level tensor-core path: the 16 x 144 product
+        // tile of this round times basis^T as m16n8k16 bf16 MMAs with a 3-term split (v = hi + lo, B = hi + lo,
+        // D += v_lo B_hi + v_hi B_lo + v_hi B_hi, fp32 accumulate) — fp32-equivalent for the 1e-4 parity bound.  tcgen05
+        // needs 128-row CTA-wide tiles; this GEMM is 16 rows per warp, so it uses mma.sync.  Hemispheres that do not
+        // occur in the round are skipped; in a mixed round each row keeps the result of its own hemisphere. ----
         if (feat != nullptr) {
             const unsigned ymask = __ballot_sync(FULL, cc.yang != 0) & 0xffffu;
-            float acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            const int g = lane >> 2, tq = lane & 3;
             for (int h = 0; h < 2; ++h) {
                 if (h == 0 && ymask == 0xffffu) continue;     // no Yin sample in this round
                 if (h == 1 && ymask == 0u) continue;          // no Yang sample
-                const bool mixed = (ymask != 0u) && (ymask != 0xffffu);
-                float sel[4];
+                float acc[4][4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) sel[a] = (!mixed || (int)((ymask >> (sg + 4 * a)) & 1u) == h) ? 1.f : 0.f;
-                const float(*BT)[32] = sm.BT[h];
+                for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll 3
-                for (int k4 = 0; k4 < K2_K / 4; ++k4) {
-                    float4 va[4];
+                for (int kt = 0; kt < K2_K / 16; ++kt) {
+                    const int k0 = kt * 16 + 2 * tq;
+                    const float2 f0 = *reinterpret_cast<const float2*>(&vt[g][k0]);
+                    const float2 f1 = *reinterpret_cast<const float2*>(&vt[g + 8][k0]);
+                    const float2 f2 = *reinterpret_cast<const float2*>(&vt[g][k0 + 8]);
+                    const float2 f3 = *reinterpret_cast<const float2*>(&vt[g + 8][k0 + 8]);
+                    uint32_t ah[4], al[4];
+                    ah[0] = egn_pack_bf16x2(f0.x, f0.y); ah[1] = egn_pack_bf16x2(f1.x, f1.y);
+                    ah[2] = egn_pack_bf16x2(f2.x, f2.y); ah[3] = egn_pack_bf16x2(f3.x, f3.y);
+                    al[0] = egn_pack_bf16x2(f0.x - __uint_as_float(ah[0] << 16), f0.y - __uint_as_float(ah[0] & 0xffff0000u));
+                    al[1] = egn_pack_bf16x2(f1.x - __uint_as_float(ah[1] << 16), f1.y - __uint_as_float(ah[1] & 0xffff0000u));
+                    al[2] = egn_pack_bf16x2(f2.x - __uint_as_float(ah[2] << 16), f2.y - __uint_as_float(ah[2] & 0xffff0000u));
+                    al[3] = egn_pack_bf16x2(f3.x - __uint_as_float(ah[3] << 16), f3.y - __uint_as_float(ah[3] & 0xffff0000u));
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        va[a] = *reinterpret_cast<const float4*>(&vt[sg + 4 * a][k4 * 4]);
-                        if (mixed) { va[a].x *= sel[a]; va[a].y *= sel[a]; va[a].z *= sel[a]; va[a].w *= sel[a]; }
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(&BT[k4 * 4 + kk][og * 4]);
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            const float x = kk == 0 ? va[a].x : kk == 1 ? va[a].y : kk == 2 ? va[a].z : va[a].w;
-                            acc[a][0] = fmaf(x, b4.x, acc[a][0]);
-                            acc[a][1] = fmaf(x, b4.y, acc[a][1]);
-                            acc[a][2] = fmaf(x, b4.z, acc[a][2]);
-                            acc[a][3] = fmaf(x, b4.w, acc[a][3]);
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = 8 * j + g;
+                        const uint32_t bh0 = sm.Bhi[h][n][kt * 8 + tq], bh1 = sm.Bhi[h][n][kt * 8 + tq + 4];
+                        const uint32_t bl0 = sm.Blo[h][n][kt * 8 + tq], bl1 = sm.Blo[h][n][kt * 8 + tq + 4];
+                        egn_mma_bf16(acc[j], al, bh0, bh1);
+                        egn_mma_bf16(acc[j], ah, bl0, bl1);
+                        egn_mma_bf16(acc[j], ah, bh0, bh1);
                     }
                 }
-            }
-            if (og < EGN_FEAT_STRIDE / 4) {
+                // c0,c1: row g, outputs 8j + 2tq, +1;  c2,c3: row g + 8
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const long long mm = r * 16 + sg + 4 * a;
-                    if (mm < M)
-                        *reinterpret_cast<float4*>(feat + mm * EGN_FEAT_STRIDE + og * 4) =
-                            make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                for (int half = 0; half < 2; ++half) {
+                    const int row = g + 8 * half;
+                    const long long mm = r * 16 + row;
+                    if (mm < M && (int)((ymask >> row) & 1u) == h) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int n = 8 * j + 2 * tq;
+                            if (n < EGN_FEAT_STRIDE)
+                                *reinterpret_cast<float2*>(feat + mm * EGN_FEAT_STRIDE + n) = make_float2(acc[j][2 * half], acc[j][2 * half + 1]);
+                        }
+                    }
                 }
             }
         }
