@@ -35,21 +35,28 @@ struct TcLayout {
     static constexpr int TOTAL = TMEM + 16;
     // bf16 mode: 114 720 B -> two CTAs per SM (the second CTA's CUDA-core phases hide the first one's MMAs);
     // split mode: 229 408 B -> one CTA per SM
-    // layer-3 partial sums of column half 1, 128 x 4 floats: aliases K chunks 16.. of the A buffer, which the
-    // layer-2 operand (16 chunks) never touches
+    // layer-3 partial sums of the column blocks 1.., (NQ-1) x 128 x 4 floats (<= 6 KB): aliases K chunks 16..19 (8 KB) of the
+    // A buffer, which the layer-2 operand (16 chunks) never touches
     static constexpr int PART = A + 16 * TC_CHUNK;
 };
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, SPLIT ? 1 : 2)
+__global__ void __launch_bounds__(SPLIT ? 512 : 256, SPLIT ? 1 : 2)
 egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ w1, const float* __restrict__ b1,
                   const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                   const float* __restrict__ b3, const float* __restrict__ rays, long long M,
                   const float* __restrict__ feat, float* __restrict__ rgbs, int* __restrict__ err_flag) {
+    // NQ threads share a row: thread t owns row (t & 127) and column block (t >> 7).  bf16 mode: 2 per row, 256 threads,
+    // two CTAs per SM (the second CTA's CUDA-core phases hide the first one's MMAs); split mode (one CTA per SM because
+    // of its 229 KB of operands): 4 per row, 512 threads, so that the serial phases between the MMAs are half as long.
+    constexpr int NQ = SPLIT ? 4 : 2;
+    constexpr int NT = 128 * NQ;
+    constexpr int EPT = 32 / NQ;                   // input elements per thread (16 / 8)
+    constexpr int CPT = EGN_HID / NQ;              // hidden columns per thread (64 / 32)
     using L = TcLayout<SPLIT>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, half = tid >> 7;
+    const int row = tid & 127, q = tid >> 7;
     const int AD = k.app_dim;
     const int in_dim = AD + 3 + 4 * AD + 12;
     unsigned char* w1hi = smem + L::W1; unsigned char* w1lo = w1hi + L::W1_BYTES;
@@ -69,12 +76,12 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < EGN_HID * TC_K1; i += TC_THREADS) {          // W1[n][kk], columns permuted to our K order
+    for (int i = tid; i < EGN_HID * TC_K1; i += NT) {          // W1[n][kk], columns permuted to our K order
         const int n = i / TC_K1, kk = i % TC_K1;
         const int src = tc_input_index(kk, AD);
         store_elem(w1hi, w1lo, SPLIT, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
     }
-    for (int i = tid; i < EGN_HID * EGN_HID; i += TC_THREADS) {
+    for (int i = tid; i < EGN_HID * EGN_HID; i += NT) {
         const int n = i / EGN_HID, kk = i % EGN_HID;
         store_elem(w2hi, w2lo, SPLIT, n, kk, w2[i]);
     }
@@ -94,45 +101,41 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const long long gm = tile * TC_TM + row;
         const bool live = gm < M;
-        // ---- A. input rows: 16 elements per thread -> 10 chunks of [x, sin x, cos x, sin 2x, cos 2x] ----
+        // ---- A. input rows: EPT elements per thread -> chunks of [x, sin x, cos x, sin 2x, cos 2x] ----
         {
-            float el[16];
+            float el[EPT];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) el[j] = 0.f;
+            for (int j = 0; j < EPT; ++j) el[j] = 0.f;
             if (live) {
-                const float4* f4 = reinterpret_cast<const float4*>(feat + gm * EGN_FEAT_STRIDE);
-                if (half == 0) {
+                const float4* f4 = reinterpret_cast<const float4*>(feat + gm * EGN_FEAT_STRIDE) + q * (EPT / 4);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const float4 v = __ldg(f4 + q); el[4 * q] = v.x; el[4 * q + 1] = v.y; el[4 * q + 2] = v.z; el[4 * q + 3] = v.w; }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) { const float4 v = __ldg(f4 + 4 + q); el[4 * q] = v.x; el[4 * q + 1] = v.y; el[4 * q + 2] = v.z; el[4 * q + 3] = v.w; }
+                for (int g = 0; g < EPT / 4; ++g) {
+                    if (q * EPT + 4 * g < EGN_FEAT_STRIDE) {
+                        const float4 v = __ldg(f4 + g);
+                        el[4 * g] = v.x; el[4 * g + 1] = v.y; el[4 * g + 2] = v.z; el[4 * g + 3] = v.w;
+                    }
                 }
-                // elements >= app_dim are the view direction (then padding)
+                // elements >= app_dim are the view direction, then the constant 1 that carries b1, then padding
                 const float* dir = rays + (gm / k.S) * 6 + 3;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int e = 16 * half + j;
-                    if (e >= AD) el[j] = (e < AD + 3) ? dir[e - AD] : 0.f;
+                for (int j = 0; j < EPT; ++j) {
+                    const int e = EPT * q + j;
+                    if (e >= AD) el[j] = (e < AD + 3) ? dir[e - AD] : (e == AD + 3 ? 1.f : 0.f);
                 }
             }
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < EPT / 8; ++pass) {
                 float v[40];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int e = 16 * half + 8 * pass + j;
                     const float x = el[8 * pass + j];
                     float s1, c1;
                     if (SPLIT) sincosf(x, &s1, &c1); else __sincosf(x, &s1, &c1);   // bf16 operands keep 8 bits: MUFU is ample
-                    const float s2 = 2.f * s1 * c1, c2 = 1.f - 2.f * s1 * s1;          // sin 2x, cos 2x by the double-angle identities
-                    const bool valid = e < AD + 3;           // padding elements must contribute exact zeros (cos 0 = 1!)
-                    v[5 * j] = (e == AD + 3) ? 1.f : x;      // constant-1 column: layer-1 bias rides in W1
-                    v[5 * j + 1] = valid ? s1 : 0.f; v[5 * j + 2] = valid ? c1 : 0.f;
-                    v[5 * j + 3] = valid ? s2 : 0.f; v[5 * j + 4] = valid ? c2 : 0.f;
+                    v[5 * j] = x; v[5 * j + 1] = s1; v[5 * j + 2] = c1;
+                    v[5 * j + 3] = 2.f * s1 * c1; v[5 * j + 4] = 1.f - 2.f * s1 * s1;   // double angle; W1's padding columns are zero
                 }
 #pragma unroll
-                for (int c = 0; c < 5; ++c) store_chunk<SPLIT>(ahi, alo, 10 * half + 5 * pass + c, row, v + 8 * c);
+                for (int c = 0; c < 5; ++c) store_chunk<SPLIT>(ahi, alo, (EPT / 8) * 5 * q + 5 * pass + c, row, v + 8 * c);
             }
         }
         fence_async_smem();
@@ -154,17 +157,17 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             }
             tc_commit(bar0);
         }
-        // ---- C. H1 = relu(D1 + b1) -> bf16 operand of layer 2 (overwrites X: its MMAs have completed) ----
+        // ---- C. H1 = relu(D1) (b1 is inside D1) -> bf16 operand of layer 2 (overwrites X: its MMAs have completed) ----
         ok &= mbar_wait(bar0, it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int col = 64 * half + 32 * cc;
+        for (int cc = 0; cc < CPT / 32; ++cc) {
+            const int col = CPT * q + 32 * cc;
             uint32_t r[32];
             tmem_ld32(tmem_lane + col, r);
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]), 0.f);        // b1 is already inside D1
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]), 0.f);
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk<SPLIT>(ahi, alo, (col >> 3) + c, row, v + 8 * c);
         }
@@ -192,31 +195,35 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         tc_fence_after();
         float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int col = 64 * half + 32 * cc;
+        for (int cc = 0; cc < CPT / 32; ++cc) {
+            const int col = CPT * q + 32 * cc;
             uint32_t r[32];
             tmem_ld32(tmem_lane + 128 + col, r);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {                 // warp-uniform addresses: one L1 transaction per load
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + q);
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + q);
-                const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + q);
-                const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + q);
-                const float h0 = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
-                const float h2 = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
+            for (int g = 0; g < 8; ++g) {                 // warp-uniform addresses: one L1 transaction per load
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + g);
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + g);
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + g);
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + g);
+                const float h0 = fmaxf(__uint_as_float(r[4 * g]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * g + 1]) + bb.y, 0.f);
+                const float h2 = fmaxf(__uint_as_float(r[4 * g + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * g + 3]) + bb.w, 0.f);
                 p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
                 p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
                 p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
             }
         }
         tc_fence_before();
-        if (half == 1) *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, 0.f);
+        if (q > 0) *reinterpret_cast<float4*>(part + ((q - 1) * TC_TM + row) * 4) = make_float4(p0, p1, p2, 0.f);
         __syncthreads();
-        if (half == 0 && live) {
-            const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
-            rgbs[gm * 3 + 0] = egn_sigmoid(p0 + q.x + bias3[0]);
-            rgbs[gm * 3 + 1] = egn_sigmoid(p1 + q.y + bias3[1]);
-            rgbs[gm * 3 + 2] = egn_sigmoid(p2 + q.z + bias3[2]);
+        if (q == 0 && live) {
+#pragma unroll
+            for (int j = 0; j < NQ - 1; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(part + (j * TC_TM + row) * 4);
+                p0 += t.x; p1 += t.y; p2 += t.z;
+            }
+            rgbs[gm * 3 + 0] = egn_sigmoid(p0 + bias3[0]);
+            rgbs[gm * 3 + 1] = egn_sigmoid(p1 + bias3[1]);
+            rgbs[gm * 3 + 2] = egn_sigmoid(p2 + bias3[2]);
         }
         __syncthreads();                                  // the next tile's X overwrites the partial-sum scratch
     }
@@ -237,11 +244,11 @@ int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* ra
     const int blocks = (int)(tiles < 148 * (split ? 1 : 2) ? tiles : 148 * (split ? 1 : 2));
     if (split) {
         cudaFuncSetAttribute(egn_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<true>::TOTAL);
-        egn_mlp_tc_kernel<true><<<blocks, TC_THREADS, TcLayout<true>::TOTAL, st>>>(
+        egn_mlp_tc_kernel<true><<<blocks, 512, TcLayout<true>::TOTAL, st>>>(
             k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs, err_flag);
     } else {
         cudaFuncSetAttribute(egn_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<false>::TOTAL);
-        egn_mlp_tc_kernel<false><<<blocks, TC_THREADS, TcLayout<false>::TOTAL, st>>>(
+        egn_mlp_tc_kernel<false><<<blocks, 256, TcLayout<false>::TOTAL, st>>>(
             k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs, err_flag);
     }
     return (int)cudaGetLastError();
