@@ -161,8 +161,8 @@ extern "C" int32_t egn_sample_rays(const EgnConfig* c, const float* tables, cons
                                    const float* u_c, const float* u_f, uint64_t seed, int64_t ray0, float* z_out,
                                    void* stream) {
     if (validate(c, true)) return 1;
-    if (!tables || !rays || !z_out) return fail("null argument");
     if (n <= 0) return 0;
+    if (!tables || !rays || !z_out) return fail("null argument");
     EgnKernelCfg k = make_kcfg(c, tables);
     int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z_out, (cudaStream_t)stream);
     return e ? cuda_fail("egn_sample_rays", e) : 0;
@@ -213,8 +213,8 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
 extern "C" int32_t egn_render_samples(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
                                       int64_t n, const float* z_vals, const EgnOutputs* out, void* workspace,
                                       int32_t keep_for_backward, void* stream) {
+    if (n <= 0) return validate(c, true);                 // an empty chunk is valid and launches nothing
     if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
-    if (n <= 0) return 0;
     return render_samples_impl(c, p, tables, rays, n, z_vals, out, workspace, (cudaStream_t)stream, nullptr, keep_for_backward != 0);
 }
 
@@ -233,8 +233,8 @@ extern "C" int32_t egn_render_forward(const EgnConfig* c, const EgnParams* p, co
                                       int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
                                       int64_t ray0, const EgnOutputs* out, void* workspace, int32_t keep_for_backward,
                                       void* stream) {
+    if (n <= 0) return validate(c, true);
     if (check_render_args(c, p, tables, rays, out, workspace)) return 1;
-    if (n <= 0) return 0;
     return render_forward_impl(c, p, tables, rays, n, is_train, u_c, u_f, seed, ray0, out, workspace, keep_for_backward != 0,
                                (cudaStream_t)stream, nullptr);
 }
@@ -266,6 +266,7 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
                                        const float* d_env, const float* d_alpha, float* d_tables, const EgnGrads* g,
                                        void* stream) {
     if (validate(c, true)) return 1;
+    if (n <= 0) return 0;
     if (!p || !tables || !rays || !workspace || !d_tables || !g) return fail("null argument");
     if (!g->basis[0] || !g->basis[1]) return fail("basis gradient buffers missing");
     const bool mlp = c->shading <= EGN_SHADE_MLP;

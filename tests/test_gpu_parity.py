@@ -201,3 +201,27 @@ def test_chunked_driver_equals_single_chunk():
         b = volume_renderer(rays, model, chunk=96, is_train=False, device="cuda:0", empty_gpu_cache=True, **RENDER_KW)
     for x, y in zip(a, b):
         assert np.array_equal(x.cpu().numpy(), y)
+
+
+@pytest.mark.parametrize("mode,tables", [("fp32", "f32"), ("tc_split", "f32"), ("tc_bf16", "f32"), ("tc_bf16", "bf16")])
+def test_edge_sizes(mode, tables):
+    """Empty chunk, a single ray, and ray counts that leave ragged warps / tiles, in every arithmetic mode: results of
+    a ray must not depend on what else is in the chunk."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays
+    scene = scene_for(dict(n_voxels=40 ** 3, seed=8, envmap_h=32, near_far=(0.1, 300.), r0=0.05, density_shift=-10.))
+    model = model_from_scene(scene)
+    model.mlp_mode, model.table_dtype = mode, tables
+    rays = make_rays(131, 'isotropic', seed=13).cuda()
+    with torch.no_grad():
+        full = model(rays, is_train=False, **RENDER_KW)
+        empty = model(rays[:0], is_train=False, **RENDER_KW)
+        assert empty[0].shape == (0, 3) and empty[4].shape == (0, 257) and empty[2].shape == (0, 3)
+        for n in (1, 7, 33, 129):
+            part = model(rays[:n], is_train=False, **RENDER_KW)
+            for a, b in zip(part, full):
+                assert torch.equal(a, b[:n]), (mode, n)
+    # train mode with the in-kernel generator: a ray's jitter depends on (seed, global ray index) only
+    a = model(rays[:64], is_train=True, seed=5, ray_index0=0, **RENDER_KW)[0]
+    b = model(rays[32:64], is_train=True, seed=5, ray_index0=32, **RENDER_KW)[0]
+    assert torch.equal(a[32:], b)
