@@ -1,0 +1,48 @@
+"""CPU: the shim/ directory exposes the reference's module paths and names (train.py:6,11-12 imports), and the drop-in
+EgoNeRF keeps the reference's parameter names / shapes (checkpoint + optimiser-group compatibility)."""
+import importlib
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shim_module_paths_and_names():
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "import renderer, models; from models.EgoNeRF import EgoNeRF; from models.envmap import EnvironmentMap;"
+            "from models import coordinates_dict;"
+            "assert callable(renderer.volume_renderer) and renderer.OctreeRender_trilinear_fast is renderer.volume_renderer;"
+            "assert 'yinyang' in coordinates_dict; print('ok', EgoNeRF.__module__)") % (ROOT, os.path.join(ROOT, "shim"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "ok egonerf_b200.models.EgoNeRF" in out.stdout
+
+
+def test_parameter_names_shapes_and_optimizer_groups_match_the_reference():
+    from egonerf_b200.scene_io import model_from_scene
+    from egonerf_b200.synthetic import make_scene
+    import inspect
+    from egonerf_b200.renderer import volume_renderer
+    scene = make_scene(n_voxels=40 ** 3, seed=8, envmap_h=16, near_far=(0.1, 300.), r0=0.05, density_shift=-10.)
+    model = model_from_scene(scene, "cpu")
+    sd = model.state_dict()
+    assert list(sd.keys()) != [] and set(sd.keys()) == set(scene.state_dict.keys())      # reference key set (EgoNeRF.py:96-122)
+    g = model.gridSize.tolist()
+    assert tuple(sd["density_plane_yin.0"].shape) == (1, 16, g[1], g[0])                  # (1, C, G[m1], G[m0])
+    assert tuple(sd["app_line_yang.2"].shape) == (1, 48, g[0], 1)                          # (1, C, G[v], 1)
+    assert tuple(sd["basis_mat_yin.weight"].shape) == (27, 144)
+    groups = model.get_optparam_groups(0.02, 0.001, 0.1)                                  # EgoNeRF.py:139-156
+    assert len(groups) == 5 * 2 + 1 + 1
+    assert [gr["lr"] for gr in groups] == [0.02] * 4 + [0.001] + [0.02] * 4 + [0.001] + [0.001, 0.1]
+    torch.optim.Adam(groups, betas=(0.9, 0.99))
+    # same keyword surface as renderer.py:11-15
+    ref_args = ["rays", "model", "chunk", "n_coarse", "n_fine", "ndc_ray", "white_bg", "is_train", "exp_sampling", "device",
+                "empty_gpu_cache", "pretrain_envmap", "pivotal_sample_th", "resampling", "use_coarse_sample", "interval_th"]
+    assert list(inspect.signature(volume_renderer).parameters) == ref_args
+    kw = model.get_kwargs()
+    for key in ("aabb", "gridSize", "density_n_comp", "appearance_n_comp", "app_dim", "density_shift", "distance_scale",
+                "near_far", "shadingMode", "view_pe", "fea_pe", "featureC", "coordinates", "use_envmap", "envmap"):
+        assert key in kw                                                                    # tensorBase.py:241-268
