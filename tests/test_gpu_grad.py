@@ -122,3 +122,53 @@ def test_ray_shards_sum_to_the_full_batch_gradient():
         s = sum(p[k] for p in parts)
         scale = max(float(full[k].abs().max()), 1e-9)
         assert float((s - full[k]).abs().max()) <= 2e-4 * scale, k
+
+
+def test_regularisers_compose_with_the_render_loss():
+    """the reference's regularisers are plain torch on the same Parameters / on the alpha output
+    (TVLoss utils.py:155-171 via TV_loss_density / TV_loss_app, density_L1, ray_entropy_loss utils.py:175-183 on alpha,
+    train.py:285-310).  Their gradients must add up with the ones egn_render_backward produces — checked against autograd
+    through the CPU oracle for the same total loss."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays
+    from oracle import egn_oracle as O
+    scene = scene_for(dict(n_voxels=40 ** 3, seed=7))
+    dev = "cuda:0"
+    model = model_from_scene(scene, dev)
+    model.mlp_mode = "fp32"
+    n = 64
+    rays = make_rays(n, 'isotropic', seed=909)
+    gen = torch.Generator().manual_seed(910)
+    u_c, u_f, target = torch.rand(n, 128, generator=gen), torch.rand(n, 128, generator=gen), torch.rand(n, 3, generator=gen)
+
+    def tv(x):                                            # TVLoss.forward, utils.py:160-168
+        ch = x[:, :, 1:, :].numel() // x.shape[0]
+        cw = x[:, :, :, 1:].numel() // x.shape[0]
+        return 2 * (((x[:, :, 1:, :] - x[:, :, :-1, :]) ** 2).sum() / ch + ((x[:, :, :, 1:] - x[:, :, :, :-1]) ** 2).sum() / cw) / x.shape[0]
+
+    def entropy(alpha):                                   # ray_entropy_loss, utils.py:175-183
+        p = alpha / (alpha.sum(-1, keepdim=True) + 1e-10)
+        return (-(p * torch.log2(p + 1e-10)).sum(-1)).mean()
+
+    def total(rgb, alpha, planes_d, planes_a, lines_d, tgt):
+        loss = ((rgb - tgt) ** 2).mean()
+        loss = loss + 0.1 * sum(tv(p) * 1e-2 for p in planes_d) + 0.05 * sum(tv(p) * 1e-2 for p in planes_a)
+        loss = loss + 1e-3 * (sum(p.abs().mean() for p in planes_d) + sum(l.abs().mean() for l in lines_d))
+        return loss + 1e-2 * entropy(alpha)
+
+    sd = {k: v.clone().requires_grad_(True) for k, v in scene.state_dict.items()}
+    (ref_out, aux) = O.render(sd, oracle_cfg(scene), rays, True, u_c, u_f, want_aux=True)
+    names_d = [f"density_plane_{h}.{i}" for h in ("yin", "yang") for i in range(3)]
+    names_a = [f"app_plane_{h}.{i}" for h in ("yin", "yang") for i in range(3)]
+    names_l = [f"density_line_{h}.{i}" for h in ("yin", "yang") for i in range(3)]
+    total(ref_out[0], ref_out[4], [sd[k] for k in names_d], [sd[k] for k in names_a], [sd[k] for k in names_l], target).backward()
+
+    out = model(rays.to(dev), is_train=True, u_coarse=u_c.to(dev), u_fine=u_f.to(dev), z_vals=aux["z"].detach().to(dev), **RENDER_KW)
+    params = dict(model.named_parameters())
+    total(out[0], out[4], [params[k] for k in names_d], [params[k] for k in names_a], [params[k] for k in names_l], target.to(dev)).backward()
+    # the module's own helpers are the reference's formulas
+    assert abs(float(model.TV_loss_density(tv)) - float(sum(tv(params[k]) * 1e-2 for k in names_d))) < 1e-6
+    for k, p in params.items():
+        ref = sd[k].grad.numpy()
+        rel = np.abs(p.grad.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-9)
+        assert rel <= 1e-3, (k, rel)
