@@ -48,7 +48,8 @@ static int validate(const EgnConfig* c, bool need_schedule) {
     if (need_schedule) {
         if (c->n_coarse < 32 || c->n_coarse > 256 || c->n_coarse % 32) return fail("n_coarse=%d must be a multiple of 32 in [32,256]", c->n_coarse);
         if (c->resampling && (c->n_fine < 32 || c->n_fine > 256 || c->n_fine % 32)) return fail("n_fine=%d must be a multiple of 32 in [32,256]", c->n_fine);
-        if (!c->r_knots || !c->z_coarse) return fail("r_knots / z_coarse tables missing");
+        if (!c->r_knots || (c->exp_sampling && !c->z_coarse)) return fail("r_knots / z_coarse tables missing");
+        if (!c->exp_sampling && !(c->step_size > 0.f)) return fail("uniform march needs step_size > 0");
     }
     return 0;
 }
@@ -70,6 +71,9 @@ static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables) {
     k.fea2dense = c->fea2dense; k.shading = c->shading; k.app_dim = c->app_dim;
     k.view_pe = c->view_pe; k.fea_pe = c->fea_pe; k.env_h = c->env_h;
     k.mlp_mode = c->mlp_mode;
+    k.march = c->exp_sampling ? 0 : 1;
+    k.step_size = c->step_size; k.far_plane = c->far_plane;
+    for (int i = 0; i < 6; ++i) k.aabb[i] = c->aabb[i];
     k.tables_bf16 = c->tables_bf16;
     return k;
 }

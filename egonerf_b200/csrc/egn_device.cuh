@@ -60,6 +60,8 @@ struct EgnKernelCfg {
     int n_coarse, n_fine, S, use_coarse_sample, resampling;
     int fea2dense, shading, app_dim, view_pe, fea_pe, env_h;
     int mlp_mode;             // EGN_MLP_*
+    int march;                // 1: uniform march (TensorBase.sample_ray) instead of the exponential schedule
+    float step_size, far_plane, aabb[6];
     const void* tables_bf16;  // optional bf16 copy of the fine tables (same element offsets)
 };
 

@@ -95,6 +95,20 @@ __device__ __forceinline__ void egn_bitonic_sort(float (&v)[EF], int lane) {
     }
 }
 
+// t_min of TensorBase.sample_ray (tensorBase.py:312-315): entry depth into the AABB, clamped to [near, far]
+__device__ __forceinline__ float egn_aabb_entry(const EgnKernelCfg& k, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                float near_plane) {
+    const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+    float t = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float vec = d[a] == 0.f ? 1e-6f : d[a];
+        const float ra = (k.aabb[3 + a] - o[a]) / vec, rb = (k.aabb[a] - o[a]) / vec;
+        t = fmaxf(t, fminf(ra, rb));
+    }
+    return fminf(fmaxf(t, near_plane), k.far_plane);
+}
+
 // =================================================================================================
 // K1: coarse pass + resampling.  One warp per ray.
 // =================================================================================================
@@ -112,7 +126,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     __shared__ float s_zn[K1_WARPS][K1_MAXC];
     const int nc = k.n_coarse, nf = k.n_fine;
     for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) s_knots[i] = k.r_knots[i];
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) s_r[i] = k.z_coarse[i];
+    if (!k.march) for (int i = threadIdx.x; i < nc; i += blockDim.x) s_r[i] = k.z_coarse[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* zc = s_zc[warp];
@@ -123,15 +137,32 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     for (long long ray = (long long)blockIdx.x * K1_WARPS + warp; ray < n; ray += (long long)gridDim.x * K1_WARPS) {
         const float ox = rays[ray * 6 + 0], oy = rays[ray * 6 + 1], oz = rays[ray * 6 + 2];
         const float dx = rays[ray * 6 + 3], dy = rays[ray * 6 + 4], dz = rays[ray * 6 + 5];
-        // ---- 1. coarse depths: near + r, jittered by interval*U in train mode (EgoNeRF.py:69-82) ----
-        for (int j = lane; j < nc; j += 32) {
-            float r = s_r[j];
-            if (is_train) {
-                float iv = (j + 1 < nc) ? (s_r[j + 1] - s_r[j]) : (s_r[nc - 1] - s_r[nc - 2]);
-                float u = u_c ? u_c[ray * nc + j] : egn_u01(egn_philox(seed, (unsigned long long)(ray0 + ray), (unsigned)j).x);
-                r = r + iv * u;
+        // ---- 1. coarse depths ----
+        if (!k.march) {
+            // near + r, jittered by interval*U in train mode (EgoNeRF.py:69-82)
+            for (int j = lane; j < nc; j += 32) {
+                float r = s_r[j];
+                if (is_train) {
+                    float iv = (j + 1 < nc) ? (s_r[j + 1] - s_r[j]) : (s_r[nc - 1] - s_r[nc - 2]);
+                    float u = u_c ? u_c[ray * nc + j] : egn_u01(egn_philox(seed, (unsigned long long)(ray0 + ray), (unsigned)j).x);
+                    r = r + iv * u;
+                }
+                zc[j] = near_plane + r;
             }
-            zc[j] = near_plane + r;
+        } else {
+            // uniform march (TensorBase.sample_ray, tensorBase.py:308-327): z_j = t_min + stepSize * (j [+ U]).  The coarse
+            // POINTS use the ray's own entry depth; in eval mode the depths handed on are those of the FIRST ray of the
+            // chunk (EgoNeRF.py:515-516 `coarse_z_vals[0].repeat(N, 1)`) — reproduced as the reference does it.
+            const float t_own = egn_aabb_entry(k, ox, oy, oz, dx, dy, dz, near_plane);
+            const float t_use = is_train ? t_own
+                                         : egn_aabb_entry(k, rays[0], rays[1], rays[2], rays[3], rays[4], rays[5], near_plane);
+            for (int j = lane; j < nc; j += 32) {
+                float rng = (float)j;
+                if (is_train) rng += u_c ? u_c[ray * nc + j] : egn_u01(egn_philox(seed, (unsigned long long)(ray0 + ray), (unsigned)j).x);
+                const float step = k.step_size * rng;
+                zc[j] = t_use + step;
+                zn[j] = t_own + step;             // zn is free until the inverse CDF: depths of the coarse points
+            }
         }
         __syncwarp();
         if (!k.resampling) {                      // EgoNeRF.py:564-577: the coarse samples are the samples
@@ -142,7 +173,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         // ---- 2. pooled-grid density of every coarse sample (EgoNeRF.py:520-528) ----
         for (int t = 0; t < cnt; ++t) {
             const int j = t * 32 + lane;
-            const float z = zc[j];
+            const float z = (k.march && !is_train) ? zn[j] : zc[j];
             YYCoord cc = egn_cart_to_yinyang(ox + dx * z, oy + dy * z, oz + dz * z, k, s_knots);
             float myf = 0.f;
 #pragma unroll

@@ -138,6 +138,7 @@ class EgoNeRF(torch.nn.Module):
                 self.envmap.load_envmap(envmap.emission, device=device)
         self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
         self.init_svd_volume(gridSize[0], device)
+        self.update_stepSize(list(gridSize))
         self._tables = None
         self._tables_key = None
         self._sched = {}
@@ -180,6 +181,15 @@ class EgoNeRF(torch.nn.Module):
             self.init_one_svd(self.app_n_comp, g, 0.1, device)
         self.basis_mat_yin = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
         self.basis_mat_yang = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+
+    def update_stepSize(self, gridSize):
+        """TensorBase.update_stepSize (tensorBase.py:206-215): step of the uniform march (`exp_sampling=False`)."""
+        aabb = torch.as_tensor(self.aabb).detach().float().cpu()
+        self.aabbSize = aabb[1] - aabb[0]
+        self.units = self.aabbSize / (torch.LongTensor(list(gridSize)) - 1)
+        self.stepSize = torch.mean(self.units) * self.step_ratio
+        self.aabbHalfDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize))) / 2.0
+        self.nSamples = int((self.aabbHalfDiag / self.stepSize).item()) + 1
 
     def init_envmap(self, envmap_res_H, init_strategy='zero', device='cuda'):
         self.envmap = EnvironmentMap(h=envmap_res_H, init_strategy=init_strategy, device=device)
@@ -312,6 +322,10 @@ class EgoNeRF(torch.nn.Module):
         cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0
         cfg.center[:] = co.center.cpu().tolist()
         cfg.near_plane = self.near_far[0]
+        cfg.far_plane = self.near_far[1]
+        cfg.step_size = float(self.stepSize)
+        cfg.aabb[:] = torch.as_tensor(self.aabb).detach().float().cpu().reshape(-1).tolist()
+        cfg.exp_sampling = 1
         cfg.density_shift, cfg.distance_scale = self.density_shift, self.distance_scale
         near, inv = co.near.cpu(), co.inv_diff.cpu()
         cfg.ang_near[:] = [float(near[1]), float(near[2])]
@@ -324,6 +338,7 @@ class EgoNeRF(torch.nn.Module):
             nc = int(opts["n_coarse"])
             cfg.n_coarse, cfg.n_fine = nc, int(opts["n_fine"])
             cfg.use_coarse_sample, cfg.resampling = int(opts["use_coarse_sample"]), int(opts["resampling"])
+            cfg.exp_sampling = int(opts.get("exp_sampling", True))
             if ('z', nc) not in self._sched:
                 self._sched[('z', nc)] = sample_schedule(self.near_far[0], self.near_far[1], co.r0, nc).to(dev).contiguous()
             cfg.z_coarse = self._sched[('z', nc)].data_ptr()
@@ -337,12 +352,12 @@ class EgoNeRF(torch.nn.Module):
         return F.relu(density_features)
 
     def sample_depths(self, rays_chunk, is_train=False, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True,
-                      u_coarse=None, u_fine=None, seed=0, ray_index0=0):
+                      u_coarse=None, u_fine=None, seed=0, ray_index0=0, exp_sampling=True):
         """Sorted sample depths (N,S): sample_ray_exp + coarse pass + sample_pdf + sort (EgoNeRF.py:507-542)."""
         _need_cuda(rays_chunk, "rays_chunk")
         lib = _lib.load()
         opts = dict(is_train=bool(is_train), n_coarse=n_coarse, n_fine=n_fine if resampling else 0,
-                    resampling=bool(resampling), use_coarse_sample=bool(use_coarse_sample))
+                    resampling=bool(resampling), use_coarse_sample=bool(use_coarse_sample), exp_sampling=bool(exp_sampling))
         cfg = self._config(opts)
         rays = rays_chunk.detach().contiguous().float()
         n, S = rays.shape[0], lib.egn_samples_per_ray(cfg)
@@ -479,9 +494,6 @@ class EgoNeRF(torch.nn.Module):
             return self.envmap.get_radiance(rays_chunk[:, 3:6])
         if ndc_ray:
             raise NotImplementedError          # EgoNeRF.py:503-504
-        if not exp_sampling:
-            raise NotImplementedError("uniform marching (exp_sampling=False, tensorBase.py:308-327) is not built; "
-                                      "every shipped config samples exponentially")
         if n_coarse <= 0:
             raise ValueError("n_coarse must be given")
         rays = rays_chunk.detach().contiguous().float()
@@ -489,7 +501,7 @@ class EgoNeRF(torch.nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if is_train and u_coarse is None else 0
         opts = dict(is_train=bool(is_train), n_coarse=n_coarse, n_fine=n_fine if resampling else 0,
                     resampling=bool(resampling), use_coarse_sample=bool(use_coarse_sample), seed=seed,
-                    ray_index0=ray_index0)
+                    ray_index0=ray_index0, exp_sampling=bool(exp_sampling))
         uc = u_coarse.contiguous().float() if u_coarse is not None else None
         uf = u_fine.contiguous().float() if u_fine is not None else None
         zv = z_vals.detach().contiguous().float() if z_vals is not None else None

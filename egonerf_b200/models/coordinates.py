@@ -96,6 +96,7 @@ class YinYangSphericalCoords:
         cfg.grid[:] = [self.N_r, self.N_theta, self.N_phi]
         cfg.c_sigma, cfg.c_app, cfg.app_dim, cfg.shading, cfg.feature_c = 16, 48, 27, 2, 128
         cfg.app_dim = 3
+        cfg.exp_sampling = 1
         c = self.center.cpu().tolist()
         cfg.center[:] = c
         near, inv = self.near.cpu(), self.inv_diff.cpu()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 2
+#define EGN_ABI_VERSION 3
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -59,6 +59,11 @@ typedef struct EgnConfig {
     float   distance_scale;
     float   ang_near[2];      /* fp32(pi/4), fp32(-3pi/4)            (coordinates.py:500-505) */
     float   ang_inv[2];       /* 1/(far-near) of theta, phi in fp32  (coordinates.py:505) */
+    int32_t exp_sampling;     /* 1: exponential schedule of sample_ray_exp (every shipped config); 0: uniform march of
+                                 TensorBase.sample_ray (models/tensorBase.py:308-327) from the AABB entry point */
+    float   far_plane;        /* near_far[1] (uniform march only) */
+    float   step_size;        /* TensorBase.stepSize = mean(aabbSize / (gridSize - 1)) * step_ratio (tensorBase.py:206-213) */
+    float   aabb[6];          /* [min xyz, max xyz] (uniform march only) */
     const float* r_knots;     /* device, N_r+1 : reference r ladder of normalize_r (coordinates.py:118-124) */
     const float* z_coarse;    /* device, n_coarse : r schedule of sample_ray_exp WITHOUT near (EgoNeRF.py:69-76);
                                  the kernels add near_plane and, in train mode, the interval jitter (:78-82) */

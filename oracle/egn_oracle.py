@@ -46,6 +46,8 @@ class OracleCfg:
     view_pe: int = 2
     fea_pe: int = 2
     app_dim: int = 27
+    exp_sampling: bool = True               # False: uniform march of TensorBase.sample_ray (tensorBase.py:308-327)
+    step_ratio: float = 0.5
     extras: dict = field(default_factory=dict)
 
 
@@ -106,6 +108,25 @@ def r_reference_grid(far_r: torch.Tensor, r0: float, n_r: int) -> torch.Tensor:
     """GenericSphericalCoords.normalize_r, interval_th branch (coordinates.py:112-124): N_r+1 knots."""
     ratio = pow(far_r / r0, 1 / (n_r - 1))          # fp32 0-dim tensor, like `self.far[0] / r0`
     return _force_linear_prefix(_exp_ladder(r0, ratio, torch.arange(n_r + 1)), r0)
+
+
+def march_step_size(aabb: torch.Tensor, grid, step_ratio: float) -> torch.Tensor:
+    """TensorBase.update_stepSize (tensorBase.py:206-213): mean(aabbSize / (gridSize - 1)) * step_ratio, fp32 0-dim."""
+    units = (aabb[1] - aabb[0]) / (torch.tensor(list(grid), dtype=torch.int64) - 1)
+    return torch.mean(units) * step_ratio
+
+
+def uniform_march(o, d, aabb, near, far, step, n, u=None):
+    """TensorBase.sample_ray (tensorBase.py:308-327): t_min = entry into the AABB clamped to [near, far];
+    z_j = t_min + step * (j [+ U])."""
+    vec = torch.where(d == 0, torch.full_like(d, 1e-6), d)
+    rate_a = (aabb[1] - o) / vec
+    rate_b = (aabb[0] - o) / vec
+    t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
+    rng = torch.arange(n)[None].float()
+    if u is not None:
+        rng = rng.repeat(o.shape[0], 1) + u
+    return t_min[..., None] + step * rng
 
 
 def jitter_schedule(r: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
@@ -351,14 +372,22 @@ def render(sd: Dict[str, torch.Tensor], cfg: OracleCfg, rays: torch.Tensor, is_t
     knots = r_reference_grid(max_corner_radius(cfg.aabb), cfg.r0, cfg.grid[0])
     nc, nf = cfg.n_coarse, cfg.n_fine
 
-    r = sample_schedule(cfg.near, cfg.far, cfg.r0, nc)
-    if is_train:
-        zc = cfg.near + jitter_schedule(r, u_coarse)
+    if cfg.exp_sampling:
+        r = sample_schedule(cfg.near, cfg.far, cfg.r0, nc)
+        if is_train:
+            zc = cfg.near + jitter_schedule(r, u_coarse)
+        else:
+            zc = (cfg.near + r).repeat(N, 1)
+        zq = zc
     else:
-        zc = (cfg.near + r).repeat(N, 1)
+        # uniform march; the coarse POINTS use every ray's own depths, but in eval mode the depths handed on are those of
+        # the first ray of the chunk (EgoNeRF.py:515-516: coarse_z_vals[0].repeat(N, 1)) — reproduced as is
+        step = march_step_size(cfg.aabb, cfg.grid, cfg.step_ratio)
+        zq = uniform_march(o, d, cfg.aabb, cfg.near, cfg.far, step, nc, u_coarse if is_train else None)
+        zc = zq if is_train else zq[0].repeat(N, 1)
     dc = zc[:, 1:] - zc[:, :-1]
     dc = torch.cat([dc, dc[:, -1:]], -1)
-    pc = o[:, None, :] + d[:, None, :] * zc[..., None]
+    pc = o[:, None, :] + d[:, None, :] * zq[..., None]
     cc, yang_c, margin_c = _coords(pc.reshape(-1, 3), center, knots)
     aux = {}
 

@@ -35,9 +35,9 @@ def build_reference(scene):
     return co, model
 
 
-def ref_render(model, rays, is_train, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True):
+def ref_render(model, rays, is_train, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, exp_sampling=True):
     return ref_volume_renderer(rays, model, chunk=rays.shape[0], n_coarse=n_coarse, n_fine=n_fine,
-                               is_train=is_train, exp_sampling=True, resampling=resampling,
+                               is_train=is_train, exp_sampling=exp_sampling, resampling=resampling,
                                use_coarse_sample=use_coarse_sample, interval_th=True, device='cpu',
                                white_bg=False)
 
@@ -181,6 +181,9 @@ def main():
     render_case("render_128_white_eval.npz", make_scene(n_voxels=128 ** 3, smooth=1), make_rays(256, 'isotropic', seed=34), False)
     render_case("render_300_eval.npz", make_scene(n_voxels=27e6), make_rays(128, 'isotropic', seed=32), False)
     render_case("render_300_train.npz", make_scene(n_voxels=27e6), make_rays(128, 'isotropic', seed=33), True)
+    # uniform march (exp_sampling=False, TensorBase.sample_ray tensorBase.py:308-327): no shipped config uses it; SURVEY a4
+    render_case("render_tiny_march_eval.npz", tiny, r64, False, exp_sampling=False)
+    render_case("render_tiny_march_train.npz", tiny, r64p, True, exp_sampling=False)
     # other decoders that work through EgoNeRF.forward in the reference: MLP, RGB
     render_case("render_tiny_mlp.npz", make_scene(n_voxels=40 ** 3, seed=9, shading='MLP'), r64, False)
     render_case("render_tiny_rgb.npz", make_scene(n_voxels=40 ** 3, seed=10, shading='RGB', app_dim=3), r64, False)

@@ -24,6 +24,8 @@ RENDER_CASES = {
     "render_128_white_eval": (dict(n_voxels=128 ** 3, smooth=1), {}),
     "render_300_eval": (dict(n_voxels=27e6), {}),
     "render_300_train": (dict(n_voxels=27e6), {}),
+    "render_tiny_march_eval": (TINY, dict(exp_sampling=False)),
+    "render_tiny_march_train": (TINY, dict(exp_sampling=False)),
     "render_tiny_mlp": (dict(n_voxels=40 ** 3, seed=9, shading='MLP'), {}),
     "render_tiny_rgb": (dict(n_voxels=40 ** 3, seed=10, shading='RGB', app_dim=3), {}),
 }

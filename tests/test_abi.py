@@ -51,6 +51,7 @@ def _cfg(**kw):
     cfg.c_sigma, cfg.c_app, cfg.app_dim, cfg.shading = 16, 48, 27, 0
     cfg.view_pe, cfg.fea_pe, cfg.feature_c = 2, 2, 128
     cfg.n_coarse, cfg.n_fine, cfg.use_coarse_sample, cfg.resampling = 128, 128, 1, 1
+    cfg.exp_sampling = 1
     for k, v in kw.items():
         setattr(cfg, k, v)
     return cfg

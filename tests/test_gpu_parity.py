@@ -93,7 +93,8 @@ def test_render_with_reference_depths(name):
 def test_sample_depths(name):
     """sample_ray_exp + coarse pass + sample_pdf + sort (EgoNeRF.py:507-542) against the reference's sorted depths."""
     g, scene, okw, rays, is_train, u_c, u_f, model, ok = _case(name)
-    kw = dict(n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=okw.get("use_coarse_sample", True))
+    kw = dict(n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=okw.get("use_coarse_sample", True),
+              exp_sampling=okw.get("exp_sampling", True))
     z = model.sample_depths(rays.cuda(), is_train=is_train, u_coarse=None if u_c is None else u_c.cuda(),
                             u_fine=None if u_f is None else u_f.cuda(), **kw).cpu().numpy()
     ref = g["z_vals"]
