@@ -250,3 +250,30 @@ def test_checkpoint_round_trip(tmp_path):
         b = clone(rays, is_train=False, **RENDER_KW)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("shading,app_dim", [("SH", 27), ("MLP", 27), ("RGB", 3)])
+def test_other_decoders_forward_and_gradients_against_oracle(shading, app_dim):
+    """SHRender (tensorBase.py:30-34 + models/sh.py:87-116; the reference's own EgoNeRF.forward crashes in SH mode, so the
+    oracle restates SHRender on flattened inputs — SURVEY Appendix B), MLPRender (:107-129) and RGBRender (:37-39):
+    forward and all parameter gradients against autograd through the oracle."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays, make_scene
+    from oracle import egn_oracle as O
+    scene = make_scene(n_voxels=40 ** 3, seed=21, shading=shading, app_dim=app_dim)
+    model = model_from_scene(scene)
+    cfg = oracle_cfg(scene)
+    n = 48
+    rays = make_rays(n, 'isotropic', seed=31)
+    gen = torch.Generator().manual_seed(32)
+    u_c, u_f, w = torch.rand(n, 128, generator=gen), torch.rand(n, 128, generator=gen), torch.randn(n, 3, generator=gen)
+    sd = {k: v.clone().requires_grad_(True) for k, v in scene.state_dict.items()}
+    ref, aux = O.render(sd, cfg, rays, True, u_c, u_f, want_aux=True)
+    (ref[0] * w).sum().backward()
+    out = model(rays.cuda(), is_train=True, u_coarse=u_c.cuda(), u_fine=u_f.cuda(), z_vals=aux["z"].detach().cuda(), **RENDER_KW)
+    (out[0] * w.cuda()).sum().backward()
+    assert (out[0].detach().cpu() - ref[0].detach()).abs().max().item() <= RGB_TOL
+    for k, p in model.named_parameters():
+        r = sd[k].grad.numpy()
+        rel = np.abs(p.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-9)
+        assert rel <= 1e-3, (shading, k, rel)
