@@ -91,7 +91,16 @@ class _VolumeRender(torch.autograd.Function):
         cfg = model._config(opts)
         d_tables = torch.zeros_like(tables)
         plist = model._param_list()
-        grads = [torch.zeros_like(p) if i >= 24 else torch.empty_like(p) for i, p in enumerate(plist)]
+        # one allocation for every gradient: the 24 factor gradients are overwritten by egn_unpack_table_grads, the rest
+        # (basis, MLP, envmap) is accumulated into and must start at zero — a single fill instead of one per tensor
+        sizes = [p.numel() for p in plist]
+        flat = torch.empty(sum(sizes), device=tables.device, dtype=torch.float32)
+        n_fac = sum(sizes[:24])
+        flat[n_fac:].zero_()
+        grads, off = [], 0
+        for p, sz in zip(plist, sizes):
+            grads.append(flat[off:off + sz].view_as(p))
+            off += sz
         G = model._grads_struct(grads)
         _lib.check(lib.egn_render_backward(cfg, model._params_struct(), tables.data_ptr(), rays.data_ptr(), ctx.n,
                                            ws.data_ptr(), _lib.ptr(d_rgb), _lib.ptr(d_bg), _lib.ptr(d_env),
@@ -142,6 +151,7 @@ class EgoNeRF(torch.nn.Module):
         self._tables = None
         self._tables_key = None
         self._sched = {}
+        self._cfg_static = None
         # arithmetic of the colour-decode MLP inside libegn_b200: "fp32" (exact FFMA), "tc_split" (tcgen05, 3-term bf16
         # split: fp32-equivalent) or "tc_bf16" (tcgen05, plain bf16).  Not a reference kwarg: set the attribute.
         self.mlp_mode = os.environ.get("EGN_MLP_MODE", "tc_split")
@@ -305,12 +315,26 @@ class EgoNeRF(torch.nn.Module):
             _lib.check(lib.egn_pack_tables_bf16(cfg, self._tables.data_ptr(), self._tables_bf16.data_ptr(), _stream()))
         return self._tables
 
+    def _static_config(self):
+        """Scalars that never change after construction, read back from the device ONCE (a `.cpu()` per forward would be
+        a host-device synchronisation per call)."""
+        if getattr(self, "_cfg_static", None) is None:
+            co = self.coordinates
+            if len(set(self.density_n_comp)) != 1 or len(set(self.app_n_comp)) != 1:
+                raise NotImplementedError("n_lamb_sigma / n_lamb_sh must be equal across the three factor pairs")
+            near, inv = co.near.cpu(), co.inv_diff.cpu()
+            self._cfg_static = dict(
+                grid=self.gridSize.tolist(), center=co.center.cpu().tolist(),
+                aabb=torch.as_tensor(self.aabb).detach().float().cpu().reshape(-1).tolist(),
+                ang_near=[float(near[1]), float(near[2])], ang_inv=[float(inv[1]), float(inv[2])],
+                step_size=float(self.stepSize))
+        return self._cfg_static
+
     def _config(self, opts):
         co = self.coordinates
+        st = self._static_config()
         cfg = _lib.EgnConfig()
-        cfg.grid[:] = self.gridSize.tolist()
-        if len(set(self.density_n_comp)) != 1 or len(set(self.app_n_comp)) != 1:
-            raise NotImplementedError("n_lamb_sigma / n_lamb_sh must be equal across the three factor pairs")
+        cfg.grid[:] = st["grid"]
         cfg.c_sigma, cfg.c_app, cfg.app_dim = self.density_n_comp[0], self.app_n_comp[0], self.app_dim
         cfg.shading = _lib.SHADING[self.shadingMode]
         cfg.view_pe, cfg.fea_pe, cfg.feature_c = self.view_pe, self.fea_pe, self.featureC
@@ -320,16 +344,15 @@ class EgoNeRF(torch.nn.Module):
         use_bf16 = self.table_dtype == "bf16" and self.mlp_mode == "tc_bf16" and self._tables_bf16 is not None
         cfg.tables_bf16 = self._tables_bf16.data_ptr() if use_bf16 else None
         cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0
-        cfg.center[:] = co.center.cpu().tolist()
+        cfg.center[:] = st["center"]
         cfg.near_plane = self.near_far[0]
         cfg.far_plane = self.near_far[1]
-        cfg.step_size = float(self.stepSize)
-        cfg.aabb[:] = torch.as_tensor(self.aabb).detach().float().cpu().reshape(-1).tolist()
+        cfg.step_size = st["step_size"]
+        cfg.aabb[:] = st["aabb"]
         cfg.exp_sampling = 1
         cfg.density_shift, cfg.distance_scale = self.density_shift, self.distance_scale
-        near, inv = co.near.cpu(), co.inv_diff.cpu()
-        cfg.ang_near[:] = [float(near[1]), float(near[2])]
-        cfg.ang_inv[:] = [float(inv[1]), float(inv[2])]
+        cfg.ang_near[:] = st["ang_near"]
+        cfg.ang_inv[:] = st["ang_inv"]
         dev = self.density_plane_yin[0].device
         if 'knots' not in self._sched:
             self._sched['knots'] = co.r_knots().to(dev).contiguous()
