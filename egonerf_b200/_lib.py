@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -24,7 +24,7 @@ class EgnConfig(C.Structure):
         ("mlp_mode", C.c_int32),
         ("center", C.c_float * 3), ("near_plane", C.c_float), ("density_shift", C.c_float),
         ("distance_scale", C.c_float), ("ang_near", C.c_float * 2), ("ang_inv", C.c_float * 2),
-        ("exp_sampling", C.c_int32), ("far_plane", C.c_float), ("step_size", C.c_float), ("aabb", C.c_float * 6),
+        ("exp_sampling", C.c_int32), ("far_plane", C.c_float), ("step_size", C.c_float), ("aabb", C.c_float * 6), ("bwd_tc", C.c_int32),
         ("r_knots", C.c_void_p), ("z_coarse", C.c_void_p), ("tables_bf16", C.c_void_p),
     ]
 

@@ -119,6 +119,9 @@ static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 #define EGN_BWD_SUB_RAYS 4096
 struct WsPlan { long long z, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, eval_total, total; };
 static bool is_fused(const EgnConfig* c) { return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_BF16; }
+static bool tc_backward(const EgnConfig* c) {
+    return c->shading == EGN_SHADE_MLP_FEA && c->view_pe == 2 && c->fea_pe == 2 && (c->mlp_mode == EGN_MLP_TC_BF16 || c->bwd_tc);
+}
 static WsPlan plan_ws(const EgnConfig* c, long long n) {
     const long long S = egn_samples_per_ray(c);
     const long long M = n * S;
@@ -131,7 +134,7 @@ static WsPlan plan_ws(const EgnConfig* c, long long n) {
     w.feat = take(M * EGN_FEAT_STRIDE);
     w.eval_total = is_fused(c) ? eval_fused : off;
     w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
-    const bool mlp = c->shading <= EGN_SHADE_MLP && c->mlp_mode != EGN_MLP_TC_BF16;   // the tcgen05 backward needs no scratch
+    const bool mlp = c->shading <= EGN_SHADE_MLP && !tc_backward(c);   // the tcgen05 backward needs no scratch
     const long long Ms = (n < EGN_BWD_SUB_RAYS ? n : EGN_BWD_SUB_RAYS) * S;
     w.h1 = take(mlp ? Ms * EGN_HID : 0); w.h2 = take(mlp ? Ms * EGN_HID : 0);
     w.dz1 = take(mlp ? Ms * EGN_HID : 0); w.dz2 = take(mlp ? Ms * EGN_HID : 0);
@@ -294,7 +297,7 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
     int e;
     if ((e = egn_launch_composite_bwd(k, p, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs,
                                       d_fsig, d_feat, g->emission, st))) return cuda_fail("composite backward", e);
-    if (mlp && c->mlp_mode == EGN_MLP_TC_BF16) {
+    if (mlp && tc_backward(c)) {
         if ((e = egn_launch_mlp_bwd_tc(k, p, rays, n, feat, rgbs, d_rgbs, d_feat, g, st))) return cuda_fail("mlp backward (tcgen05)", e);
     } else if (mlp) {
         float* h1 = (float*)(base + w.h1); float* h2 = (float*)(base + w.h2);
@@ -306,7 +309,7 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
                                         d_feat + m0 * EGN_FEAT_STRIDE, h1, h2, dz1, dz2, g, st))) return cuda_fail("mlp backward", e);
         }
     }
-    if (c->mlp_mode == EGN_MLP_TC_BF16 && c->shading == EGN_SHADE_MLP_FEA)
+    if (tc_backward(c))
         e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);
     else
         e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);

@@ -157,6 +157,8 @@ class EgoNeRF(torch.nn.Module):
         self.mlp_mode = os.environ.get("EGN_MLP_MODE", "tc_split")
         # "bf16": the fused fine pass of mlp_mode "tc_bf16" gathers from a bf16 copy of the render tables (half the bytes)
         self.table_dtype = os.environ.get("EGN_TABLE_DTYPE", "f32")
+        # True: backward on the tcgen05 kernels (bf16 operands) even when the forward runs in a parity mode
+        self.tc_backward = os.environ.get("EGN_TC_BACKWARD", "0") == "1"
         self._tables_bf16 = None
 
     # ---- parameters (EgoNeRF.py:96-122) -------------------------------------------------------------
@@ -341,6 +343,7 @@ class EgoNeRF(torch.nn.Module):
         cfg.fea2dense = _lib.ACT[self.fea2denseAct]
         tc_ok = self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
         cfg.mlp_mode = _lib.MLP_MODE[self.mlp_mode] if tc_ok else 0
+        cfg.bwd_tc = int(bool(self.tc_backward) and tc_ok)
         use_bf16 = self.table_dtype == "bf16" and self.mlp_mode == "tc_bf16" and self._tables_bf16 is not None
         cfg.tables_bf16 = self._tables_bf16.data_ptr() if use_bf16 else None
         cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0

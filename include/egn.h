@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 3
+#define EGN_ABI_VERSION 4
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -64,6 +64,8 @@ typedef struct EgnConfig {
     float   far_plane;        /* near_far[1] (uniform march only) */
     float   step_size;        /* TensorBase.stepSize = mean(aabbSize / (gridSize - 1)) * step_ratio (tensorBase.py:206-213) */
     float   aabb[6];          /* [min xyz, max xyz] (uniform march only) */
+    int32_t bwd_tc;           /* 1: egn_render_backward uses the tcgen05 backward kernels (bf16 operands, fp32 accumulate) even
+                                 when the forward ran in EGN_MLP_FP32 / EGN_MLP_TC_SPLIT; always on for EGN_MLP_TC_BF16 */
     const float* r_knots;     /* device, N_r+1 : reference r ladder of normalize_r (coordinates.py:118-124) */
     const float* z_coarse;    /* device, n_coarse : r schedule of sample_ray_exp WITHOUT near (EgoNeRF.py:69-76);
                                  the kernels add near_plane and, in train mode, the interval jitter (:78-82) */

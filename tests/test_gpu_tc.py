@@ -116,8 +116,9 @@ def test_tc_backward_matches_fp32_backward(name):
     kw.update(okw)
     cu = lambda k: T(g[k]).to(dev)
     grads = {}
-    for mode in ("fp32", "tc_bf16"):
-        model.mlp_mode = mode
+    for mode in ("fp32", "tc_bf16", "tc_split+tc_backward"):
+        model.mlp_mode = mode.split("+")[0]
+        model.tc_backward = "+" in mode
         for p in model.parameters():
             p.grad = None
         if model.envmap is not None:
@@ -127,9 +128,13 @@ def test_tc_backward_matches_fp32_backward(name):
         loss.backward()
         torch.cuda.synchronize()
         grads[mode] = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.tc_backward = False
     worst, bad = {}, {}
     for k, ref in grads["fp32"].items():
         got = grads["tc_bf16"][k]
+        hyb = grads["tc_split+tc_backward"][k]       # parity forward + tcgen05 backward: same bound
+        cs_h = float(torch.nn.functional.cosine_similarity(hyb.flatten(), ref.flatten(), dim=0))
+        assert cs_h >= 0.995, (k, cs_h)
         rel = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
         cs = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
         worst[k] = rel
