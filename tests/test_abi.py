@@ -120,3 +120,26 @@ def test_no_cpu_fallback():
     import egonerf_b200
     src = open(os.path.join(os.path.dirname(egonerf_b200.__file__), "models", "EgoNeRF.py")).read()
     assert "oracle" not in src
+
+
+def test_ctypes_structs_mirror_the_header_field_by_field():
+    """A reordered or missing field would silently shift every later argument: the ctypes mirror of EgnConfig / EgnParams /
+    EgnOutputs must list the header's fields in the header's order."""
+    text = open(os.path.join(ROOT, "include", "egn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+
+    def fields(struct):
+        body = text[text.index("typedef struct %s {" % struct):text.index("} %s;" % struct)].split("{", 1)[1]
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"(\w+)\s*(?:\[[^\]]*\])*\s*$", first)[0])
+            names += [re.findall(r"(\w+)", r)[0] for r in rest]
+        return names
+
+    assert fields("EgnConfig") == [f[0] for f in _lib.EgnConfig._fields_]
+    assert fields("EgnParams") == [f[0] for f in _lib.EgnParams._fields_]
+    assert fields("EgnOutputs") == [f[0] for f in _lib.EgnOutputs._fields_]
