@@ -21,7 +21,11 @@
 #define FU_GROUP 256
 #define FU_VK (3 * EGN_CA)                   // 144
 #define FU_VCHUNKS (FU_VK / 8)               // 18
-#define FU_VBYTES (FU_VCHUNKS * TC_CHUNK)    // 36 864
+// K-chunk stride of the V operand: 2048 B of data + 64 B of padding.  The 6 appearance lanes of a sample store chunks
+// kc, kc+1, .. of the SAME row; with a 2048 B stride they all fall into one 16-byte bank group (6-way conflict), with
+// 2112 B consecutive chunks alternate between two groups and the 24 lanes of a store spread 3 per group = the minimum.
+#define FU_VCHUNK (TC_CHUNK + 64)
+#define FU_VBYTES (FU_VCHUNKS * FU_VCHUNK)   // 38 016
 #define FU_BB_CHUNK 1024                     // basis operand: 64 rows x 16 B per K chunk
 
 struct FuLayout {
@@ -144,7 +148,7 @@ __device__ __forceinline__ void fused_gather_rows(const EgnKernelCfg& k, const v
             f += fmaxf(s, 0.f);
             if (sub >= DL) {                                   // appearance lanes: bf16 row of the A operand
                 const int kk = i * EGN_CA + (sub - DL) * NCH;  // first K index of this lane's products
-                unsigned char* dst = vbuf + (kk >> 3) * TC_CHUNK + row * 16 + (kk & 7) * 2;
+                unsigned char* dst = vbuf + (kk >> 3) * FU_VCHUNK + row * 16 + (kk & 7) * 2;
                 if constexpr (BF16) {
                     uint4 q;
                     q.x = pack_hi(prod[0], prod[1]); q.y = pack_hi(prod[2], prod[3]);
@@ -252,7 +256,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < FU_VK / 16; ++ks)
-                    tc_mma(tmem + 256, tc_desc(v_s + b * FU_VBYTES + ks * 2 * TC_CHUNK),
+                    tc_mma(tmem + 256, tc_desc(v_s + b * FU_VBYTES + ks * 2 * FU_VCHUNK, FU_VCHUNK),
                            tc_desc(bb_s + ks * 2 * FU_BB_CHUNK, FU_BB_CHUNK), TC_IDESC_128x64, ks > 0);
                 tc_commit(v_empty0 + 8 * b);
                 tc_commit(feat_full);
