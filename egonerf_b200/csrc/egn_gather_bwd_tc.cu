@@ -19,6 +19,7 @@
 #define GT_VK (3 * EGN_CA)                 // 144
 #define GT_BB_CHUNK 1024
 #define GT_DVS 148                         // dv smem row stride (floats)
+#define GT_VCHUNK (TC_CHUNK + 64)          // padded K-chunk stride of the V tile (bank-conflict-free row stores, see egn_fused.cu)
 #define IDESC_DV 0x08250490u               // M128 N144, A K-major, B MN-major
 #define IDESC_DB 0x08258490u               // M128 N144, A MN-major, B MN-major
 #define GT_TM_DV 0
@@ -28,7 +29,7 @@ struct GtLayout {
     static constexpr int BB = 0;                                          // [64 n][144 k]      18 432
     static constexpr int DF = BB + (GT_VK / 8) * GT_BB_CHUNK;             // [128 m][128]       32 768 (cols 64.. zero)
     static constexpr int V = DF + 16 * TC_CHUNK;                          // [128 m][144] bf16  36 864
-    static constexpr int DV = V + (GT_VK / 8) * TC_CHUNK;                 // [128 m][148] fp32  75 776
+    static constexpr int DV = V + (GT_VK / 8) * GT_VCHUNK;                 // [128 m][148] fp32  75 776
     static constexpr int KNOTS = DV + TC_TM * GT_DVS * 4;
     static constexpr int YANG = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
     static constexpr int MBAR = YANG + TC_TM;
@@ -234,7 +235,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 } else {
                     const int kk = i * EGN_CA + (sub - EGN_CS / 4) * 4;
                     up = *reinterpret_cast<const float4*>(dvs + srow * GT_DVS + kk);
-                    *reinterpret_cast<uint2*>(vs + (kk >> 3) * TC_CHUNK + srow * 16 + (kk & 7) * 2) =
+                    *reinterpret_cast<uint2*>(vs + (kk >> 3) * GT_VCHUNK + srow * 16 + (kk & 7) * 2) =
                         make_uint2(pack_hi(prod.x, prod.y), pack_hi(prod.z, prod.w));
                 }
                 if (slive) {
@@ -278,7 +279,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             const uint32_t first = it > 0 ? 1u : 0u;
 #pragma unroll
             for (int ks = 0; ks < TC_TM / 16; ++ks)
-                tc_mma(tmem + GT_TM_DB, desc_mn(df_s + ks * 256), desc_mn(v_s + ks * 256), IDESC_DB, first | (ks > 0));
+                tc_mma(tmem + GT_TM_DB, desc_mn(df_s + ks * 256), desc_mn(v_s + ks * 256, GT_VCHUNK), IDESC_DB, first | (ks > 0));
             tc_commit(bar + 8);
         }
     }

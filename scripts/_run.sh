@@ -1,6 +1,6 @@
-timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -k "fused" 2>&1 | tail -2
-python bench.py --no-cpu-baseline --no-parity-line > gpurun_out/bd.json 2> gpurun_out/bd.err
+timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -k "backward" 2>&1 | tail -2
+python bench.py --mode train --rays 16384 --steps 20 --no-cpu-baseline --no-parity-line > gpurun_out/bt.json 2> gpurun_out/bt.err
 python -c "
 import json
-d=json.loads(open('gpurun_out/bd.json').read().strip().splitlines()[-1]); print(round(d['value']), d['ms_per_step'], d['roofline']['stage_ms'], round(d['e2e']['value']))"
-tail -1 gpurun_out/bd.err
+d=json.loads(open('gpurun_out/bt.json').read().strip().splitlines()[-1]); print('train 16384', round(d['value']), d['ms_per_step'])"
+tail -1 gpurun_out/bt.err
