@@ -1,2 +1,1 @@
-timeout 900 compute-sanitizer --tool racecheck --print-limit 8 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck.log 2>&1; grep -E "ERROR SUMMARY|hazard|RACECHECK SUMMARY|Error|smoke" gpurun_out/sanitizer_racecheck.log | head -12
-timeout 600 compute-sanitizer --tool synccheck --print-limit 8 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_synccheck.log 2>&1; grep -E "ERROR SUMMARY|Error|smoke" gpurun_out/sanitizer_synccheck.log | head -6
+timeout 600 python -m pytest tests/test_gpu_fullsize.py -x -q -s 2>&1 | grep -E "full size|passed|failed|Error|assert" | tail -8
