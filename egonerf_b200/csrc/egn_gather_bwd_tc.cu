@@ -67,6 +67,20 @@ struct GtCache {
     }
 };
 
+// one lane's 4 channels of a tap: fp32 tables (16 B) or the bf16 copy the throughput-mode forward gathered from (8 B —
+// half the bytes and half the L2 footprint next to the 99 MB gradient table)
+template <bool BF16>
+__device__ __forceinline__ float4 gt_tap(const EgnKernelCfg& k, unsigned off) {
+    if constexpr (BF16) {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(k.tables_bf16) + off));
+        return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                           __uint_as_float(q.y & 0xffff0000u));
+    } else {
+        return ldg4(k.tables + off);
+    }
+}
+
+template <bool BF16>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
                          const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
@@ -216,8 +230,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 const unsigned o0 = pbase + (ra + j0[ax]) * EGN_CF, o1 = pbase + (ra + j1[ax]) * EGN_CF;
                 const unsigned o2 = pbase + (rb + j0[ax]) * EGN_CF, o3 = pbase + (rb + j1[ax]) * EGN_CF;
                 const unsigned q0 = lbase + j0[al] * EGN_CF, q1 = lbase + j1[al] * EGN_CF;
-                const float4 t0 = ldg4(k.tables + o0), t1 = ldg4(k.tables + o1), t2 = ldg4(k.tables + o2), t3 = ldg4(k.tables + o3);
-                const float4 l0 = ldg4(k.tables + q0), l1 = ldg4(k.tables + q1);
+                const float4 t0 = gt_tap<BF16>(k, o0), t1 = gt_tap<BF16>(k, o1), t2 = gt_tap<BF16>(k, o2), t3 = gt_tap<BF16>(k, o3);
+                const float4 l0 = gt_tap<BF16>(k, q0), l1 = gt_tap<BF16>(k, q1);
                 const float w0 = wa0[ax] * wa0[ay], w1 = wa1[ax] * wa0[ay], w2 = wa0[ax] * wa1[ay], w3 = wa1[ax] * wa1[ay];
                 const float u0 = wa0[al], u1 = wa1[al];
                 float4 P = f4zero();
@@ -311,8 +325,14 @@ int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const fl
     if (M <= 0) return 0;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     const int blocks = (int)(tiles < 148 ? tiles : 148);
-    cudaFuncSetAttribute(egn_gather_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
-    egn_gather_bwd_tc_kernel<<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig, d_feat,
-                                                                           d_tables, g->basis[0], g->basis[1]);
+    if (k.tables_bf16 != nullptr) {
+        cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
+        egn_gather_bwd_tc_kernel<true><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
+                                                                                     d_feat, d_tables, g->basis[0], g->basis[1]);
+    } else {
+        cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
+        egn_gather_bwd_tc_kernel<false><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
+                                                                                      d_feat, d_tables, g->basis[0], g->basis[1]);
+    }
     return (int)cudaGetLastError();
 }

@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_fullsize.py -x -q -s 2>&1 | grep -E "full size|passed|failed|Error|assert" | tail -8
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
