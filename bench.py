@@ -214,7 +214,7 @@ def main():
         target = torch.rand(n_rays, 3, device=dev)
         params = [p for p in model.parameters()] + ([model.envmap.emission] if model.envmap is not None else [])
         # optimiser of train.py:172-186 (Adam, betas (0.9, 0.99), per-group learning rates), fused multi-tensor implementation
-        optimizer = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
+        optimizer = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001, merged=True), betas=(0.9, 0.99), fused=True)
 
     def step_device():
         if not train:
