@@ -208,7 +208,7 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     }
     if (!fused && c->shading <= EGN_SHADE_MLP) {
         if (c->mlp_mode == EGN_MLP_FP32) e = egn_launch_mlp(k, p, rays, n, feat, rgbs, st);
-        else e = egn_launch_mlp_tc(k, p, rays, n, feat, rgbs, c->mlp_mode == EGN_MLP_TC_SPLIT, nullptr, st);
+        else e = egn_launch_mlp_tc(k, p, rays, n, feat, rgbs, c->mlp_mode == EGN_MLP_TC_SPLIT, st);
         if (e) return cuda_fail("mlp", e);
     }
     mark(se, 3, st);

@@ -3,20 +3,6 @@
 #include <cuda_runtime.h>
 #include "egn_device.cuh"
 
-// workspace carve-up (per ray chunk of n rays, S samples/ray): see egn_abi.cu
-struct EgnWorkspace {
-    float* z;        // (n,S)      sorted sample depths (fine_z_vals, EgoNeRF.py:537)
-    float* fsig;     // (n,S)      density feature before feature2density
-    float* feat;     // (n,S,28)   appearance feature (27 used)
-    float* rgbs;     // (n,S,3)    decoded sample colours
-    float* wgt;      // (n,S)      compositing weights
-    float* bgw;      // (n)        background weight T_S
-    float* rgbpre;   // (n,3)      unclamped rgb (clamp mask of the backward pass)
-    float* d_rgbs;   // (n,S,3)    backward scratch
-    float* d_fsig;   // (n,S)
-    float* d_feat;   // (n,S,28)
-};
-
 int egn_launch_pack(const EgnConfig* cfg, const EgnParams* params, float* tables, cudaStream_t st);
 int egn_launch_unpack(const EgnConfig* cfg, const float* d_tables, const EgnGrads* grads, cudaStream_t st);
 
@@ -38,9 +24,8 @@ int egn_launch_envmap_bwd(int env_h, const float* emission, const float* dirs, l
                           float* d_emission, cudaStream_t st);
 
 // tensor-core colour decode (egn_mlp_tc.cu): split = 1 -> 3-term bf16 split (fp32-equivalent), 0 -> plain bf16
-bool egn_mlp_tc_supported(const EgnKernelCfg& k);
 int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
-                      float* rgbs, int split, int* err_flag, cudaStream_t st);
+                      float* rgbs, int split, cudaStream_t st);
 // fused fine pass (egn_fused.cu): gather + basis + MLP in one warp-specialised tcgen05 kernel (bf16 operands)
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                           float* fsig, float* feat_out, float* rgbs, cudaStream_t st);

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, SPLIT ? 1 : 2)
 egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ w1, const float* __restrict__ b1,
                   const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                   const float* __restrict__ b3, const float* __restrict__ rays, long long M,
-                  const float* __restrict__ feat, float* __restrict__ rgbs, int* __restrict__ err_flag) {
+                  const float* __restrict__ feat, float* __restrict__ rgbs) {
     // NQ threads share a row: thread t owns row (t & 127) and column block (t >> 7).  bf16 mode: 2 per row, 256 threads,
     // two CTAs per SM (the second CTA's CUDA-core phases hide the first one's MMAs); split mode (one CTA per SM because
     // of its 229 KB of operands): 4 per row, 512 threads, so that the serial phases between the MMAs are half as long.
@@ -227,29 +227,25 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         }
         __syncthreads();                                  // the next tile's X overwrites the partial-sum scratch
     }
-    if (!ok) { if (err_flag) atomicExch(err_flag, 1); __trap(); }      // a lost tcgen05.commit arrive: fail loudly, never hang
+    if (!ok) __trap();                                      // a lost tcgen05.commit arrive: fail loudly, never hang
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
 }
 
-bool egn_mlp_tc_supported(const EgnKernelCfg& k) {
-    return k.shading == EGN_SHADE_MLP_FEA && k.view_pe == 2 && k.fea_pe == 2 && k.app_dim >= 1 && k.app_dim <= 27;
-}
-
 int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
-                      float* rgbs, int split, int* err_flag, cudaStream_t st) {
+                      float* rgbs, int split, cudaStream_t st) {
     const long long M = n * k.S;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     const int blocks = (int)(tiles < 148 * (split ? 1 : 2) ? tiles : 148 * (split ? 1 : 2));
     if (split) {
         cudaFuncSetAttribute(egn_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<true>::TOTAL);
         egn_mlp_tc_kernel<true><<<blocks, 512, TcLayout<true>::TOTAL, st>>>(
-            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs, err_flag);
+            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs);
     } else {
         cudaFuncSetAttribute(egn_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<false>::TOTAL);
         egn_mlp_tc_kernel<false><<<blocks, 256, TcLayout<false>::TOTAL, st>>>(
-            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs, err_flag);
+            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs);
     }
     return (int)cudaGetLastError();
 }
