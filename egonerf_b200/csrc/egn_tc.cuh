@@ -33,14 +33,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-// bounded wait: a lost arrive must not hang the GPU — after ~2^28 polls the CTA flags an error and carries on
+// bounded wait: a lost arrive must not hang the GPU.  try_wait with a suspend-time hint parks the warp in hardware (no issue
+// slots burnt, wake-up right after the arrive); ~400 x 10 ms without completion -> the caller traps.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    for (uint32_t spin = 0; spin < 400u; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
         if (done) return true;
-        if (spin > 4) __nanosleep(spin > 64 ? 256 : 32);          // back off: a spinning warp steals issue slots from the working ones
     }
     return false;
 }
