@@ -59,6 +59,8 @@ PROTOTYPES = {
     "egn_pack_tables": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p]),
     "egn_table_bf16_elems": (C.c_int64, [C.POINTER(EgnConfig)]),
     "egn_pack_tables_bf16": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "egn_adam_tables": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnGrads), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "egn_unpack_table_grads": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.POINTER(EgnGrads), C.c_void_p]),
     "egn_workspace_bytes": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),
     "egn_workspace_bytes_eval": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),

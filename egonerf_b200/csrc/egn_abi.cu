@@ -106,6 +106,21 @@ extern "C" int32_t egn_pack_tables_bf16(const EgnConfig* c, const float* tables,
     return e ? cuda_fail("egn_pack_tables_bf16", e) : 0;
 }
 
+extern "C" int32_t egn_adam_tables(const EgnConfig* c, const EgnGrads* params_out, const float* d_tables, float* exp_avg,
+                                   float* exp_avg_sq, float* tables, void* tables_bf16, float lr, float beta1, float beta2,
+                                   float eps, int32_t step, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!params_out || !d_tables || !exp_avg || !exp_avg_sq || !tables) return fail("null argument");
+    if (step < 1) return fail("Adam step counts from 1");
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i)
+            if (!params_out->density_plane[h][i] || !params_out->density_line[h][i] || !params_out->app_plane[h][i] ||
+                !params_out->app_line[h][i]) return fail("missing factor tensor h=%d i=%d", h, i);
+    int e = egn_launch_adam_tables(c, params_out, d_tables, exp_avg, exp_avg_sq, tables, tables_bf16, lr, beta1, beta2, eps, step,
+                                   (cudaStream_t)stream);
+    return e ? cuda_fail("egn_adam_tables", e) : 0;
+}
+
 extern "C" int32_t egn_unpack_table_grads(const EgnConfig* c, const float* d_tables, const EgnGrads* g, void* stream) {
     if (validate(c, false)) return 1;
     if (!d_tables || !g) return fail("null argument");

@@ -29,6 +29,9 @@ int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* ra
 // fused fine pass (egn_fused.cu): gather + basis + MLP in one warp-specialised tcgen05 kernel (bf16 operands)
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                           float* fsig, float* feat_out, float* rgbs, cudaStream_t st);
+int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables, float* m, float* v,
+                           float* tables, void* tables_bf16, float lr, float beta1, float beta2, float eps, int step,
+                           cudaStream_t st);
 int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st);
 int egn_launch_erp_rays(int H, int W, int row0, int n_rows, const float* c2w_host, float* rays, cudaStream_t st);
 // backward

@@ -3,6 +3,7 @@
 // models/EgoNeRF.py:124-133), and the inverse scatter of table gradients back to NCHW.
 #include "egn_device.cuh"
 #include <cuda_bf16.h>
+#include <math.h>
 #include "egn_host.h"
 
 struct PackJob {
@@ -128,5 +129,94 @@ int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables
     const EgnLayout L = egn_make_layout(cfg->grid);
     const long long n4 = L.pc[0][0] / 4;                    // the fine sections come first
     egn_pack_bf16_kernel<<<148 * 4, 256, 0, st>>>(tables, reinterpret_cast<__nv_bfloat162*>(tables_bf16), n4);
+    return (int)cudaGetLastError();
+}
+
+// =================================================================================================
+// Adam step of the factor tensors in render-table space (optimiser of train.py:172-186 = torch.optim.Adam
+// without weight decay / amsgrad).  One pass reads the table-layout gradient egn_render_backward produced (no unpack), the
+// moments (kept in table layout) and the current value (the fp32 table IS the parameter, texel-interleaved), and writes
+// moments, the fp32 table, its bf16 copy and — through a shared-memory transpose, coalesced along texels — the NCHW
+// parameter tensors.  Replaces egn_unpack_kernel + the framework's Adam + egn_pack_kernel (fine) + egn_pack_bf16_kernel.
+// =================================================================================================
+struct AdamHp { float lr, beta1, beta2, eps, bc1, bc2_sqrt; };
+
+__global__ void __launch_bounds__(256)
+egn_adam_tables_kernel(const __grid_constant__ PackJobs jobs, const float* __restrict__ d_tab, float* __restrict__ m_tab,
+                       float* __restrict__ v_tab, float* __restrict__ tab, __nv_bfloat162* __restrict__ tab16, AdamHp hp) {
+    __shared__ float tile[EGN_CF][33];
+    const PackJob& J = jobs.j[blockIdx.y];
+    const long long HW = (long long)J.H * J.W;
+    const long long n_tiles = (HW + 31) / 32;
+    const float step_size = hp.lr / hp.bc1;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long tex0 = t * 32;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int f = threadIdx.x + 256 * j;             // float4 index inside the 32-texel x 64-channel tile
+            const int tx = f >> 4, cg = f & 15;
+            if (tex0 + tx < HW) {
+                const long long e4 = (J.off + (tex0 + tx) * EGN_CF) / 4 + cg;
+                const float4 g = reinterpret_cast<const float4*>(d_tab)[e4];
+                float4 m = reinterpret_cast<float4*>(m_tab)[e4], v = reinterpret_cast<float4*>(v_tab)[e4];
+                float4 p = reinterpret_cast<float4*>(tab)[e4];
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+                float mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    mm[q] = mm[q] + (gg[q] - mm[q]) * (1.f - hp.beta1);                 // lerp, as torch's fused kernel
+                    vv[q] = hp.beta2 * vv[q] + (1.f - hp.beta2) * gg[q] * gg[q];
+                    const float denom = sqrtf(vv[q]) / hp.bc2_sqrt + hp.eps;
+                    pp[q] = pp[q] - step_size * (mm[q] / denom);
+                    tile[cg * 4 + q][tx] = pp[q];
+                }
+                reinterpret_cast<float4*>(m_tab)[e4] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                reinterpret_cast<float4*>(v_tab)[e4] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                reinterpret_cast<float4*>(tab)[e4] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                if (tab16) {
+                    tab16[2 * e4] = __floats2bfloat162_rn(pp[0], pp[1]);
+                    tab16[2 * e4 + 1] = __floats2bfloat162_rn(pp[2], pp[3]);
+                }
+            }
+        }
+        __syncthreads();
+        // NCHW parameters: warp w writes channels 8w .. 8w+7, lanes run along the 32 texels (128-byte stores)
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (tex0 + lane < HW) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = 8 * w + i;
+                float* dst = (c < EGN_CS) ? J.dst_d + (long long)c * HW : J.dst_a + (long long)(c - EGN_CS) * HW;
+                dst[tex0 + lane] = tile[c][lane];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables, float* m, float* v,
+                           float* tables, void* tables_bf16, float lr, float beta1, float beta2, float eps, int step,
+                           cudaStream_t st) {
+    PackJobs jobs{};
+    const int n = fill_jobs(cfg, nullptr, params_out, jobs, false);
+    AdamHp hp;
+    hp.lr = lr; hp.beta1 = beta1; hp.beta2 = beta2; hp.eps = eps;
+    hp.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    hp.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    dim3 grid(148, n);
+    egn_adam_tables_kernel<<<grid, 256, 0, st>>>(jobs, d_tables, m, v, tables, reinterpret_cast<__nv_bfloat162*>(tables_bf16), hp);
+    int e = (int)cudaGetLastError();
+    if (e) return e;
+    // pooled coarse tables from the updated density parameters (EgoNeRF.update_coarse_sigma_grid, EgoNeRF.py:124-133)
+    PackJobs cj{};
+    EgnParams src{};
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) { src.density_plane[h][i] = params_out->density_plane[h][i]; src.density_line[h][i] = params_out->density_line[h][i]; }
+    PackJobs all{};
+    const int na = fill_jobs(cfg, &src, nullptr, all, true);
+    int nc = 0;
+    for (int i = 0; i < na; ++i) if (all.j[i].type != 0) cj.j[nc++] = all.j[i];
+    dim3 cgrid(148, nc);
+    egn_pack_kernel<<<cgrid, 256, 0, st>>>(cj, tables);
     return (int)cudaGetLastError();
 }

@@ -91,21 +91,26 @@ class _VolumeRender(torch.autograd.Function):
         cfg = model._config(opts)
         d_tables = torch.zeros_like(tables)
         plist = model._param_list()
+        table_opt = getattr(model, "_table_opt", None)
         # one allocation for every gradient: the 24 factor gradients are overwritten by egn_unpack_table_grads, the rest
-        # (basis, MLP, envmap) is accumulated into and must start at zero — a single fill instead of one per tensor
-        sizes = [p.numel() for p in plist]
+        # (basis, MLP, envmap) is accumulated into and must start at zero — a single fill instead of one per tensor.
+        # With a table-space optimiser attached (egonerf_b200/optim.py) the factor gradients stay in table layout.
+        sizes = [0 if (table_opt is not None and i < 24) else p.numel() for i, p in enumerate(plist)]
         flat = torch.empty(sum(sizes), device=tables.device, dtype=torch.float32)
         n_fac = sum(sizes[:24])
         flat[n_fac:].zero_()
         grads, off = [], 0
         for p, sz in zip(plist, sizes):
-            grads.append(flat[off:off + sz].view_as(p))
+            grads.append(flat[off:off + sz].view_as(p) if sz else None)
             off += sz
         G = model._grads_struct(grads)
         _lib.check(lib.egn_render_backward(cfg, model._params_struct(), tables.data_ptr(), rays.data_ptr(), ctx.n,
                                            ws.data_ptr(), _lib.ptr(d_rgb), _lib.ptr(d_bg), _lib.ptr(d_env),
                                            _lib.ptr(d_alpha), d_tables.data_ptr(), G, _stream()))
-        _lib.check(lib.egn_unpack_table_grads(cfg, d_tables.data_ptr(), G, _stream()))
+        if table_opt is not None:
+            table_opt.accumulate(d_tables)
+        else:
+            _lib.check(lib.egn_unpack_table_grads(cfg, d_tables.data_ptr(), G, _stream()))
         return (None, None, None, None, None, None) + tuple(grads)
 
 
@@ -296,7 +301,10 @@ class EgoNeRF(torch.nn.Module):
 
     def update_coarse_sigma_grid(self):
         """Reference: AvgPool refresh of the coarse density grid (EgoNeRF.py:124-133, called every iteration by
-        train.py:356-357).  Here: re-pack the render tables (interleaved fine tables + pooled coarse tables)."""
+        train.py:356-357).  Here: re-pack the render tables (interleaved fine tables + pooled coarse tables).  With a
+        table-space optimiser attached the tables are already up to date after its step (it writes them itself)."""
+        if getattr(self, "_table_opt", None) is not None and self._table_opt.tables_fresh:
+            return
         self._tables_key = None
 
     def _render_tables(self):
@@ -481,6 +489,9 @@ class EgoNeRF(torch.nn.Module):
         persistent flat bucket (egonerf_b200/sharding.py)."""
         from ..sharding import GradientBucket
         ps = self._param_list()
+        if getattr(self, "_table_opt", None) is not None:        # factor gradients live in table layout: one buffer already
+            self._table_opt.allreduce(group, average)
+            ps = ps[24:]
         if getattr(self, "_bucket", None) is None or [id(p) for p in self._bucket.params] != [id(p) for p in ps]:
             self._bucket = GradientBucket(ps)
         self._bucket.gather_from_params()

@@ -123,6 +123,15 @@ int32_t egn_samples_per_ray(const EgnConfig* cfg);
  * re-run whenever the parameters change (once per optimiser step in training). */
 int64_t egn_table_floats(const EgnConfig* cfg);
 int32_t egn_pack_tables(const EgnConfig* cfg, const EgnParams* params, float* tables /*device*/, void* stream);
+/* Adam step (torch.optim.Adam semantics without weight decay / amsgrad; train.py:172-186) of the 24 factor tensors in
+ * render-table space: consumes the table-layout gradient of egn_render_backward directly (no
+ * egn_unpack_table_grads), keeps exp_avg / exp_avg_sq in table layout (egn_table_floats floats each, caller-zeroed once),
+ * and writes the updated values to the NCHW parameter tensors (`params_out`), the fp32 render tables, their bf16 copy
+ * (optional) and the pooled coarse tables (EgoNeRF.update_coarse_sigma_grid, models/EgoNeRF.py:124-133).  step counts from 1. */
+int32_t egn_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables /*device*/,
+                        float* exp_avg /*device*/, float* exp_avg_sq /*device*/, float* tables /*device*/,
+                        void* tables_bf16 /*device, nullable*/, float lr, float beta1, float beta2, float eps, int32_t step,
+                        void* stream);
 /* bf16 copy of the fine sections (same element offsets; egn_table_bf16_elems elements of 2 bytes) for the throughput mode */
 int64_t egn_table_bf16_elems(const EgnConfig* cfg);
 int32_t egn_pack_tables_bf16(const EgnConfig* cfg, const float* tables /*device*/, void* tables_bf16 /*device*/, void* stream);

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--every", type=int, default=50)
+    ap.add_argument("--table-adam", action="store_true", help="throughput run uses egonerf_b200.optim.TableAdam")
     args = ap.parse_args()
     dev = "cuda:0"
     teacher = model_from_scene(make_scene(n_voxels=args.voxels, seed=7), dev)
@@ -45,7 +46,11 @@ def main():
     for name, mode, tables in (("parity (tc_split fwd, fp32 bwd)", "tc_split", "f32"), ("throughput (tc_bf16, bf16 tables)", "tc_bf16", "bf16")):
         model = model_from_scene(student_scene, dev)
         model.mlp_mode, model.table_dtype = mode, tables
-        opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
+        if args.table_adam and mode == "tc_bf16":
+            from egonerf_b200.optim import TableAdam
+            opt = TableAdam(model, 0.02, 0.001)
+        else:
+            opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
         g = torch.Generator(device=dev).manual_seed(1)
         curve = []
         torch.cuda.synchronize()
@@ -60,7 +65,7 @@ def main():
             if it == args.steps:
                 break
             idx = torch.randint(0, rays_all.shape[0], (args.batch,), device=dev, generator=g)
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad()
             rgb = model(rays_all[idx], is_train=True, seed=1000 + it, **RENDER_KW)[0]
             loss = ((rgb - tgt_all[idx]) ** 2).mean()
             loss.backward()
