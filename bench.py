@@ -143,7 +143,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--table-adam", action="store_true", help="train mode: table-space fused Adam (egn_adam_tables) instead of torch's")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="train mode: torch.optim.Adam over the reference's parameter groups (what an unchanged train.py does) "
+                         "instead of the table-space fused Adam (egonerf_b200.optim.TableAdam)")
     ap.add_argument("--no-parity-line", action="store_true", help="skip the extra fp32-parity-mode measurement")
     ap.add_argument("--tables", default="bf16", choices=["f32", "bf16"], help="dtype of the fine render tables (bf16 needs --mlp tc_bf16)")
     ap.add_argument("--mlp", default="tc_bf16", choices=["fp32", "tc_split", "tc_bf16"],
@@ -215,7 +217,7 @@ def main():
         target = torch.rand(n_rays, 3, device=dev)
         params = [p for p in model.parameters()] + ([model.envmap.emission] if model.envmap is not None else [])
         # optimiser of train.py:172-186 (Adam, betas (0.9, 0.99), per-group learning rates), fused multi-tensor implementation
-        if args.table_adam:
+        if not args.torch_adam:
             from egonerf_b200.optim import TableAdam
             optimizer = TableAdam(model, 0.02, 0.001, 0.1)
             config["optimizer"] = "TableAdam (egn_adam_tables: Adam + table refresh in one pass)"
@@ -231,7 +233,7 @@ def main():
                 return out
         for p in params:
             p.grad = None
-        if args.table_adam:
+        if not args.torch_adam:
             optimizer.zero_grad()
         rgb = model(rays_dev, is_train=True, seed=1234, ray_index0=ray0, **kw)[0]
         loss = torch.mean((rgb - target) ** 2)
@@ -266,7 +268,7 @@ def main():
             return
         for p in params:
             p.grad = None
-        if args.table_adam:
+        if not args.torch_adam:
             optimizer.zero_grad()
         rgb = volume_renderer(rays_host, model, chunk=n_rays, is_train=True, device=dev, **kw)[0]
         loss = torch.mean((rgb - target) ** 2)
