@@ -359,8 +359,11 @@ def main():
                 "whole_path": {"bytes_per_ray": b_ray, "achieved": value / world * b_ray / 1e9,
                                "frac": value / world * b_ray / 1e9 / peak}}
 
-    dtype = {"fp32": "f32", "tc_split": "f32 (tensor-core MLP, 3-term bf16 split, fp32-equivalent)",
-             "tc_bf16": "bf16 MMA operands, fp32 accumulate; " + ("bf16" if args.tables == "bf16" else "f32") + " tables; f32 density/compositing"}[args.mlp]
+    dtype = "bf16" if args.mlp == "tc_bf16" else "f32"
+    config["arithmetic"] = {"fp32": "fp32 everywhere (FFMA MLP)",
+                            "tc_split": "fp32 tables; tcgen05 MLP and mma.sync basis with 3-term bf16 split (fp32-equivalent), fp32 accumulate",
+                            "tc_bf16": "bf16 MMA operands with fp32 accumulate; " + ("bf16" if args.tables == "bf16" else "fp32")
+                                       + " factor tables; density, transmittance and compositing in fp32"}[args.mlp]
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
@@ -375,7 +378,7 @@ def main():
             ms_p = timed(step_device, max(3, args.steps // 2), 3)
         st_p = [x * (n_rays / chunk) for x in model.stage_times(rays_dev[:chunk], repeats=3, **kw)]
         line["parity_mode"] = {"value": n_rays * world * max(3, args.steps // 2) / (ms_p * 1e-3), "unit": "rays/s",
-                               "dtype": "f32 tables, tcgen05 MLP with 3-term bf16 split (rgb within 1e-4 of the reference)",
+                               "dtype": "f32", "arithmetic": "fp32 tables, tcgen05 MLP + mma.sync basis with 3-term bf16 split (rgb within 1e-4 of the reference)",
                                "stage_ms": dict(zip(["sampler", "gather+basis", "mlp", "composite"], [round(x, 4) for x in st_p]))}
         model.mlp_mode, model.table_dtype = args.mlp, args.tables
     if rank == 0:
