@@ -6,6 +6,9 @@ import numpy as np
 import torch
 
 
+MIN_EVAL_CHUNK = 65536
+
+
 def volume_renderer(rays, model, chunk=4096, n_coarse=-1, n_fine=0, ndc_ray=False, white_bg=True, is_train=False,
                     exp_sampling=False, device='cuda', empty_gpu_cache=False, pretrain_envmap=False,
                     pivotal_sample_th=0., resampling=False, use_coarse_sample=True, interval_th=False):
@@ -13,6 +16,13 @@ def volume_renderer(rays, model, chunk=4096, n_coarse=-1, n_fine=0, ndc_ray=Fals
         return model(rays_chunk=rays.to(device), pretrain_envmap=True)
     rgbs, depths, bgs, envs, alphas = [], [], [], [], []
     n_all = rays.shape[0]
+    # `chunk` is a memory knob of the reference (its forward materialises (N, S, 150) tensors).  Here a ray's result does
+    # not depend on the chunk it is rendered in (tests/test_gpu_parity.py::test_edge_sizes, test_gpu_fullsize.py) and the
+    # eval workspace is 24-136 B/sample, so evaluation regroups small chunks (renderer.evaluation passes 4096) into chunks
+    # of MIN_EVAL_CHUNK rays: same outputs, 16x fewer launches.  Not for the uniform march, whose eval mode hands on the
+    # depths of the FIRST ray of each chunk (EgoNeRF.py:515-516) and is therefore chunk-dependent in the reference itself.
+    if not is_train and exp_sampling and chunk < MIN_EVAL_CHUNK:
+        chunk = MIN_EVAL_CHUNK
     start = time.time()
     has_env = False
     for c0 in range(0, n_all, chunk):

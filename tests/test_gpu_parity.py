@@ -191,6 +191,7 @@ def test_erp_frame_config_512_samples_against_oracle():
 def test_chunked_driver_equals_single_chunk():
     """renderer.volume_renderer's chunk loop (renderer.py:25-26) must not change results (ragged last chunk included)."""
     from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200 import renderer
     from egonerf_b200.renderer import volume_renderer
     from egonerf_b200.synthetic import make_rays
     scene = scene_for(dict(n_voxels=40 ** 3, seed=8, envmap_h=32, near_far=(0.1, 300.), r0=0.05, density_shift=-10.))
@@ -199,9 +200,14 @@ def test_chunked_driver_equals_single_chunk():
     import contextlib, io
     with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
         a = volume_renderer(rays, model, chunk=1000, is_train=False, device="cuda:0", **RENDER_KW)
-        b = volume_renderer(rays, model, chunk=96, is_train=False, device="cuda:0", empty_gpu_cache=True, **RENDER_KW)
-    for x, y in zip(a, b):
-        assert np.array_equal(x.cpu().numpy(), y)
+        c = volume_renderer(rays, model, chunk=96, is_train=False, device="cuda:0", empty_gpu_cache=True, **RENDER_KW)   # regrouped
+        keep, renderer.MIN_EVAL_CHUNK = renderer.MIN_EVAL_CHUNK, 1          # force the literal 96-ray chunk loop (11 chunks, ragged tail)
+        try:
+            b = volume_renderer(rays, model, chunk=96, is_train=False, device="cuda:0", empty_gpu_cache=True, **RENDER_KW)
+        finally:
+            renderer.MIN_EVAL_CHUNK = keep
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x.cpu().numpy(), y) and np.array_equal(y, z)
 
 
 @pytest.mark.parametrize("mode,tables", [("fp32", "f32"), ("tc_split", "f32"), ("tc_bf16", "f32"), ("tc_bf16", "bf16")])
