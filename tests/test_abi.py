@@ -143,3 +143,29 @@ def test_ctypes_structs_mirror_the_header_field_by_field():
     assert fields("EgnConfig") == [f[0] for f in _lib.EgnConfig._fields_]
     assert fields("EgnParams") == [f[0] for f in _lib.EgnParams._fields_]
     assert fields("EgnOutputs") == [f[0] for f in _lib.EgnOutputs._fields_]
+
+
+def test_product_code_never_touches_the_oracle_or_the_reference_tree():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use oracle/; nothing shipped may read
+    /root/reference (it does not exist on the GPU box)."""
+    import ast
+    pkg = os.path.join(ROOT, "egonerf_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                if "/root/reference" in text or re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M):
+                    offenders.append(os.path.join(base, f))
+    for f in os.listdir(os.path.join(ROOT, "shim")):
+        pass
+    assert not offenders, offenders
+    # bench.py: the oracle is imported inside oracle_rays_per_s (cpu_baseline / --impl reference) and nowhere else
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef):
+            uses = any(isinstance(n, ast.ImportFrom) and n.module and n.module.startswith("oracle") for n in ast.walk(node))
+            assert (not uses) or node.name == "oracle_rays_per_s", node.name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any(getattr(n, "module", "") and str(n.module).startswith("oracle") for n in top)
+    assert "/root/reference" not in open(os.path.join(ROOT, "bench.py")).read().replace("Nothing here reads /root/reference", "")
