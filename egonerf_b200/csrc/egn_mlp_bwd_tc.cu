@@ -98,27 +98,37 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     uint32_t it = 0;
     bool ok = true;
     float acc3[3] = {0.f, 0.f, 0.f};
+    // this thread's 8 input elements of a tile (features, then view direction / constant 1 / padding), fetched one tile
+    // ahead so that the global-memory latency overlaps the last MMA batch of the previous tile
+    auto load_elements = [&](long long t, float (&e8)[8]) {
+        const long long g_m = t * TC_TM + row;
+        const bool lv = t < tiles && g_m < M;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e8[j] = 0.f;
+        if (lv) {
+            const float4* f4 = reinterpret_cast<const float4*>(feat + g_m * EGN_FEAT_STRIDE) + 2 * q;
+            const float4 a = __ldg(f4);
+            e8[0] = a.x; e8[1] = a.y; e8[2] = a.z; e8[3] = a.w;
+            if (q < 3) { const float4 b = __ldg(f4 + 1); e8[4] = b.x; e8[5] = b.y; e8[6] = b.z; e8[7] = b.w; }
+        }
+        const float* dir = rays + (lv ? g_m / k.S : 0) * 6 + 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = 8 * q + j;
+            if (e >= AD) e8[j] = (e < AD + 3) ? (lv ? __ldg(dir + (e - AD)) : 0.f) : (e == AD + 3 ? 1.f : 0.f);
+        }
+    };
+    float el_next[8];
+    load_elements(blockIdx.x, el_next);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const long long gm = tile * TC_TM + row;
         const bool live = gm < M;
         const uint32_t par = it & 1;
-        // ---- P1. X rows: 8 elements per thread -> 5 chunks ----
+        // ---- P1. X rows: 8 elements per thread -> 5 chunks (the elements were loaded one tile ahead) ----
         float el[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) el[j] = 0.f;
-        if (live) {
-            const float4* f4 = reinterpret_cast<const float4*>(feat + gm * EGN_FEAT_STRIDE) + 2 * q;
-            const float4 a = __ldg(f4);
-            el[0] = a.x; el[1] = a.y; el[2] = a.z; el[3] = a.w;
-            if (q < 3) { const float4 b = __ldg(f4 + 1); el[4] = b.x; el[5] = b.y; el[6] = b.z; el[7] = b.w; }
-        }
+        for (int j = 0; j < 8; ++j) el[j] = el_next[j];
         {
-            const float* dir = rays + (live ? gm / k.S : 0) * 6 + 3;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int e = 8 * q + j;
-                if (e >= AD) el[j] = (e < AD + 3) ? (live ? __ldg(dir + (e - AD)) : 0.f) : (e == AD + 3 ? 1.f : 0.f);
-            }
             float v[40];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -168,17 +178,17 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
             tc_commit(bar + 8);
         }
         // ---- P3. H2 = relu(D2) (b2 rides in W2); dO; dZ2 = (dO W3) [H2 > 0] ----
+        float dq[3] = {0.f, 0.f, 0.f};                     // loaded while the layer-2 MMAs run
+        if (live) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float c = __ldg(rgbs + gm * 3 + ch);
+                dq[ch] = __ldg(d_rgbs + gm * 3 + ch) * c * (1.f - c);
+            }
+        }
         ok &= mbar_wait(bar + 8, par);
         tc_fence_after();
         {
-            float dq[3] = {0.f, 0.f, 0.f};
-            if (live) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float c = rgbs[gm * 3 + ch];
-                    dq[ch] = d_rgbs[gm * 3 + ch] * c * (1.f - c);
-                }
-            }
             if (q == 0) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
@@ -249,6 +259,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 tc_mma(tmem + BT_WORK, desc_k(dz_s + ks * 2 * TC_CHUNK), desc_mn(w1_s + ks * 256), IDESC_B1X, ks > 0);
             tc_commit(bar + 24);
         }
+        load_elements(tile + gridDim.x, el_next);          // in flight while the last MMA batch runs
         // ---- P5. d_feat through the positional encoding ----
         ok &= mbar_wait(bar + 24, par);
         tc_fence_after();

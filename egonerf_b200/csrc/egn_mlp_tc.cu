@@ -98,31 +98,37 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     uint32_t it = 0;
     bool ok = true;
+    // this thread's input elements of a tile: app features [EPT*q, EPT*q + EPT), then the view direction, then the
+    // constant 1 that carries b1, then padding.  Loaded one tile ahead (during the layer-2 MMA) so that the global-memory
+    // latency is off the critical path of the serial phase chain.
+    auto load_elements = [&](long long t, float (&el)[EPT]) {
+        const long long g_m = t * TC_TM + row;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) el[j] = 0.f;
+        if (t < tiles && g_m < M) {
+            const float4* f4 = reinterpret_cast<const float4*>(feat + g_m * EGN_FEAT_STRIDE) + q * (EPT / 4);
+#pragma unroll
+            for (int g = 0; g < EPT / 4; ++g) {
+                if (q * EPT + 4 * g < EGN_FEAT_STRIDE) {
+                    const float4 v = __ldg(f4 + g);
+                    el[4 * g] = v.x; el[4 * g + 1] = v.y; el[4 * g + 2] = v.z; el[4 * g + 3] = v.w;
+                }
+            }
+            const float* dir = rays + (g_m / k.S) * 6 + 3;
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int e = EPT * q + j;
+                if (e >= AD) el[j] = (e < AD + 3) ? __ldg(dir + (e - AD)) : (e == AD + 3 ? 1.f : 0.f);
+            }
+        }
+    };
+    float el[EPT];
+    load_elements(blockIdx.x, el);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const long long gm = tile * TC_TM + row;
         const bool live = gm < M;
         // ---- A. input rows: EPT elements per thread -> chunks of [x, sin x, cos x, sin 2x, cos 2x] ----
         {
-            float el[EPT];
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) el[j] = 0.f;
-            if (live) {
-                const float4* f4 = reinterpret_cast<const float4*>(feat + gm * EGN_FEAT_STRIDE) + q * (EPT / 4);
-#pragma unroll
-                for (int g = 0; g < EPT / 4; ++g) {
-                    if (q * EPT + 4 * g < EGN_FEAT_STRIDE) {
-                        const float4 v = __ldg(f4 + g);
-                        el[4 * g] = v.x; el[4 * g + 1] = v.y; el[4 * g + 2] = v.z; el[4 * g + 3] = v.w;
-                    }
-                }
-                // elements >= app_dim are the view direction, then the constant 1 that carries b1, then padding
-                const float* dir = rays + (gm / k.S) * 6 + 3;
-#pragma unroll
-                for (int j = 0; j < EPT; ++j) {
-                    const int e = EPT * q + j;
-                    if (e >= AD) el[j] = (e < AD + 3) ? dir[e - AD] : (e == AD + 3 ? 1.f : 0.f);
-                }
-            }
 #pragma unroll
             for (int pass = 0; pass < EPT / 8; ++pass) {
                 float v[40];
@@ -190,6 +196,7 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             }
             tc_commit(bar1);
         }
+        load_elements(tile + gridDim.x, el);              // next tile's inputs: in flight while layer 2 runs
         // ---- E. H2 = relu(D2 + b2); rgb = sigmoid(W3 H2 + b3) in fp32 ----
         ok &= mbar_wait(bar1, it & 1);
         tc_fence_after();
