@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegn_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -86,6 +86,8 @@ PROTOTYPES = {
     "egn_envmap_backward": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
     "egn_erp_rays": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_float_p, C.c_void_p, C.c_void_p]),
+    "egn_resample_factor": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "egn_host_sample_schedule": (C.c_int32, [C.c_float, C.c_float, C.c_float, C.c_int32, c_float_p]),
     "egn_host_r_knots": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p]),
 }

@@ -389,6 +389,15 @@ extern "C" int32_t egn_erp_rays(int32_t H, int32_t W, int32_t row0, int32_t n_ro
     return e ? cuda_fail("egn_erp_rays", e) : 0;
 }
 
+extern "C" int32_t egn_resample_factor(const float* src, int32_t channels, int32_t h, int32_t w, const float* ypos, int32_t h2,
+                                       const float* xpos, int32_t w2, float* dst, void* stream) {
+    if (channels <= 0 || h <= 0 || w <= 0 || h2 <= 0 || w2 <= 0) return fail("bad factor shape");
+    if (!src || !ypos || !xpos || !dst) return fail("null argument");
+    if (src == dst) return fail("egn_resample_factor cannot work in place");
+    int e = egn_launch_resample_factor(src, channels, h, w, ypos, h2, xpos, w2, dst, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_resample_factor", e) : 0;
+}
+
 // ---- host helpers -------------------------------------------------------------------------------------
 // "first K intervals forced to r0, the rest shifted" (EgoNeRF.py:72-76, coordinates.py:120-124), fp32 arithmetic
 static void force_linear_prefix(float* r, int n, float r0) {

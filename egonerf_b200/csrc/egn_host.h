@@ -33,6 +33,8 @@ int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, con
                            float* tables, void* tables_bf16, float lr, float beta1, float beta2, float eps, int step,
                            cudaStream_t st);
 int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st);
+int egn_launch_resample_factor(const float* src, int C, int H, int W, const float* ypos, int H2, const float* xpos, int W2,
+                               float* dst, cudaStream_t st);
 int egn_launch_erp_rays(int H, int W, int row0, int n_rows, const float* c2w_host, float* rays, cudaStream_t st);
 // backward
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,

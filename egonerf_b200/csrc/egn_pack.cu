@@ -220,3 +220,37 @@ int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, con
     egn_pack_kernel<<<cgrid, 256, 0, st>>>(cj, tables);
     return (int)cudaGetLastError();
 }
+
+// ---- coarse-to-fine resampling of one factor tensor (EgoNeRF.up_sampling_VM, models/EgoNeRF.py:415-425) ------------------
+// One thread per output texel of an NCHW tensor.  The source position of every output row / column comes from the host
+// (texel units): the exponential r ladder of coordinates.py:238-246 for an r axis, j*(L-1)/(L2-1) for an angular axis.
+// Taps and weights follow F.grid_sample(bilinear, zeros, align_corners=True): out-of-range taps contribute zero.
+__global__ void egn_resample_factor_kernel(const float* __restrict__ src, int C, int H, int W, const float* __restrict__ ypos,
+                                           int H2, const float* __restrict__ xpos, int W2, float* __restrict__ dst) {
+    const long long total = (long long)C * H2 * W2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x2 = (int)(idx % W2);
+    const int y2 = (int)((idx / W2) % H2);
+    const int c = (int)(idx / ((long long)W2 * H2));
+    const float ix = __ldg(xpos + x2), iy = __ldg(ypos + y2);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx1 = ix - x0f, wx0 = (x0f + 1.f) - ix;
+    const float wy1 = iy - y0f, wy0 = (y0f + 1.f) - iy;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float* img = src + (long long)c * H * W;
+    auto tap = [&](int y, int x) { return (x >= 0 && x < W && y >= 0 && y < H) ? __ldg(img + (long long)y * W + x) : 0.f; };
+    float acc = tap(y0, x0) * (wx0 * wy0);
+    acc += tap(y0, x0 + 1) * (wx1 * wy0);
+    acc += tap(y0 + 1, x0) * (wx0 * wy1);
+    acc += tap(y0 + 1, x0 + 1) * (wx1 * wy1);
+    dst[idx] = acc;
+}
+
+int egn_launch_resample_factor(const float* src, int C, int H, int W, const float* ypos, int H2, const float* xpos, int W2,
+                               float* dst, cudaStream_t st) {
+    const long long total = (long long)C * H2 * W2;
+    if (total == 0) return 0;
+    egn_resample_factor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, C, H, W, ypos, H2, xpos, W2, dst);
+    return (int)cudaGetLastError();
+}

@@ -339,6 +339,10 @@ class EgoNeRF(torch.nn.Module):
             co = self.coordinates
             if len(set(self.density_n_comp)) != 1 or len(set(self.app_n_comp)) != 1:
                 raise NotImplementedError("n_lamb_sigma / n_lamb_sh must be equal across the three factor pairs")
+            if [co.N_r, co.N_theta, co.N_phi] != self.gridSize.tolist():
+                raise RuntimeError(f"factor grid {self.gridSize.tolist()} != coordinate resolution "
+                                   f"{[co.N_r, co.N_theta, co.N_phi]}: call coordinates.set_resolution after "
+                                   "upsample_volume_grid (train.py:376-377)")
             near, inv = co.near.cpu(), co.inv_diff.cpu()
             self._cfg_static = dict(
                 grid=self.gridSize.tolist(), center=co.center.cpu().tolist(),
@@ -349,6 +353,9 @@ class EgoNeRF(torch.nn.Module):
 
     def _config(self, opts):
         co = self.coordinates
+        if self._sched.get('ladder') != (co.N_r, co.r0):          # set_resolution changes N_r and resets r0
+            self._sched = {'ladder': (co.N_r, co.r0)}
+            self._cfg_static = None
         st = self._static_config()
         cfg = _lib.EgnConfig()
         cfg.grid[:] = st["grid"]
@@ -463,9 +470,34 @@ class EgoNeRF(torch.nn.Module):
     def TV_loss_app(self, reg):
         return sum(reg(getattr(self, f'app_plane_{h}')[i]) * 1e-2 for i in range(3) for h in ('yin', 'yang'))
 
+    @torch.no_grad()
+    def up_sampling_VM(self, plane_coef, line_coef, res_target):
+        """EgoNeRF.up_sampling_VM (EgoNeRF.py:415-425): planes are (1, C, G[m1], G[m0]) -> ids [m1, m0]; lines ids [v]."""
+        for i in range(3):
+            m0, m1 = MAT_MODE[i]
+            plane_coef[i] = self.coordinates.up_sampling_VM(plane_coef[i].data, res_target=res_target, ids=[m1, m0])
+            line_coef[i] = self.coordinates.up_sampling_VM(line_coef[i].data, res_target=res_target, ids=[VEC_MODE[i]])
+        return plane_coef, line_coef
+
+    @torch.no_grad()
     def upsample_volume_grid(self, res_target):
-        raise NotImplementedError("coarse-to-fine upsampling is disabled in every shipped config "
-                                  "(configs/EgoNeRF/common.txt:12); SURVEY.md §8 f4")
+        """EgoNeRF.upsample_volume_grid (EgoNeRF.py:427-436; train.py:371-377): resample all 24 factor tensors to
+        `res_target` = [N_r, N_theta, N_phi].  As in the reference the caller then calls
+        `coordinates.set_resolution(res_target)` (which also resets r0 to 0.05, coordinates.py:206-215) and rebuilds the
+        optimiser; rendering between the two calls is refused (`_static_config`)."""
+        res_target = [int(v) for v in res_target]
+        self.app_plane_yin, self.app_line_yin = self.up_sampling_VM(self.app_plane_yin, self.app_line_yin, res_target)
+        self.density_plane_yin, self.density_line_yin = self.up_sampling_VM(self.density_plane_yin, self.density_line_yin, res_target)
+        self.app_plane_yang, self.app_line_yang = self.up_sampling_VM(self.app_plane_yang, self.app_line_yang, res_target)
+        self.density_plane_yang, self.density_line_yang = self.up_sampling_VM(self.density_plane_yang, self.density_line_yang, res_target)
+        self.gridSize = torch.LongTensor(res_target).to(self.gridSize.device)
+        self.update_stepSize(res_target)
+        # everything derived from the old resolution: render tables, ladders, cached scalars, table-space optimiser state
+        self._tables = self._tables_key = self._tables_bf16 = self._cfg_static = None
+        self._sched = {}
+        self._table_opt = None
+        self._bucket = None
+        print(f'upsamping to {res_target}')
 
     def updateAlphaMask(self, gridSize=None):
         raise NotImplementedError("alpha-mask update is disabled in every shipped config (common.txt:13); SURVEY.md §8 f4")

@@ -90,6 +90,55 @@ class YinYangSphericalCoords:
             self._knots = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(self.N_r + 1)), self.r0)
         return self._knots
 
+    def normalize_r(self, r: torch.Tensor) -> torch.Tensor:
+        """Host restatement of GenericSphericalCoords.normalize_r, interval_th branch (coordinates.py:112-131,156) for
+        the short ladders of `up_sampling_positions` (a few hundred radii): knot index + linear fraction, /N_r."""
+        g = self.r_knots()
+        hi = torch.clamp(torch.searchsorted(g, r.contiguous(), side='right'), 1, g.shape[0] - 1)
+        lo = hi - 1
+        return (lo + (r - g[lo]) / (g[hi] - g[lo])) / self.N_r
+
+    # ---- coarse-to-fine (coordinates.py:27-39, 226-266) ---------------------------------------------
+    def up_sampling_positions(self, axis: int, n_in: int, n_out: int, beside_r: bool = False) -> torch.Tensor:
+        """Source position (texel units, fp32, CPU) of each of the `n_out` samples along grid axis `axis` (0 = r).
+        r: the target ladder (same r0, ratio recomputed for n_out knots, short intervals clamped) normalised on the
+        CURRENT ladder and mapped through grid_sample's align_corners rule (coordinates.py:238-246,258-264);
+        theta / phi: F.interpolate(align_corners=True), src = j * (n_in - 1) / (n_out - 1) (coordinates.py:38-39) -- or,
+        for the angular axis of a plane that also has an r axis (`beside_r`), linspace(-1, 1) through grid_sample's rule
+        (coordinates.py:250-264); the two differ by rounding only."""
+        if axis == 0:
+            ratio = pow(self.far[0].cpu() / self.r0, 1 / (n_out - 1))
+            target = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(n_out)), self.r0)
+            r_samples = self.normalize_r(target) * 2 - 1
+            return ((r_samples + 1) / 2) * (n_in - 1)
+        if beside_r:
+            return ((torch.linspace(-1, 1, n_out) + 1) / 2) * (n_in - 1)
+        scale = torch.tensor(float(n_in - 1), dtype=torch.float32) / (n_out - 1) if n_out > 1 else torch.zeros(())
+        return torch.arange(n_out, dtype=torch.float32) * scale
+
+    def up_sampling_VM(self, weights: torch.Tensor, res_target, ids):
+        """coordinates.py:226-266 (r axis) / :27-39 (angular axes) for one (1, C, res[ids[0]], res[ids[1]] or 1) factor
+        tensor; the resampling itself runs in libegn_b200 (`egn_resample_factor`)."""
+        assert len(ids) in (1, 2), 'ids should be 1 or 2!'
+        if not weights.is_cuda:
+            raise RuntimeError("egonerf_b200 runs on CUDA tensors only (no CPU fallback)")
+        lib = _lib.load()
+        src = weights.detach().contiguous().float()
+        _, C, H, W = src.shape
+        H2 = int(res_target[ids[0]])
+        has_r = 0 in ids
+        ypos = self.up_sampling_positions(ids[0], H, H2, has_r)
+        if len(ids) == 2:
+            W2 = int(res_target[ids[1]])
+            xpos = self.up_sampling_positions(ids[1], W, W2, has_r)
+        else:
+            W2, xpos = 1, torch.zeros(1)
+        ypos, xpos = ypos.to(src.device).contiguous(), xpos.to(src.device).contiguous()
+        dst = torch.empty(1, C, H2, W2, device=src.device, dtype=torch.float32)
+        _lib.check(lib.egn_resample_factor(src.data_ptr(), C, H, W, ypos.data_ptr(), H2, xpos.data_ptr(), W2, dst.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        return torch.nn.Parameter(dst)
+
     # ---- operators (run in libegn_b200) -------------------------------------------------------------
     def _cfg(self):
         cfg = _lib.EgnConfig()

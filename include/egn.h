@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 4
+#define EGN_ABI_VERSION 5
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -214,6 +214,14 @@ int32_t egn_envmap_backward(const EgnConfig* cfg, const float* emission, const f
  * rays: device (n_rows * W, 6). */
 int32_t egn_erp_rays(int32_t H, int32_t W, int32_t row0, int32_t n_rows, const float* c2w /*host*/, float* rays /*device*/,
                      void* stream);
+
+/* Coarse-to-fine resampling of ONE factor tensor (train.py:371-377 -> EgoNeRF.upsample_volume_grid models/EgoNeRF.py:427-436
+ * -> coordinates.up_sampling_VM models/coordinates.py:27-39 (angular axes, F.interpolate) / :226-266 (r axis, F.grid_sample on
+ * the exponential ladder)).  src: NCHW (channels, h, w); dst: (channels, h2, w2).  ypos[h2] / xpos[w2] (device) hold the
+ * SOURCE position of every output row / column in texel units; bilinear, taps outside the source contribute zero.
+ * The host computes the positions (egonerf_b200/models/coordinates.py up_sampling_positions). */
+int32_t egn_resample_factor(const float* src /*device*/, int32_t channels, int32_t h, int32_t w, const float* ypos /*device*/,
+                            int32_t h2, const float* xpos /*device*/, int32_t w2, float* dst /*device*/, void* stream);
 
 /* ---- host helpers (no GPU): the two ladders, for callers that do not build them with torch ------ */
 int32_t egn_host_sample_schedule(float near_plane, float far_plane, float r0, int32_t n, float* z_out);   /* EgoNeRF.py:69-76 */

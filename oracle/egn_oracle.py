@@ -229,6 +229,74 @@ def avg_pool_factors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# f4: coarse-to-fine resampling of the factor tensors (train.py:371-377)
+# --------------------------------------------------------------------------------------------------
+def upsample_r_samples(far_r: torch.Tensor, r0: float, n_r_old: int, n_r_new: int) -> torch.Tensor:
+    """GenericSphericalCoords.up_sampling_VM, interval_th branch (coordinates.py:238-246): the n_r_new radii of the target
+    ladder (ratio recomputed for n_r_new, same r0, short intervals forced to r0) located on the CURRENT ladder, in [-1,1]."""
+    ratio = pow(far_r / r0, 1 / (n_r_new - 1))
+    target = _force_linear_prefix(_exp_ladder(r0, ratio, torch.arange(n_r_new)), r0)
+    return normalize_radius(target, r_reference_grid(far_r, r0, n_r_old))
+
+
+def _interp_align_corners(img: torch.Tensor, h2: int, w2: int) -> torch.Tensor:
+    """F.interpolate(mode='bilinear', align_corners=True) of a (C,H,W) image (Coordinates.up_sampling_VM,
+    coordinates.py:27-39): src = j * (in-1)/(out-1); index0 = trunc, index1 = index0 + 1 (clamped); lambda1 = src - index0."""
+    C, H, W = img.shape
+
+    def axis(n_in, n_out):
+        if n_out == n_in:
+            i0 = torch.arange(n_out)
+            return i0, i0, torch.zeros(n_out)
+        scale = (torch.tensor(float(n_in - 1)) / (n_out - 1)) if n_out > 1 else torch.zeros(())
+        src = torch.arange(n_out, dtype=torch.float32) * scale
+        i0 = src.long().clamp(max=n_in - 1)
+        i1 = i0 + (i0 < n_in - 1).long()
+        return i0, i1, (src - i0).clamp(0, 1)
+
+    y0, y1, ly = axis(H, h2)
+    x0, x1, lx = axis(W, w2)
+    top = img[:, y0][:, :, x0] * (1 - lx) + img[:, y0][:, :, x1] * lx
+    bot = img[:, y1][:, :, x0] * (1 - lx) + img[:, y1][:, :, x1] * lx
+    return top * (1 - ly)[None, :, None] + bot * ly[None, :, None]
+
+
+def upsample_factor(w: torch.Tensor, res_target, ids, far_r: torch.Tensor, r0: float, n_r_old: int) -> torch.Tensor:
+    """One (1,C,H,W) factor tensor -> res_target (GenericSphericalCoords.up_sampling_VM coordinates.py:226-266; planes are
+    passed with ids = [m1, m0], lines with ids = [v], EgoNeRF.py:415-425).  Axes without r: F.interpolate.  With r:
+    F.grid_sample on (r_samples x linspace(-1,1))."""
+    img = w[0]
+    C, H, W = img.shape
+    if 0 not in ids:
+        h2 = res_target[ids[0]]
+        w2 = res_target[ids[1]] if len(ids) == 2 else 1
+        return _interp_align_corners(img, h2, w2)[None]
+    rs = upsample_r_samples(far_r, r0, n_r_old, res_target[0])
+    if len(ids) == 1:                                        # (C, N_r, 1) line: x = -1 on a width-1 image, y = r_samples
+        return _tap1d(img[:, :, 0], rs).t().reshape(1, C, -1, 1)
+    other = 1 - ids.index(0)
+    lin = torch.linspace(-1, 1, res_target[ids[other]])
+    if ids.index(0) == 1:                                    # (C, other, r): x = r, y = other
+        xx, yy = torch.meshgrid(rs, lin, indexing="xy")      # (n_other, n_r)
+    else:                                                    # (C, r, other)
+        xx, yy = torch.meshgrid(lin, rs, indexing="xy")
+    out = _tap2d(img, xx.reshape(-1), yy.reshape(-1))        # (h2*w2, C)
+    return out.t().reshape(1, C, xx.shape[0], xx.shape[1])
+
+
+def upsample_factors(sd: Dict[str, torch.Tensor], res_target, far_r: torch.Tensor, r0: float, n_r_old: int):
+    """EgoNeRF.upsample_volume_grid (EgoNeRF.py:427-436) on a state dict: all 24 factor tensors, the rest copied."""
+    out = dict(sd)
+    for kind in ("density", "app"):
+        for h in ("yin", "yang"):
+            for i in range(3):
+                m0, m1 = MAT_MODE[i]
+                out[f"{kind}_plane_{h}.{i}"] = upsample_factor(sd[f"{kind}_plane_{h}.{i}"], res_target, [m1, m0], far_r, r0, n_r_old)
+                out[f"{kind}_line_{h}.{i}"] = upsample_factor(sd[f"{kind}_line_{h}.{i}"], res_target, [VEC_MODE[i]], far_r, r0, n_r_old)
+    return out
+
+
 def _products(sd, plane_key, line_key, coords, is_yang):
     """Returns list over i<3 of (M, C_i) plane*line products for the active hemisphere of every sample."""
     M = coords.shape[0]

@@ -188,6 +188,19 @@ def main():
     render_case("render_tiny_mlp.npz", make_scene(n_voxels=40 ** 3, seed=9, shading='MLP'), r64, False)
     render_case("render_tiny_rgb.npz", make_scene(n_voxels=40 ** 3, seed=10, shading='RGB', app_dim=3), r64, False)
 
+    # ---- 4. coarse-to-fine upsampling (train.py:371-377): 20^3 -> 28^3 voxels, then a render on the new grid
+    up = make_scene(n_voxels=20 ** 3, seed=3)
+    co, model = build_reference(up)
+    reso = co.N_to_reso(28 ** 3, model.aabb)
+    model.upsample_volume_grid(reso)
+    co.set_resolution(reso)                       # also resets r0 to 0.05 (coordinates.py:214)
+    model.update_coarse_sigma_grid()
+    with torch.no_grad():
+        out = ref_render(model, r64, False)
+    factors = {"sd:" + k: v for k, v in model.state_dict().items() if "plane" in k or "line" in k}
+    npz("upsample_tiny.npz", seed=3, n_voxels=20 ** 3, grid_old=np.array(up.grid), grid_new=np.array(reso), r0_after=co.r0,
+        rays=r64, rgb=out[0], depth=out[1], alpha=out[4], checksum=sd_checksum(up.state_dict), **factors)
+
 
 if __name__ == "__main__":
     main()

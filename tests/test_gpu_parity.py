@@ -283,3 +283,50 @@ def test_other_decoders_forward_and_gradients_against_oracle(shading, app_dim):
         r = sd[k].grad.numpy()
         rel = np.abs(p.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-9)
         assert rel <= 1e-3, (shading, k, rel)
+
+
+def test_upsample_volume_grid_matches_reference_golden():
+    """SURVEY 8 f4 (train.py:371-377): `model.upsample_volume_grid(reso)` + `coordinates.set_resolution(reso)` reproduce the
+    reference's resampled factor tensors (fp32 rounding: <= 2e-6 on values up to ~3) and its render on the new grid."""
+    import dataclasses
+    from oracle import egn_oracle as O
+    from egonerf_b200.scene_io import model_from_scene
+    g = load_golden("upsample_tiny")
+    scene = scene_for(dict(n_voxels=int(g["n_voxels"]), seed=int(g["seed"])))
+    assert np.allclose(checksum(scene.state_dict), g["checksum"], rtol=1e-6)
+    model = model_from_scene(scene)
+    rays = T(g["rays"])
+    before = _render(model, rays, False, None, None, {})[0]            # tables / ladders of the old grid are now cached
+    co = model.coordinates
+    reso = co.N_to_reso(28 ** 3, model.aabb)
+    assert reso == [int(v) for v in g["grid_new"]]
+    model.upsample_volume_grid(reso)
+    with pytest.raises(RuntimeError, match="set_resolution"):          # the window the reference never renders in
+        _render(model, rays, False, None, None, {})
+    co.set_resolution(reso)
+    assert co.r0 == float(g["r0_after"]) == 0.05                       # coordinates.py:214 quirk
+    sd = model.state_dict()
+    n = 0
+    for k in g.files:
+        if k.startswith("sd:"):
+            assert tuple(sd[k[3:]].shape) == g[k].shape, k
+            assert np.abs(sd[k[3:]].cpu().numpy() - g[k]).max() <= 2e-6, k
+            n += 1
+    assert n == 24 and model.gridSize.tolist() == reso
+    # against the oracle's restatement as well (same inputs)
+    new = O.upsample_factors(scene.state_dict, reso, O.max_corner_radius(scene.aabb), scene.r0, scene.grid[0])
+    assert max(float((sd[k].cpu() - v).abs().max()) for k, v in new.items() if "plane" in k or "line" in k) <= 2e-6
+    model.update_coarse_sigma_grid()
+    up_scene = dataclasses.replace(scene, grid=reso, r0=0.05, state_dict=new)
+    ok = stable_rays(up_scene, oracle_cfg(up_scene), rays, False, None, None).numpy()
+    rgb, depth, _, _, alpha = _render(model, rays, False, None, None, {})
+    assert alpha.shape == g["alpha"].shape
+    e_rgb = np.abs(rgb.cpu().numpy() - g["rgb"])[ok].max()
+    print(f"after upsampling: rgb {e_rgb:.2e}; moved {float((rgb - before).abs().max()):.2e} from the coarse grid's render")
+    assert e_rgb <= RGB_TOL
+    assert np.abs(depth.cpu().numpy() - g["depth"])[ok].max() <= 5e-4 * scene.near_far[1]
+    # training continues on the new grid: gradients have the new shapes
+    model.train()
+    out = model(rays.cuda(), is_train=True, n_coarse=128, n_fine=128, exp_sampling=True, resampling=True)
+    out[0].sum().backward()
+    assert model.density_plane_yin[0].grad.shape == model.density_plane_yin[0].shape == (1, 16, reso[1], reso[0])

@@ -148,3 +148,30 @@ def test_gradients(name):
     if em is not None:
         ref = g["grad:envmap.emission"]
         assert np.abs(em.grad.numpy() - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-6)
+
+
+def test_upsampled_factors_and_render_after_upsampling():
+    """the oracle's restatement of the coarse-to-fine step (train.py:371-377) reproduces the reference's
+    24 resampled factor tensors to 1 ulp and, with the r0 = 0.05 reset of set_resolution, its render on the new grid."""
+    import dataclasses
+    g = load_golden("upsample_tiny")
+    scene = scene_for(dict(n_voxels=int(g["n_voxels"]), seed=int(g["seed"])))
+    assert np.allclose(checksum(scene.state_dict), g["checksum"], rtol=1e-6)
+    assert list(g["grid_old"]) == scene.grid
+    reso = [int(v) for v in g["grid_new"]]
+    assert reso == O.yinyang_resolution(28 ** 3)
+    new = O.upsample_factors(scene.state_dict, reso, O.max_corner_radius(scene.aabb), scene.r0, scene.grid[0])
+    n = 0
+    for k in g.files:
+        if k.startswith("sd:"):
+            ref = g[k]
+            assert tuple(new[k[3:]].shape) == ref.shape
+            assert np.abs(new[k[3:]].numpy() - ref).max() <= 1e-6, k         # values up to ~3: <= 2 ulp
+            n += 1
+    assert n == 24
+    up_scene = dataclasses.replace(scene, grid=reso, r0=float(g["r0_after"]), state_dict=new)
+    assert up_scene.r0 == 0.05
+    with torch.no_grad():
+        out = O.render(new, oracle_cfg(up_scene), T(g["rays"]), False)
+    assert np.abs(out[0].numpy() - g["rgb"]).max() <= 1e-5
+    assert np.abs(out[1].numpy() - g["depth"]).max() <= 1e-4 * scene.near_far[1]
