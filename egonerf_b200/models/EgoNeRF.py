@@ -32,6 +32,27 @@ def _need_cuda(t, what):
         raise RuntimeError(f"egonerf_b200: {what} must be a CUDA tensor — there is no CPU fallback")
 
 
+class YinYangAlphaGridMask(torch.nn.Module):
+    """EgoNeRF.py:11-24: one binary occupancy volume per hemisphere, (1,1,N_phi',N_theta',N_r'), sampled trilinearly at
+    the active hemisphere's normalised coordinates.  Only `compute_alpha` reads it (the reference's `EgoNeRF.forward` never
+    does, SURVEY.md 8a "quirks"); a few torch ops, not on the path."""
+
+    def __init__(self, device, alpha_volume_yin, alpha_volume_yang):
+        super().__init__()
+        self.device = device
+        self.alpha_volume_yin = alpha_volume_yin.view(1, 1, *alpha_volume_yin.shape[-3:])
+        self.alpha_volume_yang = alpha_volume_yang.view(1, 1, *alpha_volume_yang.shape[-3:])
+
+    def sample_alpha(self, norm_samples):
+        alpha_vals = torch.empty_like(norm_samples[:, 0])
+        is_yin = norm_samples[:, -1] == 0
+        alpha_vals[is_yin] = F.grid_sample(self.alpha_volume_yin, norm_samples[is_yin][:, :3].view(1, -1, 1, 1, 3),
+                                           align_corners=True).view(-1)
+        alpha_vals[~is_yin] = F.grid_sample(self.alpha_volume_yang, norm_samples[~is_yin][:, 3:6].view(1, -1, 1, 1, 3),
+                                            align_corners=True).view(-1)
+        return alpha_vals
+
+
 class _VolumeRender(torch.autograd.Function):
     """EgoNeRF.forward (EgoNeRF.py:491-602) as one autograd node around egn_render_forward / egn_render_backward."""
 
@@ -246,12 +267,23 @@ class EgoNeRF(torch.nn.Module):
 
     def save(self, path, global_step):
         ckpt = {'kwargs': self.get_kwargs(), 'state_dict': self.state_dict(), 'global_step': global_step}
+        if self.alphaMask is not None:                                   # bit-packed, EgoNeRF.py:161-167
+            for h in ('yin', 'yang'):
+                vol = getattr(self.alphaMask, f'alpha_volume_{h}').bool().cpu().numpy()
+                ckpt.update({f'alphaMask_{h}.shape': vol.shape, f'alphaMask_{h}.mask': np.packbits(vol.reshape(-1))})
         if self.envmap is not None:
             ckpt.update({'envmap.emission': self.envmap.emission.detach().cpu().numpy(),
                          'envmap_res_H': self.envmap.emission.shape[2]})
         torch.save(ckpt, path)
 
     def load(self, ckpt):
+        if 'alphaMask_yin.shape' in ckpt.keys():                         # EgoNeRF.py:175-180
+            vols = []
+            for h in ('yin', 'yang'):
+                shape = ckpt[f'alphaMask_{h}.shape']
+                bits = np.unpackbits(ckpt[f'alphaMask_{h}.mask'])[:int(np.prod(shape))].reshape(shape)
+                vols.append(torch.from_numpy(bits).float().to(self.device))
+            self.alphaMask = YinYangAlphaGridMask(self.device, *vols)
         if self.envmap is not None:
             self.envmap = EnvironmentMap(h=ckpt['envmap_res_H'], init_strategy='zero', device=self.device)
             self.envmap.load_envmap(emission=ckpt['envmap.emission'], device=self.device)
@@ -499,10 +531,51 @@ class EgoNeRF(torch.nn.Module):
         self._bucket = None
         print(f'upsamping to {res_target}')
 
-    def updateAlphaMask(self, gridSize=None):
-        raise NotImplementedError("alpha-mask update is disabled in every shipped config (common.txt:13); SURVEY.md §8 f4")
+    def compute_alpha(self, norm_locs, length=1):
+        """TensorBase.compute_alpha (tensorBase.py:421-436): alpha of one step of `length` at normalised 7-coords; samples
+        the occupancy mask rejects get sigma = 0.  The density gather runs in libegn_b200 (`egn_density_feature`)."""
+        if self.alphaMask is not None:
+            alpha_mask = self.alphaMask.sample_alpha(norm_locs) > 0
+        else:
+            alpha_mask = torch.ones_like(norm_locs[:, 0], dtype=torch.bool)
+        sigma = torch.zeros(norm_locs.shape[:-1], device=norm_locs.device)
+        if alpha_mask.any():
+            sigma[alpha_mask] = self.feature2density(self.compute_densityfeature(norm_locs[alpha_mask]))
+        return 1 - torch.exp(-sigma * float(length)).view(norm_locs.shape[:-1])
 
-    # ---- measurement hooks (bench.py) ------------------------------------------------------------------
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize=None):
+        """EgoNeRF.getDenseAlpha (EgoNeRF.py:438-465): alpha of one march step on a regular lattice of normalised
+        coordinates, for each hemisphere; (g0, g1, g2) each.  Evaluated in slabs of <= 2^22 lattice points."""
+        gridSize = self.gridSize.tolist() if gridSize is None else [int(v) for v in gridSize]
+        dev = self.density_plane_yin[0].device
+        lin = [torch.linspace(0, 1, g, device=dev) * 2 - 1 for g in gridSize]
+        alpha = [torch.empty(gridSize, device=dev), torch.empty(gridSize, device=dev)]
+        slab = max(1, (1 << 22) // (gridSize[1] * gridSize[2]))
+        for i0 in range(0, gridSize[0], slab):
+            pts = torch.stack(torch.meshgrid(lin[0][i0:i0 + slab], lin[1], lin[2], indexing='ij'), -1).reshape(-1, 3)
+            for h in (0, 1):
+                c7 = torch.zeros(pts.shape[0], 7, device=dev)
+                c7[:, 3 * h:3 * h + 3] = pts
+                c7[:, 6] = h
+                alpha[h][i0:i0 + slab] = self.compute_alpha(c7, self.stepSize).view(-1, gridSize[1], gridSize[2])
+        return alpha[0], alpha[1]
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=None):
+        """EgoNeRF.updateAlphaMask (EgoNeRF.py:467-489): dense alpha -> 3x3x3 max-pool -> threshold at `alphaMask_thres` ->
+        YinYangAlphaGridMask.  Deprecated in the reference (and unreachable from train.py:359-362); kept for callers of
+        `compute_alpha`.  Returns None like the reference."""
+        gridSize = self.gridSize.tolist() if gridSize is None else [int(v) for v in gridSize]
+        vols = []
+        for a in self.getDenseAlpha(gridSize):
+            a = a.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+            a = F.max_pool3d(a, kernel_size=3, padding=1, stride=1).view(gridSize[::-1])
+            vols.append((a >= self.alphaMask_thres).float())
+        self.alphaMask = YinYangAlphaGridMask(self.device, vols[0], vols[1])
+        total = float(vols[0].sum() + vols[1].sum())
+        print("alpha rest %%%f" % (total / (2 * gridSize[0] * gridSize[1] * gridSize[2]) * 100))
+
     def launches_per_forward(self):
         """Kernels of libegn_b200 launched by one `forward` (sampler, gather, [MLP], composite)."""
         if not isinstance(self.renderModule, torch.nn.Module):

@@ -343,6 +343,55 @@ def feature_to_density(f, shift, act="softplus"):
     return torch.nn.functional.softplus(f + shift) if act == "softplus" else torch.relu(f)
 
 
+# --------------------------------------------------------------------------------------------------
+# f4: occupancy mask (deprecated in the reference; only compute_alpha reads it)
+# --------------------------------------------------------------------------------------------------
+def sample_alpha_mask(vol_yin, vol_yang, coords7):
+    """YinYangAlphaGridMask.sample_alpha (EgoNeRF.py:19-24): trilinear, zeros padding, align_corners, volumes (1,1,D,H,W)
+    with x = r -> W."""
+    out = torch.empty(coords7.shape[0])
+    yin = coords7[:, 6] == 0
+    gs = torch.nn.functional.grid_sample
+    out[yin] = gs(vol_yin, coords7[yin][:, :3].view(1, -1, 1, 1, 3), align_corners=True).view(-1)
+    out[~yin] = gs(vol_yang, coords7[~yin][:, 3:6].view(1, -1, 1, 1, 3), align_corners=True).view(-1)
+    return out
+
+
+def compute_alpha(sd, coords7, step, shift, mask=None, act="softplus"):
+    """TensorBase.compute_alpha (tensorBase.py:421-436) at normalised 7-coords; `mask` = (vol_yin, vol_yang) or None."""
+    keep = torch.ones(coords7.shape[0], dtype=torch.bool) if mask is None else sample_alpha_mask(mask[0], mask[1], coords7) > 0
+    sigma = torch.zeros(coords7.shape[0])
+    if keep.any():
+        c = coords7[keep]
+        is_yang = c[:, 6] != 0
+        c3 = torch.where(is_yang[:, None], c[:, 3:6], c[:, 0:3])
+        sigma[keep] = feature_to_density(density_feature(sd, c3, is_yang), shift, act)
+    return 1 - torch.exp(-sigma * step)
+
+
+def dense_alpha(sd, grid, step, shift):
+    """EgoNeRF.getDenseAlpha (EgoNeRF.py:438-465): (g0,g1,g2) alpha lattices of the Yin and the Yang hemisphere."""
+    lin = [torch.linspace(0, 1, g) * 2 - 1 for g in grid]
+    pts = torch.stack(torch.meshgrid(*lin, indexing="ij"), -1).reshape(-1, 3)
+    out = []
+    for h in (0, 1):
+        c7 = torch.zeros(pts.shape[0], 7)
+        c7[:, 3 * h:3 * h + 3] = pts
+        c7[:, 6] = h
+        out.append(compute_alpha(sd, c7, step, shift).view(*grid))
+    return out
+
+
+def alpha_mask_volumes(alpha_yin, alpha_yang, thres):
+    """EgoNeRF.updateAlphaMask (EgoNeRF.py:471-486): clamp, (r,theta,phi) -> (phi,theta,r), 3^3 max-pool, binarise."""
+    vols = []
+    for a in (alpha_yin, alpha_yang):
+        a = a.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        a = torch.nn.functional.max_pool3d(a, kernel_size=3, padding=1, stride=1)
+        vols.append((a >= thres).float())
+    return vols
+
+
 def alpha_composite_weights(sigma, dist):
     """raw2alpha (tensorBase.py:22-27)."""
     alpha = 1. - torch.exp(-sigma * dist)

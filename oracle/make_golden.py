@@ -201,6 +201,39 @@ def main():
     npz("upsample_tiny.npz", seed=3, n_voxels=20 ** 3, grid_old=np.array(up.grid), grid_new=np.array(reso), r0_after=co.r0,
         rays=r64, rgb=out[0], depth=out[1], alpha=out[4], checksum=sd_checksum(up.state_dict), **factors)
 
+    # ---- 5. occupancy mask (EgoNeRF.py:11-24,438-489, tensorBase.py:421-436; deprecated in the reference) -------
+    import warnings
+    warnings.simplefilter("ignore", DeprecationWarning)
+    co, model = build_reference(tiny)
+    gs = (8, 9, 20)
+    with torch.no_grad():
+        a_yin, a_yang = model.getDenseAlpha(gs)
+        dense = torch.cat([a_yin.reshape(-1), a_yang.reshape(-1)])
+        pooled = torch.cat([torch.nn.functional.max_pool3d(a.clamp(0, 1).transpose(0, 2).contiguous()[None, None], 3, 1, 1).reshape(-1)
+                            for a in (a_yin, a_yang)])
+        # a threshold that keeps about half of the lattice and that no pooled alpha sits within 1e-4 of
+        srt = torch.sort(pooled.unique())[0]
+        gaps = srt[1:] - srt[:-1]
+        k = int(torch.argmin((srt[:-1] - pooled.median()).abs() + (gaps < 1e-3) * 1e3))
+        thres = float((srt[k] + srt[k + 1]) / 2)
+        assert (pooled - thres).abs().min() > 1e-4
+        model.alphaMask_thres = thres
+        model.updateAlphaMask(gs)
+        g5 = torch.Generator().manual_seed(12)
+        M = 2000
+        c3 = torch.rand(M, 3, generator=g5) * 2.1 - 1.05
+        yang = torch.rand(M, generator=g5) < 0.5
+        c7 = torch.zeros(M, 7)
+        c7[~yang, 0:3] = c3[~yang]
+        c7[yang, 3:6] = c3[yang]
+        c7[:, 6] = yang.float()
+        masked_alpha = model.compute_alpha(c7, model.stepSize)
+    npz("alpha_mask_tiny.npz", grid=np.array(gs), thres=thres, step=model.stepSize, alpha_yin=a_yin, alpha_yang=a_yang,
+        mask_yin=model.alphaMask.alpha_volume_yin, mask_yang=model.alphaMask.alpha_volume_yang, coords7=c7,
+        masked_alpha=masked_alpha, checksum=sd_checksum(tiny.state_dict))
+    print("mask occupancy", float(model.alphaMask.alpha_volume_yin.mean()), float(model.alphaMask.alpha_volume_yang.mean()),
+          "rejected samples", float((masked_alpha == 0).float().mean()))
+
 
 if __name__ == "__main__":
     main()

@@ -330,3 +330,38 @@ def test_upsample_volume_grid_matches_reference_golden():
     out = model(rays.cuda(), is_train=True, n_coarse=128, n_fine=128, exp_sampling=True, resampling=True)
     out[0].sum().backward()
     assert model.density_plane_yin[0].grad.shape == model.density_plane_yin[0].shape == (1, 16, reso[1], reso[0])
+
+
+def test_occupancy_mask_family_matches_reference_golden(tmp_path):
+    """getDenseAlpha / updateAlphaMask / compute_alpha / the bit-packed mask of save+load against the reference
+    fixture (density gathers in libegn_b200; lattice alphas <= 1e-5, binary volumes and rejected samples identical)."""
+    from egonerf_b200.scene_io import model_from_scene
+    from tests.helpers import TINY
+    g = load_golden("alpha_mask_tiny")
+    scene = scene_for(TINY)
+    model = model_from_scene(scene)
+    grid = tuple(int(v) for v in g["grid"])
+    assert abs(float(model.stepSize) - float(g["step"])) < 1e-7
+    a_yin, a_yang = model.getDenseAlpha(grid)
+    assert np.abs(a_yin.cpu().numpy() - g["alpha_yin"]).max() <= 1e-5
+    assert np.abs(a_yang.cpu().numpy() - g["alpha_yang"]).max() <= 1e-5
+    model.alphaMask_thres = float(g["thres"])
+    assert model.updateAlphaMask(grid) is None
+    assert np.array_equal(model.alphaMask.alpha_volume_yin.cpu().numpy(), g["mask_yin"])
+    assert np.array_equal(model.alphaMask.alpha_volume_yang.cpu().numpy(), g["mask_yang"])
+    c7 = T(g["coords7"]).cuda()
+    ma = model.compute_alpha(c7, model.stepSize).cpu().numpy()
+    assert np.array_equal(ma == 0, g["masked_alpha"] == 0)
+    assert np.abs(ma - g["masked_alpha"]).max() <= 1e-5
+    # the mask travels through the checkpoint bit-packed like the reference's (EgoNeRF.py:161-167,175-180)
+    path = str(tmp_path / "masked.th")
+    model.save(path, global_step=3)
+    ckpt = torch.load(path, weights_only=False)
+    assert ckpt["alphaMask_yin.shape"] == (1, 1) + grid[::-1] and ckpt["alphaMask_yin.mask"].dtype == np.uint8
+    fresh = model_from_scene(scene)
+    assert fresh.alphaMask is None and fresh.load(ckpt) == 3
+    assert torch.equal(fresh.alphaMask.alpha_volume_yang, model.alphaMask.alpha_volume_yang)
+    assert np.array_equal(fresh.compute_alpha(c7, fresh.stepSize).cpu().numpy(), ma)
+    # the render path ignores the mask, as the reference's EgoNeRF.forward does
+    rays = T(load_golden("render_tiny_eval")["rays"])
+    assert torch.equal(_render(fresh, rays, False, None, None, {})[0], _render(model_from_scene(scene), rays, False, None, None, {})[0])

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import egn_oracle as O
-from tests.helpers import RENDER_CASES, T, checksum, load_golden, oracle_cfg, scene_for, stable_rays
+from tests.helpers import RENDER_CASES, TINY, T, checksum, load_golden, oracle_cfg, scene_for, stable_rays
 
 FAST = [n for n in RENDER_CASES if "tiny" in n]
 SLOW = [n for n in RENDER_CASES if "tiny" not in n]
@@ -175,3 +175,21 @@ def test_upsampled_factors_and_render_after_upsampling():
         out = O.render(new, oracle_cfg(up_scene), T(g["rays"]), False)
     assert np.abs(out[0].numpy() - g["rgb"]).max() <= 1e-5
     assert np.abs(out[1].numpy() - g["depth"]).max() <= 1e-4 * scene.near_far[1]
+
+
+def test_occupancy_mask_family():
+    """getDenseAlpha / updateAlphaMask / compute_alpha (EgoNeRF.py:438-489, tensorBase.py:421-436) restated
+    by the oracle reproduce the reference's lattice alphas, binary volumes and masked alphas."""
+    g = load_golden("alpha_mask_tiny")
+    scene = scene_for(TINY)
+    assert np.allclose(checksum(scene.state_dict), g["checksum"], rtol=1e-6)
+    grid = [int(v) for v in g["grid"]]
+    a_yin, a_yang = O.dense_alpha(scene.state_dict, grid, T(g["step"]), scene.density_shift)
+    assert np.abs(a_yin.numpy() - g["alpha_yin"]).max() <= 1e-6
+    assert np.abs(a_yang.numpy() - g["alpha_yang"]).max() <= 1e-6
+    vols = O.alpha_mask_volumes(a_yin, a_yang, float(g["thres"]))
+    assert np.array_equal(vols[0].numpy(), g["mask_yin"]) and np.array_equal(vols[1].numpy(), g["mask_yang"])
+    assert 0.3 < vols[0].mean() < 0.7                                   # a mask that actually rejects something
+    ma = O.compute_alpha(scene.state_dict, T(g["coords7"]), T(g["step"]), scene.density_shift, mask=vols)
+    assert np.array_equal(ma.numpy() == 0, g["masked_alpha"] == 0)
+    assert np.abs(ma.numpy() - g["masked_alpha"]).max() <= 1e-6
