@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegn_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -25,7 +25,8 @@ class EgnConfig(C.Structure):
         ("center", C.c_float * 3), ("near_plane", C.c_float), ("density_shift", C.c_float),
         ("distance_scale", C.c_float), ("ang_near", C.c_float * 2), ("ang_inv", C.c_float * 2),
         ("exp_sampling", C.c_int32), ("far_plane", C.c_float), ("step_size", C.c_float), ("aabb", C.c_float * 6), ("bwd_tc", C.c_int32),
-        ("r_knots", C.c_void_p), ("z_coarse", C.c_void_p), ("tables_bf16", C.c_void_p),
+        ("plain_ladders", C.c_int32), ("jitter_ratio", C.c_float), ("jitter_r0", C.c_float),
+        ("r_knots", C.c_void_p), ("r_knots_coarse", C.c_void_p), ("z_coarse", C.c_void_p), ("tables_bf16", C.c_void_p),
     ]
 
 
@@ -90,6 +91,8 @@ PROTOTYPES = {
                                         C.c_int32, C.c_void_p, C.c_void_p]),
     "egn_host_sample_schedule": (C.c_int32, [C.c_float, C.c_float, C.c_float, C.c_int32, c_float_p]),
     "egn_host_r_knots": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p]),
+    "egn_host_plain_sample_schedule": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p, c_float_p, c_float_p]),
+    "egn_host_plain_r_knots": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p]),
 }
 
 _lib = None

@@ -32,7 +32,7 @@ static int validate(const EgnConfig* c, bool need_schedule) {
         return fail("this build supports n_lamb_sigma=[%d]*3, n_lamb_sh=[%d]*3 (got %d, %d)", EGN_CS, EGN_CA, c->c_sigma, c->c_app);
     for (int a = 0; a < 3; ++a)
         if (c->grid[a] < 4) return fail("grid[%d]=%d too small", a, c->grid[a]);
-    if (c->grid[0] > EGN_MAX_KNOTS) return fail("N_r=%d exceeds %d", c->grid[0], EGN_MAX_KNOTS);
+    if (c->grid[0] + 2 > EGN_MAX_KNOTS) return fail("N_r=%d exceeds %d", c->grid[0], EGN_MAX_KNOTS - 2);
     if (c->app_dim < 1 || c->app_dim > 27) return fail("app_dim=%d unsupported (1..27)", c->app_dim);
     if (c->shading < 0 || c->shading > 3) return fail("unknown shading %d", c->shading);
     if (c->shading == EGN_SHADE_SH && c->app_dim != 27) return fail("SH shading needs app_dim 27");
@@ -50,16 +50,31 @@ static int validate(const EgnConfig* c, bool need_schedule) {
         if (c->resampling && (c->n_fine < 32 || c->n_fine > 256 || c->n_fine % 32)) return fail("n_fine=%d must be a multiple of 32 in [32,256]", c->n_fine);
         if (!c->r_knots || (c->exp_sampling && !c->z_coarse)) return fail("r_knots / z_coarse tables missing");
         if (!c->exp_sampling && !(c->step_size > 0.f)) return fail("uniform march needs step_size > 0");
+        if (c->plain_ladders && !c->r_knots_coarse) return fail("plain_ladders needs r_knots_coarse (N_r/2 + 3 knots)");
+        if (c->plain_ladders && c->exp_sampling && !(c->jitter_ratio > 1.f && c->jitter_r0 > 0.f))
+            return fail("plain_ladders needs jitter_ratio > 1 and jitter_r0 > 0");
     }
     return 0;
 }
 
-static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables) {
+static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables, bool render = false) {
     EgnKernelCfg k;
     memset(&k, 0, sizeof(k));
     k.lay = egn_make_layout(c->grid);
     k.tables = tables;
     k.r_knots = c->r_knots;
+    k.plain_ladders = c->plain_ladders ? 1 : 0;
+    k.knots_last = c->grid[0] + (k.plain_ladders ? 2 : 0);
+    k.r_knots_c = k.plain_ladders ? c->r_knots_coarse : c->r_knots;
+    k.r_div_c = k.plain_ladders ? c->grid[0] / 2 : c->grid[0];
+    k.knots_last_c = k.r_div_c + (k.plain_ladders ? 2 : 0);
+    k.r_div = c->grid[0];
+    if (render && k.plain_ladders && !c->resampling) {
+        // reference quirk (EgoNeRF.py:523,565-572): without resampling the fine grid is read at the coordinates the coarse pass
+        // normalised with downsample=2 -- with the plain ladders that is the N_r/2 ladder
+        k.r_knots = k.r_knots_c; k.knots_last = k.knots_last_c; k.r_div = k.r_div_c;
+    }
+    k.jitter_ratio = c->jitter_ratio; k.jitter_r0 = c->jitter_r0;
     k.z_coarse = c->z_coarse;
     for (int a = 0; a < 3; ++a) k.center[a] = c->center[a];
     for (int a = 0; a < 2; ++a) { k.ang_near[a] = c->ang_near[a]; k.ang_inv[a] = c->ang_inv[a]; }
@@ -185,7 +200,7 @@ extern "C" int32_t egn_sample_rays(const EgnConfig* c, const float* tables, cons
     if (validate(c, true)) return 1;
     if (n <= 0) return 0;
     if (!tables || !rays || !z_out) return fail("null argument");
-    EgnKernelCfg k = make_kcfg(c, tables);
+    EgnKernelCfg k = make_kcfg(c, tables, true);
     int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z_out, (cudaStream_t)stream);
     return e ? cuda_fail("egn_sample_rays", e) : 0;
 }
@@ -197,7 +212,7 @@ static inline void mark(StageEvents* se, int i, cudaStream_t st) { if (se && se-
 static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays, int64_t n,
                                const float* z_vals, const EgnOutputs* out, void* workspace, cudaStream_t st,
                                StageEvents* se, bool save_feat) {
-    EgnKernelCfg k = make_kcfg(c, tables);
+    EgnKernelCfg k = make_kcfg(c, tables, true);
     WsPlan w = plan_ws(c, n);
     char* base = (char*)workspace;
     float* z = (float*)(base + w.z);
@@ -244,7 +259,7 @@ static int render_forward_impl(const EgnConfig* c, const EgnParams* p, const flo
                                int64_t n, int32_t is_train, const float* u_c, const float* u_f, uint64_t seed,
                                int64_t ray0, const EgnOutputs* out, void* workspace, bool keep, cudaStream_t st, StageEvents* se) {
     float* z = (float*)((char*)workspace + plan_ws(c, n).z);
-    EgnKernelCfg k = make_kcfg(c, tables);
+    EgnKernelCfg k = make_kcfg(c, tables, true);
     mark(se, 0, st);
     int e = egn_launch_coarse(k, rays, n, is_train, u_c, u_f, seed, ray0, c->near_plane, z, st);
     if (e) return cuda_fail("egn_sample_rays", e);
@@ -298,7 +313,7 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
     if (c->env_h > 0 && (!p->emission || !g->emission)) return fail("envmap configured but emission / its gradient missing");
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    EgnKernelCfg k = make_kcfg(c, tables);
+    EgnKernelCfg k = make_kcfg(c, tables, true);
     WsPlan w = plan_ws(c, n);
     char* base = (char*)workspace;
     const float* z = (const float*)(base + w.z);
@@ -430,5 +445,29 @@ extern "C" int32_t egn_host_r_knots(float far_r, float r0, int32_t n_r, float* k
     knots[0] = 0.f;
     for (int i = 1; i <= n_r; ++i) knots[i] = r0 * powf(ratio, (float)(i - 1));
     force_linear_prefix(knots, n_r + 1, r0);
+    return 0;
+}
+
+// ---- the same two ladders for a run without --interval_th (opt.py:190) ---------------------------------
+extern "C" int32_t egn_host_plain_sample_schedule(float near_plane, float far_plane, int32_t n, float* z_out, float* ratio_out,
+                                                  float* r0_out) {
+    if (n < 2 || !z_out) return fail("bad arguments");
+    const double ratio = 1.0 + (M_PI / 2.0) / (double)n;                                 // EgoNeRF.py:60
+    const double r0 = ((double)far_plane - (double)near_plane) * (ratio - 1.0) / (pow(ratio, (double)n) - 1.0);
+    float run = 0.f;
+    for (int j = 0; j < n; ++j) {                                                        // exclusive running sum of ratio^i
+        z_out[j] = run * (float)r0;
+        run += powf((float)ratio, (float)j);
+    }
+    if (ratio_out) *ratio_out = (float)ratio;
+    if (r0_out) *r0_out = (float)r0;
+    return 0;
+}
+
+extern "C" int32_t egn_host_plain_r_knots(float far_r, float r0, int32_t n_r, float* knots) {
+    if (n_r < 2 || !knots) return fail("bad arguments");
+    const float ratio = powf(far_r / r0, 1.f / (float)(n_r - 1));                        // coordinates.py:139,215
+    knots[0] = 0.f;
+    for (int i = 1; i <= n_r + 2; ++i) knots[i] = r0 * powf(ratio, (float)(i - 1));
     return 0;
 }

@@ -194,7 +194,7 @@ egn_gather_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
         const float* B = h ? basis1 : basis0;
         sm.Bo[h][o][kk] = (o < k.app_dim) ? B[o * GB_K + kk] : 0.f;
     }
-    for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) sm.knots[i] = k.r_knots[i];
+    for (int i = threadIdx.x; i <= k.knots_last; i += blockDim.x) sm.knots[i] = k.r_knots[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane & 15;

@@ -52,7 +52,12 @@ static inline EgnLayout egn_make_layout(const int32_t grid[3]) {
 struct EgnKernelCfg {
     EgnLayout lay;
     const float* tables;
-    const float* r_knots;     // N_r + 1
+    const float* r_knots;     // knots_last + 1 entries (fine pass)
+    const float* r_knots_c;   // knots_last_c + 1 entries (coarse pass; the same ladder unless plain_ladders)
+    int knots_last, knots_last_c;   // last knot index = upper clamp of the search
+    int r_div, r_div_c;       // cells of the fine / coarse-pass ladder (N_r; coarse: N_r/2 with plain ladders)
+    int plain_ladders;
+    float jitter_ratio, jitter_r0;
     const float* z_coarse;    // n_coarse
     float center[3];
     float ang_near[2], ang_inv[2];
@@ -81,7 +86,7 @@ struct YYCoord {       // index-space coordinate of one sample in its active hem
 // GenericSphericalCoords.normalize_r, interval_th branch (:112-131,156).  IEEE sqrtf/acosf/atan2f, no FMA
 // contraction (the library is compiled with -fmad=false): a 1-ulp change flips the hemisphere of a sample.
 __device__ __forceinline__ YYCoord egn_cart_to_yinyang(float px, float py, float pz, const EgnKernelCfg& k,
-                                                       const float* __restrict__ knots /*smem or global*/) {
+                                                       const float* __restrict__ knots /*smem or global*/, int last, int n_r) {
     float qx = px - k.center[0], qy = py - k.center[1], qz = pz - k.center[2];
     float r = sqrtf(qx * qx + qy * qy + qz * qz);
     float th = acosf(qz / r);
@@ -97,19 +102,24 @@ __device__ __forceinline__ YYCoord egn_cart_to_yinyang(float px, float py, float
     o.yang = yin ? 0 : 1;
     o.c[1] = (th - k.ang_near[0]) * k.ang_inv[0] * 2.f - 1.f;
     o.c[2] = (ph - k.ang_near[1]) * k.ang_inv[1] * 2.f - 1.f;
-    // searchsorted(knots, r, right=True) clamped to [1, N_r]
-    const int n_r = k.lay.G[0];
-    int lo = 0, hi = n_r + 1;                      // first index with knots[idx] > r
+    // searchsorted(knots, r, right=True) clamped to [1, last]; with the plain ladders in + frac == 1 + k + lin of
+    // coordinates.py:141-155 (knots[i] = r0 * ratio^(i-1)), r < r0 falls in cell 0: frac = r / r0
+    int lo = 0, hi = last + 1;                     // first index with knots[idx] > r
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (knots[mid] > r) hi = mid; else lo = mid + 1;
     }
-    int out = min(max(lo, 1), n_r);
+    int out = min(max(lo, 1), last);
     int in = out - 1;
     float g0 = knots[in], g1 = knots[out];
     float frac = (r - g0) / (g1 - g0);
     o.c[0] = ((float)in + frac) / (float)n_r * 2.f - 1.f;
     return o;
+}
+
+__device__ __forceinline__ YYCoord egn_cart_to_yinyang(float px, float py, float pz, const EgnKernelCfg& k,
+                                                       const float* __restrict__ knots) {       // fine pass
+    return egn_cart_to_yinyang(px, py, pz, k, knots, k.knots_last, k.r_div);
 }
 
 // F.grid_sample(align_corners=True) un-normalisation: ((x+1)/2)*(size-1)

@@ -125,7 +125,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     __shared__ float s_w[K1_WARPS][K1_MAXC];
     __shared__ float s_zn[K1_WARPS][K1_MAXC];
     const int nc = k.n_coarse, nf = k.n_fine;
-    for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) s_knots[i] = k.r_knots[i];
+    for (int i = threadIdx.x; i <= k.knots_last_c; i += blockDim.x) s_knots[i] = k.r_knots_c[i];
     if (!k.march) for (int i = threadIdx.x; i < nc; i += blockDim.x) s_r[i] = k.z_coarse[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +138,29 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         const float ox = rays[ray * 6 + 0], oy = rays[ray * 6 + 1], oz = rays[ray * 6 + 2];
         const float dx = rays[ray * 6 + 3], dy = rays[ray * 6 + 4], dz = rays[ray * 6 + 5];
         // ---- 1. coarse depths ----
-        if (!k.march) {
+        if (!k.march && k.plain_ladders && is_train) {
+            // without interval_th the jitter sits in the exponent and accumulates (EgoNeRF.py:59-67):
+            // z_j = near + r0 * sum_{i<j} ratio^(i + u_i).  Each lane sums its cnt consecutive terms, a warp scan adds
+            // the totals of the lanes before it.
+            for (int j = lane; j < nc; j += 32) {
+                const float u = u_c ? u_c[ray * nc + j] : egn_u01(egn_philox(seed, (unsigned long long)(ray0 + ray), (unsigned)j).x);
+                zn[j] = powf(k.jitter_ratio, (float)j + u);
+            }
+            __syncwarp();
+            float run = 0.f;
+            for (int t = 0; t < cnt; ++t) run += zn[lane * cnt + t];
+            float before = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_up_sync(FULL, before, o);
+                if (lane >= o) before += v;
+            }
+            before -= run;                                   // exclusive: terms of the lanes before this one
+            for (int t = 0; t < cnt; ++t) {
+                zc[lane * cnt + t] = near_plane + before * k.jitter_r0;
+                before += zn[lane * cnt + t];
+            }
+        } else if (!k.march) {
             // near + r, jittered by interval*U in train mode (EgoNeRF.py:69-82)
             for (int j = lane; j < nc; j += 32) {
                 float r = s_r[j];
@@ -174,7 +196,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         for (int t = 0; t < cnt; ++t) {
             const int j = t * 32 + lane;
             const float z = (k.march && !is_train) ? zn[j] : zc[j];
-            YYCoord cc = egn_cart_to_yinyang(ox + dx * z, oy + dy * z, oz + dz * z, k, s_knots);
+            YYCoord cc = egn_cart_to_yinyang(ox + dx * z, oy + dy * z, oz + dz * z, k, s_knots, k.knots_last_c, k.r_div_c);
             float myf = 0.f;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {         // 8 samples per pass, 4 lanes (one float4 each) per sample
@@ -410,7 +432,7 @@ egn_gather_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         sm.Blo[h][o][pr] = egn_pack_bf16x2(w0 - __uint_as_float(hi << 16), w1 - __uint_as_float(hi & 0xffff0000u));
     }
     if (!FROM_COORDS)
-        for (int i = threadIdx.x; i <= k.lay.G[0]; i += blockDim.x) sm.knots[i] = k.r_knots[i];
+        for (int i = threadIdx.x; i <= k.knots_last; i += blockDim.x) sm.knots[i] = k.r_knots[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float(*vt)[K2_VT] = sm.vt[warp];

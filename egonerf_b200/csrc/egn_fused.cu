@@ -217,7 +217,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
         const float* B = (n >> 5) ? basis1 : basis0;
         store_elem(bbs, nullptr, false, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
     }
-    for (int i = tid; i <= k.lay.G[0]; i += FU_THREADS) s_knots[i] = k.r_knots[i];
+    for (int i = tid; i <= k.knots_last; i += FU_THREADS) s_knots[i] = k.r_knots[i];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();

@@ -115,7 +115,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         store_elem(bbs, nullptr, false, n, kk, o < AD ? B[o * GT_VK + kk] : 0.f, GT_BB_CHUNK);
     }
     for (int i = tid; i < 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i <= k.lay.G[0]; i += GT_THREADS) s_knots[i] = k.r_knots[i];
+    for (int i = tid; i <= k.knots_last; i += GT_THREADS) s_knots[i] = k.r_knots[i];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();

@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib
-from .coordinates import YinYangSphericalCoords, sample_schedule
+from .coordinates import YinYangSphericalCoords, sample_schedule, plain_sample_schedule
 from .envmap import EnvironmentMap
 from .decoders import MLPRender_Fea, MLPRender, SHRender, RGBRender
 
@@ -413,15 +413,27 @@ class EgoNeRF(torch.nn.Module):
         dev = self.density_plane_yin[0].device
         if 'knots' not in self._sched:
             self._sched['knots'] = co.r_knots().to(dev).contiguous()
+            if not co.interval_th:                                # coarse pass: normalize_coord(downsample=2), EgoNeRF.py:523
+                self._sched['knots_coarse'] = co.r_knots(downsample=2).to(dev).contiguous()
         cfg.r_knots = self._sched['knots'].data_ptr()
+        cfg.plain_ladders = int(not co.interval_th)
+        if not co.interval_th:
+            cfg.r_knots_coarse = self._sched['knots_coarse'].data_ptr()
         if opts is not None:
             nc = int(opts["n_coarse"])
             cfg.n_coarse, cfg.n_fine = nc, int(opts["n_fine"])
             cfg.use_coarse_sample, cfg.resampling = int(opts["use_coarse_sample"]), int(opts["resampling"])
             cfg.exp_sampling = int(opts.get("exp_sampling", True))
             if ('z', nc) not in self._sched:
-                self._sched[('z', nc)] = sample_schedule(self.near_far[0], self.near_far[1], co.r0, nc).to(dev).contiguous()
+                if co.interval_th:
+                    self._sched[('z', nc)] = sample_schedule(self.near_far[0], self.near_far[1], co.r0, nc).to(dev).contiguous()
+                else:
+                    r, ratio, r0p = plain_sample_schedule(self.near_far[0], self.near_far[1], nc)
+                    self._sched[('z', nc)] = r.to(dev).contiguous()
+                    self._sched[('jitter', nc)] = (ratio, r0p)
             cfg.z_coarse = self._sched[('z', nc)].data_ptr()
+            if not co.interval_th:
+                cfg.jitter_ratio, cfg.jitter_r0 = self._sched[('jitter', nc)]
         return cfg
 
     # ---- stand-alone operators ------------------------------------------------------------------------

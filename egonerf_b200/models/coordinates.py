@@ -2,9 +2,9 @@
 GenericSphericalCoords :73-266).  It holds the scalars and the two exponential ladders the kernels need; the
 per-sample arithmetic (from_cartesian / normalize_coord) runs in libegn_b200 (`egn_yinyang_coords`).
 
-Only what the EgoNeRF path uses is mirrored: `exp_r=True` with `interval_th=True`, which is what every shipped
-config selects (configs/EgoNeRF/common.txt:2-3,14).  The other eight coordinate systems of the reference are
-out of scope.
+Only what the EgoNeRF path uses is mirrored: `exp_r=True`, with `interval_th=True` (what every shipped config selects,
+configs/EgoNeRF/common.txt:2-3,14) or without it (the CLI default, opt.py:190).  The other eight coordinate systems of
+the reference are out of scope.
 """
 from __future__ import annotations
 
@@ -41,13 +41,24 @@ def sample_schedule(near: float, far: float, r0: float, n: int) -> torch.Tensor:
     return clamp_short_intervals(exp_ladder(r0, ratio, torch.arange(n).float()), r0)
 
 
+def plain_sample_schedule(near: float, far: float, n: int):
+    """Without interval_th (EgoNeRF.py:59-66): r_j = r0' * sum_{i<j} ratio^i with ratio = 1 + (pi/2)/n and r0' chosen so that
+    the n intervals span far - near.  Returns (radii (n,), ratio, r0'); the reference sums with a (1,n) x (n,n) product
+    against a strictly-upper-triangular ones matrix, kept here so that the eval depths are the reference's bit for bit."""
+    ratio = 1 + (pi / 2.) / n
+    r0 = (far - near) * (ratio - 1) / (pow(ratio, n) - 1)
+    terms = torch.pow(ratio, torch.arange(n)[None].float())
+    before = torch.tril(torch.ones(n, n), diagonal=-1).T            # [i, j] = 1 for i < j (same operand layout as the reference)
+    return (terms @ before * r0)[0], ratio, r0
+
+
 class YinYangSphericalCoords:
     """[r_n, theta_n, phi_n, r_e, theta_e, phi_e, Y]: Y = 0 Yin grid, 1 Yang grid."""
 
     def __init__(self, device, aabb, exp_r=True, N_voxel=None, r0=None, interval_th=False):
-        if not exp_r or not interval_th:
-            raise NotImplementedError("egonerf_b200 implements the exp_r + interval_th Yin-Yang grid only "
-                                      "(the configuration of every shipped EgoNeRF config)")
+        if not exp_r:
+            raise NotImplementedError("egonerf_b200 implements the exponential-r Yin-Yang grid only "
+                                      "(exp_sampling is set by every shipped EgoNeRF config)")
         self.device = device
         self.aabb = aabb.to(device)
         self.center = self.aabb.sum(0).div(2)
@@ -83,17 +94,25 @@ class YinYangSphericalCoords:
         self._knots = None
 
     # ---- ladders ------------------------------------------------------------------------------------
-    def r_knots(self) -> torch.Tensor:
-        """The N_r + 1 knot radii normalize_r rebuilds on every call (coordinates.py:118-124), fp32, CPU."""
-        if self._knots is None:
-            ratio = pow(self.far[0].cpu() / self.r0, 1 / (self.N_r - 1))
-            self._knots = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(self.N_r + 1)), self.r0)
-        return self._knots
+    def r_knots(self, downsample=None) -> torch.Tensor:
+        """interval_th: the N_r + 1 knot radii normalize_r rebuilds on every call (coordinates.py:118-124; `downsample` is
+        ignored, :112-117).  Otherwise: the knots r0 * ratio^k behind the closed form of :132-155, [0, r0, r0*ratio, ...],
+        for N_r // downsample cells with the ratio recomputed (:137-139), two knots past the grid.  fp32, CPU."""
+        if self.interval_th:
+            if self._knots is None:
+                ratio = pow(self.far[0].cpu() / self.r0, 1 / (self.N_r - 1))
+                self._knots = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(self.N_r + 1)), self.r0)
+            return self._knots
+        n_r = self.N_r if downsample is None else self.N_r // downsample
+        ratio = self.ratio if downsample is None else pow(self.far[0].cpu() / self.r0, 1 / (n_r - 1))
+        knots = torch.zeros(n_r + 3)
+        knots[1:] = self.r0 * torch.pow(ratio, torch.arange(n_r + 2, dtype=torch.int32))
+        return knots
 
     def normalize_r(self, r: torch.Tensor) -> torch.Tensor:
         """Host restatement of GenericSphericalCoords.normalize_r, interval_th branch (coordinates.py:112-131,156) for
         the short ladders of `up_sampling_positions` (a few hundred radii): knot index + linear fraction, /N_r."""
-        g = self.r_knots()
+        g = self.r_knots()                  # plain ladders: in + frac == 1 + k + lin of coordinates.py:141-155
         hi = torch.clamp(torch.searchsorted(g, r.contiguous(), side='right'), 1, g.shape[0] - 1)
         lo = hi - 1
         return (lo + (r - g[lo]) / (g[hi] - g[lo])) / self.N_r
@@ -108,7 +127,11 @@ class YinYangSphericalCoords:
         (coordinates.py:250-264); the two differ by rounding only."""
         if axis == 0:
             ratio = pow(self.far[0].cpu() / self.r0, 1 / (n_out - 1))
-            target = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(n_out)), self.r0)
+            if self.interval_th:
+                target = clamp_short_intervals(exp_ladder(self.r0, ratio, torch.arange(n_out)), self.r0)
+            else:                                                    # coordinates.py:247-250
+                target = torch.zeros(n_out)
+                target[1:] = self.r0 * torch.pow(ratio, torch.arange(n_out - 1))
             r_samples = self.normalize_r(target) * 2 - 1
             return ((r_samples + 1) / 2) * (n_in - 1)
         if beside_r:
@@ -153,6 +176,7 @@ class YinYangSphericalCoords:
         cfg.ang_inv[:] = [float(inv[1]), float(inv[2])]
         self._knots_dev = self.r_knots().to(self.device).contiguous()
         cfg.r_knots = self._knots_dev.data_ptr()
+        cfg.plain_ladders = int(not self.interval_th)
         return cfg
 
     def cart_to_normalized(self, xyz: torch.Tensor) -> torch.Tensor:

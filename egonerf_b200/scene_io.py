@@ -5,10 +5,10 @@ from .models.coordinates import YinYangSphericalCoords
 from .models.EgoNeRF import EgoNeRF
 
 
-def model_from_scene(scene, device="cuda"):
+def model_from_scene(scene, device="cuda", interval_th=True):
     """Builds the drop-in EgoNeRF exactly as train.py:118-171 does and loads the scene's parameters."""
     aabb = scene.aabb.to(device)
-    co = YinYangSphericalCoords(device, aabb, exp_r=True, N_voxel=scene.n_voxels, r0=scene.r0, interval_th=True)
+    co = YinYangSphericalCoords(device, aabb, exp_r=True, N_voxel=scene.n_voxels, r0=scene.r0, interval_th=interval_th)
     reso = co.N_to_reso(scene.n_voxels, aabb)
     assert reso == scene.grid, (reso, scene.grid)
     model = EgoNeRF(aabb, reso, device, co, **scene.model_kwargs())

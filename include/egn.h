@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 5
+#define EGN_ABI_VERSION 6
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -66,7 +66,18 @@ typedef struct EgnConfig {
     float   aabb[6];          /* [min xyz, max xyz] (uniform march only) */
     int32_t bwd_tc;           /* 1: egn_render_backward uses the tcgen05 backward kernels (bf16 operands, fp32 accumulate) even
                                  when the forward ran in EGN_MLP_FP32 / EGN_MLP_TC_SPLIT; always on for EGN_MLP_TC_BF16 */
-    const float* r_knots;     /* device, N_r+1 : reference r ladder of normalize_r (coordinates.py:118-124) */
+    int32_t plain_ladders;    /* 0: `interval_th` ladders (intervals shorter than r0 forced to r0; coordinates.py:112-131,
+                                 EgoNeRF.py:68-82) -- every shipped config.  1: the plain exponential ladders of a run
+                                 WITHOUT --interval_th (opt.py:190): normalize_r = 1 + k + lin on r0*ratio^k
+                                 (coordinates.py:132-156), the coarse pass on the N_r/2 ladder (`downsample=2`, :137-139),
+                                 train jitter in the exponent (EgoNeRF.py:59-67) */
+    float   jitter_ratio;     /* plain_ladders, train: z_j = near + jitter_r0 * sum_{i<j} jitter_ratio^(i + u_i);  */
+    float   jitter_r0;        /*   ratio = 1 + (pi/2)/n_coarse, r0 = (far-near)(ratio-1)/(ratio^n_coarse - 1)     */
+    const float* r_knots;     /* device: reference r ladder of normalize_r.  interval_th: N_r+1 knots (coordinates.py:118-124).
+                                 plain_ladders: N_r+3 knots [0, r0, r0*ratio, ..., r0*ratio^(N_r+1)] (two past the grid: the
+                                 closed form of :141-155 extrapolates exponentially, the search here clamps to the last knot) */
+    const float* r_knots_coarse; /* device, plain_ladders only: the same ladder for N_r/2 cells, N_r/2+3 knots (ratio recomputed,
+                                 coordinates.py:137-139); ignored (may be NULL) otherwise: interval_th ignores `downsample` */
     const float* z_coarse;    /* device, n_coarse : r schedule of sample_ray_exp WITHOUT near (EgoNeRF.py:69-76);
                                  the kernels add near_plane and, in train mode, the interval jitter (:78-82) */
     const void*  tables_bf16; /* device, optional: bf16 copy of the fine render tables (egn_pack_tables_bf16), read by the
@@ -226,6 +237,12 @@ int32_t egn_resample_factor(const float* src /*device*/, int32_t channels, int32
 /* ---- host helpers (no GPU): the two ladders, for callers that do not build them with torch ------ */
 int32_t egn_host_sample_schedule(float near_plane, float far_plane, float r0, int32_t n, float* z_out);   /* EgoNeRF.py:69-76 */
 int32_t egn_host_r_knots(float far_r, float r0, int32_t n_r, float* knots_out /*n_r+1*/);                  /* coordinates.py:118-124 */
+/* ... and for EgnConfig.plain_ladders (a run without --interval_th): schedule of EgoNeRF.py:59-66 (eval; also returns the
+ * ratio / r0 of the train jitter) and the N_r+3 knots r0*ratio^(i-1) behind coordinates.py:132-155 (call it with n_r = N_r/2
+ * for r_knots_coarse). */
+int32_t egn_host_plain_sample_schedule(float near_plane, float far_plane, int32_t n, float* z_out, float* ratio_out /*nullable*/,
+                                       float* r0_out /*nullable*/);
+int32_t egn_host_plain_r_knots(float far_r, float r0, int32_t n_r, float* knots_out /*n_r+3*/);
 
 #ifdef __cplusplus
 }

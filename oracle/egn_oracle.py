@@ -47,6 +47,7 @@ class OracleCfg:
     fea_pe: int = 2
     app_dim: int = 27
     exp_sampling: bool = True               # False: uniform march of TensorBase.sample_ray (tensorBase.py:308-327)
+    interval_th: bool = True                # False: the plain exponential ladders of a run without --interval_th (opt.py:190)
     step_ratio: float = 0.5
     extras: dict = field(default_factory=dict)
 
@@ -129,6 +130,18 @@ def uniform_march(o, d, aabb, near, far, step, n, u=None):
     return t_min[..., None] + step * rng
 
 
+def plain_sample_schedule(near: float, far: float, n: int, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EgoNeRF.sample_ray_exp without interval_th (EgoNeRF.py:59-66): radii (1|N, n) WITHOUT near.  ratio = 1 + (pi/2)/n,
+    r0' = (far-near)(ratio-1)/(ratio^n - 1); r_j = r0' * sum_{i<j} ratio^(i [+ u_i]) -- the jitter sits in the exponent.
+    The reference forms the exclusive sums as a product with a strictly-lower-triangular ones matrix, transposed."""
+    ratio = 1 + (PI / 2.) / n
+    r0 = (far - near) * (ratio - 1) / (pow(ratio, n) - 1)
+    e = torch.arange(n)[None].float()
+    if u is not None:
+        e = e.repeat(u.shape[0], 1) + u
+    return torch.pow(ratio, e) @ torch.tril(torch.ones(n, n), diagonal=-1).T * r0
+
+
 def jitter_schedule(r: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     """EgoNeRF.py:77-81 (train): r + interval * U, last interval repeated.  r (n,), u (N,n)."""
     r = r.repeat(u.shape[0], 1)
@@ -170,6 +183,22 @@ def normalize_radius(r: torch.Tensor, knots: torch.Tensor) -> torch.Tensor:
     lo = hi - 1
     frac = (r - knots[lo]) / (knots[hi] - knots[lo])
     return (lo + frac) / n_r * 2 - 1
+
+
+def normalize_radius_plain(r: torch.Tensor, far_r: torch.Tensor, r0: float, n_r: int, downsample=None) -> torch.Tensor:
+    """GenericSphericalCoords.normalize_r without interval_th (coordinates.py:132-156) + the *2-1 of normalize_coord:
+    k = trunc(log(r/r0)/log(ratio)); r < r0 -> r/r0, else 1 + k + (r - r0 ratio^k)/(r0 ratio^(k+1) - r0 ratio^k); / N_r.
+    `downsample` halves N_r and recomputes the ratio (the coarse pass, EgoNeRF.py:523)."""
+    if downsample is not None:
+        n_r = n_r // downsample
+    ratio = pow(far_r / r0, 1 / (n_r - 1))                  # fp32 0-dim tensor (coordinates.py:139,215)
+    k = (torch.log(r / r0) / math.log(ratio)).to(torch.int32)
+    below = r < r0
+    lo = r0 * torch.pow(ratio, k)
+    hi = r0 * torch.pow(ratio, k + 1)
+    lo[below], hi[below] = 0, r0
+    idx = torch.where(below, r / r0, 1 + k + (r - lo) / (hi - lo))
+    return idx / n_r * 2 - 1
 
 
 # --------------------------------------------------------------------------------------------------
@@ -469,9 +498,10 @@ def envmap_radiance(emission, dirs):
 # the whole path
 # --------------------------------------------------------------------------------------------------
 def _coords(p, center, knots):
+    """`knots`: the interval_th ladder, or a callable r -> normalised r (plain ladders)."""
     r, a, b, is_yang, (th_n, ph_n) = cart_to_yinyang(p, center)
     an, bn = normalize_angles(a, b)
-    rn = normalize_radius(r, knots)
+    rn = knots(r) if callable(knots) else normalize_radius(r, knots)
     margin = torch.stack([(th_n - PI / 4).abs(), (th_n - 3 * PI / 4).abs(),
                           (ph_n + 3 * PI / 4).abs(), (ph_n - 3 * PI / 4).abs()], -1).amin(-1)
     return torch.stack([rn, an, bn], -1), is_yang, margin
@@ -486,10 +516,22 @@ def render(sd: Dict[str, torch.Tensor], cfg: OracleCfg, rays: torch.Tensor, is_t
     N = rays.shape[0]
     o, d = rays[:, :3], rays[:, 3:6]
     center = scene_center(cfg.aabb)
-    knots = r_reference_grid(max_corner_radius(cfg.aabb), cfg.r0, cfg.grid[0])
+    far_r = max_corner_radius(cfg.aabb)
+    if cfg.interval_th:
+        knots = knots_c = r_reference_grid(far_r, cfg.r0, cfg.grid[0])       # `downsample` is ignored (coordinates.py:112-117)
+    else:
+        def knots(r):
+            return normalize_radius_plain(r, far_r, cfg.r0, cfg.grid[0])
+
+        def knots_c(r):                                                        # normalize_coord(downsample=2), EgoNeRF.py:523
+            return normalize_radius_plain(r, far_r, cfg.r0, cfg.grid[0], downsample=2)
     nc, nf = cfg.n_coarse, cfg.n_fine
 
-    if cfg.exp_sampling:
+    if cfg.exp_sampling and not cfg.interval_th:
+        zc = cfg.near + plain_sample_schedule(cfg.near, cfg.far, nc, u_coarse if is_train else None)
+        zc = zc if is_train else zc[0].repeat(N, 1)
+        zq = zc
+    elif cfg.exp_sampling:
         r = sample_schedule(cfg.near, cfg.far, cfg.r0, nc)
         if is_train:
             zc = cfg.near + jitter_schedule(r, u_coarse)
@@ -505,7 +547,7 @@ def render(sd: Dict[str, torch.Tensor], cfg: OracleCfg, rays: torch.Tensor, is_t
     dc = zc[:, 1:] - zc[:, :-1]
     dc = torch.cat([dc, dc[:, -1:]], -1)
     pc = o[:, None, :] + d[:, None, :] * zq[..., None]
-    cc, yang_c, margin_c = _coords(pc.reshape(-1, 3), center, knots)
+    cc, yang_c, margin_c = _coords(pc.reshape(-1, 3), center, knots_c)
     aux = {}
 
     if cfg.resampling:

@@ -22,12 +22,12 @@ OUT = os.path.join(ROOT, "tests", "golden")
 coordinates_dict, RefEgoNeRF, ref_volume_renderer, ref_sample_pdf, ref_raw2alpha = import_reference()
 
 
-def build_reference(scene):
+def build_reference(scene, interval_th=True):
     co = coordinates_dict['yinyang']('cpu', scene.aabb, exp_r=True, N_voxel=scene.n_voxels, r0=scene.r0,
-                                     interval_th=True)
+                                     interval_th=interval_th)
     reso = co.N_to_reso(scene.n_voxels, scene.aabb)
     assert reso == scene.grid, (reso, scene.grid)
-    model = RefEgoNeRF(scene.aabb, reso, 'cpu', co, **scene.model_kwargs())
+    model = RefEgoNeRF(scene.aabb, reso, 'cpu', co, **dict(scene.model_kwargs(), interval_th=interval_th))
     model.load_state_dict(scene.state_dict, strict=True)
     if scene.emission is not None:
         model.envmap.emission = scene.emission.clone().requires_grad_(True)
@@ -35,10 +35,11 @@ def build_reference(scene):
     return co, model
 
 
-def ref_render(model, rays, is_train, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, exp_sampling=True):
+def ref_render(model, rays, is_train, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, exp_sampling=True,
+               interval_th=True):
     return ref_volume_renderer(rays, model, chunk=rays.shape[0], n_coarse=n_coarse, n_fine=n_fine,
                                is_train=is_train, exp_sampling=exp_sampling, resampling=resampling,
-                               use_coarse_sample=use_coarse_sample, interval_th=True, device='cpu',
+                               use_coarse_sample=use_coarse_sample, interval_th=interval_th, device='cpu',
                                white_bg=False)
 
 
@@ -120,7 +121,7 @@ def main():
 
     # ---- 3. whole-path renders ---------------------------------------------------------------------
     def render_case(name, scene, rays, is_train, seed=1234, grads=False, **kw):
-        co, model = build_reference(scene)
+        co, model = build_reference(scene, kw.get("interval_th", True))
         N = rays.shape[0]
         u_c = u_f = None
         if is_train:
@@ -187,6 +188,19 @@ def main():
     # other decoders that work through EgoNeRF.forward in the reference: MLP, RGB
     render_case("render_tiny_mlp.npz", make_scene(n_voxels=40 ** 3, seed=9, shading='MLP'), r64, False)
     render_case("render_tiny_rgb.npz", make_scene(n_voxels=40 ** 3, seed=10, shading='RGB', app_dim=3), r64, False)
+
+    # ---- 3b. a run WITHOUT --interval_th (opt.py:190 default): plain exponential ladders (EgoNeRF.py:59-67,
+    # coordinates.py:132-156), coarse pass on the N_r/2 ladder
+    render_case("render_tiny_plain_eval.npz", tiny, r64, False, interval_th=False)
+    render_case("render_tiny_plain_train_grad.npz", tiny, r64p, True, grads=True, seed=78, interval_th=False)
+    render_case("render_tiny_plain_noresample.npz", tiny, r64, False, resampling=False, n_fine=0, interval_th=False)
+    co = coordinates_dict['yinyang']('cpu', tiny.aabb, exp_r=True, N_voxel=tiny.n_voxels, r0=tiny.r0, interval_th=False)
+    gk = torch.Generator().manual_seed(6)
+    pts = torch.cat([torch.tensor([[1., 0, 0], [0, 0, 1.], [.03, 0, 0], [.02, .01, 0], [0., 0, 0], [26., 0, 0], [30., 0, 0]]),
+                     (torch.rand(1500, 3, generator=gk) - .5) * 30, torch.randn(1500, 3, generator=gk) * 0.3])
+    unn = co.from_cartesian(pts)
+    npz("kat_coords_plain.npz", aabb=tiny.aabb, grid=np.array(co.N_to_reso(tiny.n_voxels, tiny.aabb)), r0=tiny.r0, far_r=co.far[0],
+        points=pts, normalized=co.normalize_coord(unn), normalized_coarse=co.normalize_coord(unn, downsample=2))
 
     # ---- 4. coarse-to-fine upsampling (train.py:371-377): 20^3 -> 28^3 voxels, then a render on the new grid
     up = make_scene(n_voxels=20 ** 3, seed=3)

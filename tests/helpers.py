@@ -26,6 +26,10 @@ RENDER_CASES = {
     "render_300_train": (dict(n_voxels=27e6), {}),
     "render_tiny_march_eval": (TINY, dict(exp_sampling=False)),
     "render_tiny_march_train": (TINY, dict(exp_sampling=False)),
+    # a run without --interval_th: plain exponential ladders, coarse pass on the N_r/2 ladder
+    "render_tiny_plain_eval": (TINY, dict(interval_th=False)),
+    "render_tiny_plain_train_grad": (TINY, dict(interval_th=False)),
+    "render_tiny_plain_noresample": (TINY, dict(interval_th=False, resampling=False, n_fine=0)),
     "render_tiny_mlp": (dict(n_voxels=40 ** 3, seed=9, shading='MLP'), {}),
     "render_tiny_rgb": (dict(n_voxels=40 ** 3, seed=10, shading='RGB', app_dim=3), {}),
 }

@@ -97,6 +97,33 @@ def test_host_r_knots_matches_oracle(lib, half, r0, n_r):
     assert np.abs(np.array(out) - ref).max() <= 4e-6 * ref.max()
 
 
+def test_host_plain_ladders_match_oracle(lib):
+    """The ladders of a run without --interval_th (EgnConfig.plain_ladders): C helpers and Python mirror against the oracle."""
+    from egonerf_b200.models.coordinates import YinYangSphericalCoords, plain_sample_schedule
+    n = 128
+    out, ratio, r0p = (C.c_float * n)(), C.c_float(), C.c_float()
+    assert lib.egn_host_plain_sample_schedule(0.01, 15., n, out, C.byref(ratio), C.byref(r0p)) == 0
+    ref = O.plain_sample_schedule(0.01, 15., n)[0].numpy()
+    assert np.abs(np.array(out) - ref).max() <= 4e-6 * ref.max()
+    r, ratio_py, r0_py = plain_sample_schedule(0.01, 15., n)
+    assert torch.equal(r, O.plain_sample_schedule(0.01, 15., n)[0])                 # eval depths: bit-exact
+    assert abs(ratio.value - ratio_py) < 1e-7 and abs(r0p.value - r0_py) < 1e-8
+    aabb = torch.tensor([[-15.5] * 3, [15.5] * 3])
+    co = YinYangSphericalCoords("cpu", aabb, exp_r=True, N_voxel=40 ** 3, r0=0.03, interval_th=False)
+    far_r = O.max_corner_radius(aabb)
+    for ds, n_r in ((None, co.N_r), (2, co.N_r // 2)):
+        knots = co.r_knots(downsample=ds)
+        assert knots.shape[0] == n_r + 3 and knots[0] == 0 and abs(float(knots[1]) - 0.03) < 1e-9
+        ck = (C.c_float * (n_r + 3))()
+        assert lib.egn_host_plain_r_knots(float(far_r), 0.03, n_r, ck) == 0
+        assert np.abs(np.array(ck) - knots.numpy()).max() <= 4e-6 * float(knots.max())
+        # searching the knot ladder == the reference's closed form (log / trunc / pow), away from the knots themselves
+        r = torch.rand(4000, generator=torch.Generator().manual_seed(1)) * float(far_r) * 1.05
+        hi = torch.clamp(torch.searchsorted(knots, r, side="right"), 1, n_r + 2)
+        mine = ((hi - 1) + (r - knots[hi - 1]) / (knots[hi] - knots[hi - 1])) / n_r * 2 - 1
+        assert (mine - O.normalize_radius_plain(r, far_r, 0.03, co.N_r, downsample=ds)).abs().max() <= 2e-6
+
+
 def test_python_mirror_ladders_are_bit_exact():
     """The drop-in modules feed the kernels the ladders built by the host mirror: these must equal the oracle's."""
     from egonerf_b200.models.coordinates import YinYangSphericalCoords, sample_schedule

@@ -14,7 +14,7 @@ import torch
 from tests.helpers import RENDER_CASES, T, load_golden, oracle_cfg, scene_for
 
 pytestmark = pytest.mark.gpu
-GRAD_CASES = ["render_tiny_train_grad", "render_tiny_env_train_grad"]
+GRAD_CASES = ["render_tiny_train_grad", "render_tiny_env_train_grad", "render_tiny_plain_train_grad"]
 
 
 def _loss(out, g, dev):
@@ -31,7 +31,7 @@ def _run(name, use_ref_depths):
     g = load_golden(name)
     scene = scene_for(skw)
     dev = "cuda:0"
-    model = model_from_scene(scene, dev)
+    model = model_from_scene(scene, dev, interval_th=okw.get("interval_th", True))
     kw = dict(RENDER_KW)
     kw.update(okw)
     out = model(T(g["rays"]).to(dev), is_train=True, u_coarse=T(g["u_coarse"]).to(dev), u_fine=T(g["u_fine"]).to(dev),

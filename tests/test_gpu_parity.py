@@ -51,7 +51,7 @@ def _case(name):
     is_train = bool(g["is_train"])
     u_c = T(g["u_coarse"]) if "u_coarse" in g else None
     u_f = T(g["u_fine"]) if "u_fine" in g else None
-    model = model_from_scene(scene)
+    model = model_from_scene(scene, interval_th=okw.get("interval_th", True))
     ok = stable_rays(scene, oracle_cfg(scene, **okw), rays, is_train, u_c, u_f).numpy()
     assert ok.mean() > 0.97, "too many boundary-ambiguous rays"
     return g, scene, okw, rays, is_train, u_c, u_f, model, ok
@@ -365,3 +365,17 @@ def test_occupancy_mask_family_matches_reference_golden(tmp_path):
     # the render path ignores the mask, as the reference's EgoNeRF.forward does
     rays = T(load_golden("render_tiny_eval")["rays"])
     assert torch.equal(_render(fresh, rays, False, None, None, {})[0], _render(model_from_scene(scene), rays, False, None, None, {})[0])
+
+
+def test_plain_ladder_coordinates_match_reference_golden():
+    """A run without --interval_th: `egn_yinyang_coords` on the plain ladder against the reference's normalize_coord."""
+    from egonerf_b200.models.coordinates import YinYangSphericalCoords
+    g = load_golden("kat_coords_plain")
+    co = YinYangSphericalCoords("cuda", T(g["aabb"]), exp_r=True, N_voxel=40 ** 3, r0=float(g["r0"]), interval_th=False)
+    assert [co.N_r, co.N_theta, co.N_phi] == [int(v) for v in g["grid"]]
+    got = co.cart_to_normalized(T(g["points"]).cuda()).cpu()
+    ref = T(g["normalized"])
+    assert torch.equal(got[:, 6], ref[:, 6])
+    act_g = torch.where(ref[:, 6:7] != 0, got[:, 3:6], got[:, 0:3])
+    act_r = torch.where(ref[:, 6:7] != 0, ref[:, 3:6], ref[:, 0:3])
+    assert (act_g - act_r).abs().max() <= 2e-6

@@ -17,7 +17,7 @@ MLP_FEA_CASES = [n for n in RENDER_CASES if "mlp" not in n and "rgb" not in n an
 def _model(name):
     from egonerf_b200.scene_io import model_from_scene
     skw, okw = RENDER_CASES[name]
-    return model_from_scene(scene_for(skw)), okw, load_golden(name)
+    return model_from_scene(scene_for(skw), interval_th=okw.get("interval_th", True)), okw, load_golden(name)
 
 
 def _render(model, g, okw, mode, use_ref_depths=True):

@@ -126,7 +126,7 @@ def test_render_baseline_shapes(name):
     _run_case(name)
 
 
-@pytest.mark.parametrize("name", ["render_tiny_train_grad", "render_tiny_env_train_grad"])
+@pytest.mark.parametrize("name", ["render_tiny_train_grad", "render_tiny_env_train_grad", "render_tiny_plain_train_grad"])
 def test_gradients(name):
     """autograd through the oracle against the reference's own .grad (all 38/39 parameter tensors)."""
     skw, okw = RENDER_CASES[name]
@@ -193,3 +193,22 @@ def test_occupancy_mask_family():
     ma = O.compute_alpha(scene.state_dict, T(g["coords7"]), T(g["step"]), scene.density_shift, mask=vols)
     assert np.array_equal(ma.numpy() == 0, g["masked_alpha"] == 0)
     assert np.abs(ma.numpy() - g["masked_alpha"]).max() <= 1e-6
+
+
+def test_plain_ladder_coordinates():
+    """Without interval_th: normalize_coord = closed form on r0 * ratio^k (coordinates.py:132-156), halved ladder under
+    `downsample=2`; includes r < r0, r = r0, the origin and radii beyond the grid."""
+    g = load_golden("kat_coords_plain")
+    aabb, grid, r0 = T(g["aabb"]), [int(v) for v in g["grid"]], float(g["r0"])
+    far_r = O.max_corner_radius(aabb)
+    assert float(far_r) == float(g["far_r"])
+    r, a, b, is_yang, _ = O.cart_to_yinyang(T(g["points"]), O.scene_center(aabb))
+    an, bn = O.normalize_angles(a, b)
+    for key, ds in (("normalized", None), ("normalized_coarse", 2)):
+        rn = O.normalize_radius_plain(r, far_r, r0, grid[0], downsample=ds)
+        ref = T(g[key])
+        act = torch.where(is_yang[:, None], ref[:, 3:6], ref[:, 0:3])
+        assert torch.equal(ref[:, 6] != 0, is_yang)
+        ok = torch.isfinite(act[:, 0])                      # the origin: log(0) -> the reference itself yields r/r0 = 0
+        assert ok.all()
+        assert (torch.stack([rn, an, bn], -1) - act).abs().max() <= 2e-6, key
