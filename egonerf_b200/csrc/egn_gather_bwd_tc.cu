@@ -79,6 +79,13 @@ __device__ __forceinline__ float4 gt_tap(const EgnKernelCfg& k, unsigned off) {
         return ldg4(k.tables + off);
     }
 }
+__device__ __forceinline__ uint2 gt_raw(const EgnKernelCfg& k, unsigned off) {
+    return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(k.tables_bf16) + off));
+}
+__device__ __forceinline__ float4 gt_widen(const uint2& q) {
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xffff0000u));
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -221,6 +228,21 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 j0[a] = (unsigned)min(max(i0, 0), G - 1);
                 j1[a] = (unsigned)min(max(i0 + 1, 0), G - 1);
             }
+            // bf16 tables: all 18 taps of the sample are requested before the first one is used (8 B per lane and tap stay
+            // packed until then) -- three times the loads in flight of a per-factor-pair loop
+            uint2 raw[BF16 ? 3 : 1][6];
+            if constexpr (BF16) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+                    const unsigned W = (unsigned)k.lay.G[ax];
+                    const unsigned pbase = (unsigned)k.lay.pf[yang][i] + sub * 4, lbase = (unsigned)k.lay.lf[yang][i] + sub * 4;
+                    const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
+                    raw[i][0] = gt_raw(k, pbase + (ra + j0[ax]) * EGN_CF); raw[i][1] = gt_raw(k, pbase + (ra + j1[ax]) * EGN_CF);
+                    raw[i][2] = gt_raw(k, pbase + (rb + j0[ax]) * EGN_CF); raw[i][3] = gt_raw(k, pbase + (rb + j1[ax]) * EGN_CF);
+                    raw[i][4] = gt_raw(k, lbase + j0[al] * EGN_CF); raw[i][5] = gt_raw(k, lbase + j1[al] * EGN_CF);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
@@ -230,8 +252,14 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 const unsigned o0 = pbase + (ra + j0[ax]) * EGN_CF, o1 = pbase + (ra + j1[ax]) * EGN_CF;
                 const unsigned o2 = pbase + (rb + j0[ax]) * EGN_CF, o3 = pbase + (rb + j1[ax]) * EGN_CF;
                 const unsigned q0 = lbase + j0[al] * EGN_CF, q1 = lbase + j1[al] * EGN_CF;
-                const float4 t0 = gt_tap<BF16>(k, o0), t1 = gt_tap<BF16>(k, o1), t2 = gt_tap<BF16>(k, o2), t3 = gt_tap<BF16>(k, o3);
-                const float4 l0 = gt_tap<BF16>(k, q0), l1 = gt_tap<BF16>(k, q1);
+                float4 t0, t1, t2, t3, l0, l1;
+                if constexpr (BF16) {
+                    t0 = gt_widen(raw[i][0]); t1 = gt_widen(raw[i][1]); t2 = gt_widen(raw[i][2]); t3 = gt_widen(raw[i][3]);
+                    l0 = gt_widen(raw[i][4]); l1 = gt_widen(raw[i][5]);
+                } else {
+                    t0 = gt_tap<BF16>(k, o0); t1 = gt_tap<BF16>(k, o1); t2 = gt_tap<BF16>(k, o2); t3 = gt_tap<BF16>(k, o3);
+                    l0 = gt_tap<BF16>(k, q0); l1 = gt_tap<BF16>(k, q1);
+                }
                 const float w0 = wa0[ax] * wa0[ay], w1 = wa1[ax] * wa0[ay], w2 = wa0[ax] * wa1[ay], w3 = wa1[ax] * wa1[ay];
                 const float u0 = wa0[al], u1 = wa1[al];
                 float4 P = f4zero();
