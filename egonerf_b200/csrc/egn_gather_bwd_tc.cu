@@ -32,7 +32,9 @@ struct GtLayout {
     static constexpr int DV = V + (GT_VK / 8) * GT_VCHUNK;                 // [128 m][148] fp32  75 776
     static constexpr int KNOTS = DV + TC_TM * GT_DVS * 4;
     static constexpr int YANG = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
-    static constexpr int MBAR = YANG + TC_TM;
+    static constexpr int COORD = YANG + TC_TM;                             // [128] float4: normalised r, polar, azimuth, flags
+    static constexpr int DSG = COORD + TC_TM * 16;                         // [128] d(sigma feature)
+    static constexpr int MBAR = DSG + TC_TM * 4;
     static constexpr int TMEM = MBAR + 16;
     static constexpr int TOTAL = TMEM + 16;
 };
@@ -104,6 +106,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     float* dvs = reinterpret_cast<float*>(smem + L::DV);
     float* s_knots = reinterpret_cast<float*>(smem + L::KNOTS);
     unsigned char* s_yang = smem + L::YANG;
+    float4* s_coord = reinterpret_cast<float4*>(smem + L::COORD);
+    float* s_dsg = reinterpret_cast<float*>(smem + L::DSG);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
     const uint32_t bar = smem_u32(smem + L::MBAR);
 
@@ -137,35 +141,43 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     bool ok = true;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const uint32_t par = it & 1;
-        // ---- Ph0. coordinates of this warp's 8 samples (lane j < 8 owns row 8 * warp + j) ----
-        const long long mg = tile * TC_TM + 8 * warp + (lane & 7);
-        YYCoord cc;
-        cc.c[0] = cc.c[1] = cc.c[2] = -3.f;
-        cc.yang = 0;
-        float dsg = 0.f;
-        const bool glive = mg < M;
-        if (glive) {
-            const long long ray = mg / k.S;
-            const float z = zs[mg];
-            const float* ry = rays + ray * 6;
-            cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
-            dsg = d_fsig[mg];
-        }
-        if (lane < 8) s_yang[8 * warp + lane] = (unsigned char)cc.yang;
-        if (it > 0) ok &= mbar_wait(bar + 8, (it - 1) & 1);     // MMA2 of the previous tile has finished with dF2 and V
-        __syncthreads();
-        // ---- Ph1. dF2 tile ----
+        // ---- Ph1a. this thread's 8 values of d_feat: requested now, in flight during Ph0 ----
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
         {
             const long long gm = tile * TC_TM + row;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;
             if (gm < M) {
                 const float4* f4 = reinterpret_cast<const float4*>(d_feat + gm * EGN_FEAT_STRIDE) + 2 * q;
                 const float4 a = __ldg(f4);
                 v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
                 if (q < 3) { const float4 b = __ldg(f4 + 1); v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
             }
+        }
+        // ---- Ph0. coordinates + d(sigma feature) of the tile's 128 samples: one sample per lane of warps 0..3 -> smem ----
+        if (warp < 4) {
+            const int r = 32 * warp + lane;
+            const long long mg = tile * TC_TM + r;
+            YYCoord cc;
+            cc.c[0] = cc.c[1] = cc.c[2] = -3.f;
+            cc.yang = 0;
+            float dsg = 0.f;
+            const bool glive = mg < M;
+            if (glive) {
+                const long long ray = mg / k.S;
+                const float z = zs[mg];
+                const float* ry = rays + ray * 6;
+                cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+                dsg = d_fsig[mg];
+            }
+            s_coord[r] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang | (glive ? 2 : 0)));
+            s_dsg[r] = dsg;
+            s_yang[r] = (unsigned char)cc.yang;
+        }
+        if (it > 0) ok &= mbar_wait(bar + 8, (it - 1) & 1);     // MMA2 of the previous tile has finished with dF2 and V
+        __syncthreads();
+        // ---- Ph1b. dF2 tile ----
+        {
             const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int yang = s_yang[row];
             store_chunk<false>(dfs, nullptr, 4 * yang + q, row, v);
@@ -207,13 +219,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         for (int itr = 0; itr < 4; ++itr) {
             const int src = 2 * itr + (lane >> 4);              // sample within the warp's 8
             const int srow = 8 * warp + src;
-            float c[3];
-            c[0] = __shfl_sync(FULL, cc.c[0], src);
-            c[1] = __shfl_sync(FULL, cc.c[1], src);
-            c[2] = __shfl_sync(FULL, cc.c[2], src);
-            const int yang = __shfl_sync(FULL, cc.yang, src);
-            const float dsig = __shfl_sync(FULL, dsg, src);
-            const bool slive = __shfl_sync(FULL, (int)glive, src) != 0;
+            const float4 sc = s_coord[srow];
+            const float c[3] = {sc.x, sc.y, sc.z};
+            const int yang = __float_as_int(sc.w) & 1;
+            const bool slive = (__float_as_int(sc.w) & 2) != 0;
+            const float dsig = s_dsg[srow];
             unsigned j0[3], j1[3];
             float wa0[3], wa1[3];
 #pragma unroll
