@@ -38,8 +38,8 @@ struct FuLayout {
     static constexpr int KNOTS = YANG + 4 * TC_TM;
     static constexpr int MBAR = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
     static constexpr int TMEM = MBAR + 8 * 8;
-    static constexpr int TOTAL = TMEM + 16;
-    static constexpr int PART = A + 16 * TC_CHUNK;                    // layer-3 partial sums (see egn_mlp_tc.cu)
+    static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4
+    static constexpr int TOTAL = PART + TC_TM * 16;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
 
@@ -245,22 +245,58 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
         const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t a_s = smem_u32(as), w1_s = smem_u32(w1s), w2_s = smem_u32(w2s), bb_s = smem_u32(bbs), v_s = smem_u32(vs);
         const float bias3[3] = {__ldg(b3), __ldg(b3 + 1), __ldg(b3 + 2)};
+        // Software pipeline over tiles.  The tensor pipe works on layer 0 of tile t+1 while this group waits for layer 2 of
+        // tile t, and on layer 1 of tile t while the group runs layer 3 of tile t-1 out of TMEM: only the layer-2 wait is
+        // exposed.  TMEM: D1 = columns 0..127, D2 = 128..255, feat2 = 256..319.
+        auto issue_layer0 = [&](uint32_t i) {                   // thread 0: feat2 = V . [B_yin | B_yang]^T for CTA-local tile i
+            const uint32_t bb = i & 1;
+            ok &= mbar_wait(v_full0 + 8 * bb, (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < FU_VK / 16; ++ks)
+                tc_mma(tmem + 256, tc_desc(v_s + bb * FU_VBYTES + ks * 2 * FU_VCHUNK, FU_VCHUNK),
+                       tc_desc(bb_s + ks * 2 * FU_BB_CHUNK, FU_BB_CHUNK), TC_IDESC_128x64, ks > 0);
+            tc_commit(v_empty0 + 8 * bb);
+            tc_commit(feat_full);
+        };
+        // layer 3 + sigmoid of the tile whose D2 sits in TMEM (its layer-2 completion has been waited for)
+        auto layer3 = [&](long long gm3) {
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col = 64 * half + 32 * cc;
+                uint32_t r[32];
+                tmem_ld32(tmem_lane + 128 + col, r);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + q);
+                    const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + q);
+                    const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + q);
+                    const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + q);
+                    const float h0 = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
+                    const float h2 = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
+                    p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
+                    p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
+                    p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
+                }
+            }
+            tc_fence_before();
+            if (half == 1) *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, 0.f);
+            named_bar_sync(1, FU_GROUP);
+            if (half == 0 && gm3 < M) {
+                const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
+                rgbs[gm3 * 3 + 0] = egn_sigmoid(p0 + q.x + bias3[0]);
+                rgbs[gm3 * 3 + 1] = egn_sigmoid(p1 + q.y + bias3[1]);
+                rgbs[gm3 * 3 + 2] = egn_sigmoid(p2 + q.z + bias3[2]);
+            }
+        };
+        if (tid == 0 && (long long)blockIdx.x < tiles) issue_layer0(0);
         uint32_t it = 0;
+        long long gm_prev = M;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const uint32_t b = it & 1, u = it >> 1;
             const long long gm = tile * TC_TM + row;
             const bool live = gm < M;
-            // ---- layer 0: feat2 (TMEM columns 256..319) = V . [B_yin | B_yang]^T ----
-            ok &= mbar_wait(v_full0 + 8 * b, u & 1);
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < FU_VK / 16; ++ks)
-                    tc_mma(tmem + 256, tc_desc(v_s + b * FU_VBYTES + ks * 2 * FU_VCHUNK, FU_VCHUNK),
-                           tc_desc(bb_s + ks * 2 * FU_BB_CHUNK, FU_BB_CHUNK), TC_IDESC_128x64, ks > 0);
-                tc_commit(v_empty0 + 8 * b);
-                tc_commit(feat_full);
-            }
+            // ---- layer 0 of this tile was issued one iteration ago ----
             ok &= mbar_wait(feat_full, it & 1);
             tc_fence_after();
             // ---- A. this thread's 16 elements: features of its hemisphere (from TMEM), then view direction / 1 / padding ----
@@ -302,7 +338,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
             fence_async_smem();
             tc_fence_before();
             named_bar_sync(1, FU_GROUP);
-            // ---- B. layer 1 ----
+            // ---- B. layer 1 (runs on the tensor pipe during layer 3 of the previous tile) ----
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll
@@ -310,6 +346,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
                     tc_mma(tmem, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w1_s + ks * 2 * TC_CHUNK), TC_IDESC_128x128, ks > 0);
                 tc_commit(d1_full);
             }
+            if (it > 0) layer3(gm_prev);
             ok &= mbar_wait(d1_full, it & 1);
             tc_fence_after();
             // ---- C. H1 = relu(D1) -> operand of layer 2 ----
@@ -327,47 +364,20 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
             fence_async_smem();
             tc_fence_before();
             named_bar_sync(1, FU_GROUP);
-            // ---- D. layer 2 ----
+            // ---- D. layer 2, then layer 0 of the next tile ----
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < EGN_HID / 16; ++ks)
                     tc_mma(tmem + 128, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w2_s + ks * 2 * TC_CHUNK), TC_IDESC_128x128, ks > 0);
                 tc_commit(d2_full);
+                if (tile + gridDim.x < tiles) issue_layer0(it + 1);
             }
             ok &= mbar_wait(d2_full, it & 1);
             tc_fence_after();
-            // ---- E. layer 3 + sigmoid ----
-            float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int col = 64 * half + 32 * cc;
-                uint32_t r[32];
-                tmem_ld32(tmem_lane + 128 + col, r);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + q);
-                    const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + q);
-                    const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + q);
-                    const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + q);
-                    const float h0 = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
-                    const float h2 = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
-                    p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
-                    p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
-                    p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
-                }
-            }
-            tc_fence_before();
-            if (half == 1) *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, 0.f);
-            named_bar_sync(1, FU_GROUP);
-            if (half == 0 && live) {
-                const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
-                rgbs[gm * 3 + 0] = egn_sigmoid(p0 + q.x + bias3[0]);
-                rgbs[gm * 3 + 1] = egn_sigmoid(p1 + q.y + bias3[1]);
-                rgbs[gm * 3 + 2] = egn_sigmoid(p2 + q.z + bias3[2]);
-            }
-            named_bar_sync(1, FU_GROUP);                       // the next tile's X overwrites the partial-sum scratch
+            gm_prev = gm;
         }
+        if (it > 0) layer3(gm_prev);                            // layer 3 of the last tile
     }
     if (!ok) __trap();                                          // a lost mbarrier arrive: fail loudly, never hang
     tc_fence_before();
