@@ -68,7 +68,7 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
 
     // ---- one-time setup: TMEM, barriers, weights ----
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(SPLIT ? 512 : 256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
@@ -122,11 +122,53 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             }
         }
     };
+    // layer 3 of a finished tile (its D2 sits in TMEM columns 128..255): H2 = relu(D2 + b2); rgb = sigmoid(W3 H2 + b3) in fp32.
+    // The partial sums of the NQ column blocks of a row meet in TMEM columns 256.. of the row's lane (the four threads of a
+    // row live in warps w, w+4, w+8, w+12 = the same lane quadrant): no shared memory, so this can run while the tensor pipe
+    // reads the operand tiles of the NEXT tile's layer 1.
+    auto layer3 = [&](long long gm3) {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < CPT / 32; ++cc) {
+            const int col = CPT * q + 32 * cc;
+            uint32_t r[32];
+            tmem_ld32(tmem_lane + 128 + col, r);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {                 // warp-uniform addresses: one L1 transaction per load
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + g);
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + g);
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + g);
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + g);
+                const float h0 = fmaxf(__uint_as_float(r[4 * g]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * g + 1]) + bb.y, 0.f);
+                const float h2 = fmaxf(__uint_as_float(r[4 * g + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * g + 3]) + bb.w, 0.f);
+                p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
+                p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
+                p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
+            }
+        }
+        if (q > 0) tmem_st4(tmem_lane + 256 + 4 * (q - 1), __float_as_uint(p0), __float_as_uint(p1), __float_as_uint(p2), 0u);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (q == 0) {
+            uint32_t t[16];
+            tmem_ld16(tmem_lane + 256, t);
+            if (gm3 < M) {
+#pragma unroll
+                for (int j = 0; j < NQ - 1; ++j) {
+                    p0 += __uint_as_float(t[4 * j]); p1 += __uint_as_float(t[4 * j + 1]); p2 += __uint_as_float(t[4 * j + 2]);
+                }
+                rgbs[gm3 * 3 + 0] = egn_sigmoid(p0 + bias3[0]);
+                rgbs[gm3 * 3 + 1] = egn_sigmoid(p1 + bias3[1]);
+                rgbs[gm3 * 3 + 2] = egn_sigmoid(p2 + bias3[2]);
+            }
+        }
+    };
     float el[EPT];
     load_elements(blockIdx.x, el);
+    long long gm_prev = M;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const long long gm = tile * TC_TM + row;
-        const bool live = gm < M;
         // ---- A. input rows: EPT elements per thread -> chunks of [x, sin x, cos x, sin 2x, cos 2x] ----
         {
 #pragma unroll
@@ -163,6 +205,8 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             }
             tc_commit(bar0);
         }
+        // ---- E(previous tile): its layer 3 runs on the CUDA cores while the tensor pipe works on this tile's layer 1 ----
+        if (it > 0) layer3(gm_prev);
         // ---- C. H1 = relu(D1) (b1 is inside D1) -> bf16 operand of layer 2 (overwrites X: its MMAs have completed) ----
         ok &= mbar_wait(bar0, it & 1);
         tc_fence_after();
@@ -197,62 +241,27 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             tc_commit(bar1);
         }
         load_elements(tile + gridDim.x, el);              // next tile's inputs: in flight while layer 2 runs
-        // ---- E. H2 = relu(D2 + b2); rgb = sigmoid(W3 H2 + b3) in fp32 ----
-        ok &= mbar_wait(bar1, it & 1);
+        ok &= mbar_wait(bar1, it & 1);                    // A is free for the next tile's X, D2 is ready for layer 3
         tc_fence_after();
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < CPT / 32; ++cc) {
-            const int col = CPT * q + 32 * cc;
-            uint32_t r[32];
-            tmem_ld32(tmem_lane + 128 + col, r);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {                 // warp-uniform addresses: one L1 transaction per load
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + g);
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + g);
-                const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + g);
-                const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + g);
-                const float h0 = fmaxf(__uint_as_float(r[4 * g]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * g + 1]) + bb.y, 0.f);
-                const float h2 = fmaxf(__uint_as_float(r[4 * g + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * g + 3]) + bb.w, 0.f);
-                p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
-                p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
-                p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
-            }
-        }
-        tc_fence_before();
-        if (q > 0) *reinterpret_cast<float4*>(part + ((q - 1) * TC_TM + row) * 4) = make_float4(p0, p1, p2, 0.f);
-        __syncthreads();
-        if (q == 0 && live) {
-#pragma unroll
-            for (int j = 0; j < NQ - 1; ++j) {
-                const float4 t = *reinterpret_cast<const float4*>(part + (j * TC_TM + row) * 4);
-                p0 += t.x; p1 += t.y; p2 += t.z;
-            }
-            rgbs[gm * 3 + 0] = egn_sigmoid(p0 + bias3[0]);
-            rgbs[gm * 3 + 1] = egn_sigmoid(p1 + bias3[1]);
-            rgbs[gm * 3 + 2] = egn_sigmoid(p2 + bias3[2]);
-        }
-        __syncthreads();                                  // the next tile's X overwrites the partial-sum scratch
+        gm_prev = gm;
     }
+    if (it > 0) layer3(gm_prev);                          // layer 3 of the last tile
     if (!ok) __trap();                                      // a lost tcgen05.commit arrive: fail loudly, never hang
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(SPLIT ? 512 : 256) : "memory");
 }
 
 int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                       float* rgbs, int split, cudaStream_t st) {
     const long long M = n * k.S;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
-    const int blocks = (int)(tiles < 148 * (split ? 1 : 2) ? tiles : 148 * (split ? 1 : 2));
-    if (split) {
-        cudaFuncSetAttribute(egn_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<true>::TOTAL);
-        egn_mlp_tc_kernel<true><<<blocks, 512, TcLayout<true>::TOTAL, st>>>(
-            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs);
-    } else {
-        cudaFuncSetAttribute(egn_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<false>::TOTAL);
-        egn_mlp_tc_kernel<false><<<blocks, 256, TcLayout<false>::TOTAL, st>>>(
-            k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs);
-    }
+    // Only the 3-term split instantiation is launched: plain bf16 operands (EGN_MLP_TC_BF16) always take the fused fine pass
+    // (egn_fused.cu), which contains the same MLP.
+    (void)split;
+    const int blocks = (int)(tiles < 148 ? tiles : 148);
+    cudaFuncSetAttribute(egn_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcLayout<true>::TOTAL);
+    egn_mlp_tc_kernel<true><<<blocks, 512, TcLayout<true>::TOTAL, st>>>(
+        k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, feat, rgbs);
     return (int)cudaGetLastError();
 }
