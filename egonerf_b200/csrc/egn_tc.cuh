@@ -34,15 +34,27 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
 // bounded wait: a lost arrive must not hang the GPU.  try_wait with a suspend-time hint parks the warp in hardware (no issue
-// slots burnt, wake-up right after the arrive); ~400 x 10 ms without completion -> the caller traps.
+// slots burnt, wake-up right after the arrive).  The bound is WALL-CLOCK (%globaltimer, 2 s), not a retry count: the parked
+// wait may return early any number of times (other barrier traffic of the CTA, instrumented runs under a profiler), and a
+// retry budget would then expire without a lost arrive.  On expiry the caller traps.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < 400u; ++spin) {
+    for (uint32_t spin = 0; spin < 400u; ++spin) {           // the common case: a few parked waits, no timer traffic
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
         if (done) return true;
     }
-    return false;
+    uint32_t t0;                                             // low word of the ns timer: wraps at 4.29 s, the bound is 2 s
+    asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t0));
+#pragma unroll 1
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        if (done) return true;
+        uint32_t now;
+        asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(now));
+        if (now - t0 > 2000000000u) return false;
+    }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
