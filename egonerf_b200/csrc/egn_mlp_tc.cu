@@ -3,10 +3,12 @@
 // Same function as egn_mlp.cu (MLPRender_Fea, models/tensorBase.py:54-78 with fea_pe = view_pe = 2): per 128-sample tile
 //     X[128 x 160] (bf16)  --tcgen05.mma-->  D1 (TMEM, fp32)  --+b1, relu-->  H1[128 x 128] (bf16, shared memory)
 //     --tcgen05.mma-->  D2 (TMEM)  --+b2, relu, . W3 (fp32 FFMA), sigmoid-->  rgb
-// Two arithmetic modes (EgnConfig.mlp_mode):
-//   EGN_MLP_TC_SPLIT  every operand is split x = hi + lo (two bf16), D += A_lo B_hi + A_hi B_lo + A_hi B_hi with fp32
-//                     accumulation: products carry ~2^-17 relative error — fp32-equivalent for the 1e-4 parity bound
-//   EGN_MLP_TC_BF16   plain bf16 operands (throughput mode, PSNR-gated)
+// This kernel is the stand-alone MLP of the parity mode (EgnConfig.mlp_mode = EGN_MLP_TC_SPLIT): every operand is split
+// x = hi + lo (two bf16), D += A_lo B_hi + A_hi B_lo + A_hi B_hi with fp32 accumulation: products carry ~2^-17 relative
+// error -- fp32-equivalent for the 1e-4 parity bound.  The plain-bf16 mode (EGN_MLP_TC_BF16) runs the same MLP inside the
+// fused fine pass (egn_fused.cu); the SPLIT = false instantiation of this template is no longer launched.
+// The tile loop is software-pipelined: layer 3 of tile t-1 runs on the CUDA cores while the tensor pipe works on layer 1 of
+// tile t (see `layer3` below).
 //
 // Operand layout in shared memory: canonical K-major, no swizzle (UMMA "interleave"): 8 x 8 core matrices of 128 B,
 // element (row, k) at (k / 8) * 2048 + row * 16 + (k % 8) * 2 for 128-row tiles, i.e. LBO (K step) = 2048 B,
@@ -15,7 +17,7 @@
 // weights are staged): element e contributes [x, sin x, cos x, sin 2x, cos 2x] at k = 5e .. 5e+4 (e < app_dim: feature,
 // then the 3 view-direction components), so that a thread produces whole 16-byte chunks from 8 elements.
 //
-// 256 threads: thread t owns row (t & 127) and column half (t >> 7) — warps w and w+4 share TMEM lane quadrant w & 3.
+// 512 threads: thread t owns row (t & 127) and column block (t >> 7) — warps w, w+4, w+8, w+12 share TMEM lane quadrant w & 3.
 // One elected thread issues the MMAs; completion comes back through tcgen05.commit -> mbarrier.
 #include "egn_tc.cuh"
 #include "egn_host.h"
