@@ -196,3 +196,43 @@ def test_product_code_never_touches_the_oracle_or_the_reference_tree():
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     assert not any(getattr(n, "module", "") and str(n.module).startswith("oracle") for n in top)
     assert "/root/reference" not in open(os.path.join(ROOT, "bench.py")).read().replace("Nothing here reads /root/reference", "")
+
+
+def test_header_is_plain_c99_and_links_from_c(lib, tmp_path):
+    """The drop-in boundary is a C ABI: include/egn.h must compile as strict C99 (no C++-isms, no torch types) and a plain C
+    program must be able to size buffers and build the host ladders through libegn_b200.so (no GPU calls here)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "egn.h"
+int main(void) {
+    float z[128], k[151];
+    EgnConfig cfg = {0};
+    if (egn_abi_version() != EGN_ABI_VERSION) return 2;
+    if (egn_host_sample_schedule(0.01f, 15.f, 0.03f, 128, z)) { printf("err %s\n", egn_last_error()); return 1; }
+    if (egn_host_r_knots(26.846788f, 0.03f, 150, k)) return 1;
+    cfg.grid[0] = 150; cfg.grid[1] = 172; cfg.grid[2] = 516; cfg.c_sigma = 16; cfg.c_app = 48; cfg.app_dim = 27;
+    cfg.view_pe = cfg.fea_pe = 2; cfg.feature_c = 128; cfg.n_coarse = cfg.n_fine = 128;
+    cfg.use_coarse_sample = cfg.resampling = 1; cfg.mlp_mode = EGN_MLP_TC_BF16;
+    printf("%d %lld %lld %.6f %.6f\n", egn_samples_per_ray(&cfg), (long long)egn_table_floats(&cfg),
+           (long long)egn_workspace_bytes_eval(&cfg, 4096), z[127], k[150]);
+    cfg.c_sigma = 8;
+    if (egn_table_floats(&cfg) != -1) return 3;
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), "-L", libdir, "-legn_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    S, nfl, ws, z_last, k_last = run.stdout.split()
+    assert int(S) == 256 and int(nfl) == lib.egn_table_floats(_cfg(grid=(C.c_int32 * 3)(150, 172, 516))) and int(ws) > 0
+    assert abs(float(z_last) + 0.01 - 15.5509796) < 2e-5            # SURVEY 8c known-answer value of the sample schedule
+    assert abs(float(k_last) - float(O.r_reference_grid(torch.tensor(26.846788), 0.03, 150)[150])) < 1e-4
