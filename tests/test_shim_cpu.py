@@ -46,3 +46,34 @@ def test_parameter_names_shapes_and_optimizer_groups_match_the_reference():
     for key in ("aabb", "gridSize", "density_n_comp", "appearance_n_comp", "app_dim", "density_shift", "distance_scale",
                 "near_far", "shadingMode", "view_pe", "fea_pe", "featureC", "coordinates", "use_envmap", "envmap"):
         assert key in kw                                                                    # tensorBase.py:241-268
+
+
+def test_surface_train_py_touches_exists_with_reference_signatures():
+    """Every model / coordinates attribute the reference's train.py and renderer.py touch (train.py:96-97,123,189,253-270,
+    356-380; renderer.py:24-31) exists on the drop-in objects, with the reference's argument names."""
+    import inspect
+    from egonerf_b200.models.EgoNeRF import EgoNeRF, YinYangAlphaGridMask
+    from egonerf_b200.models.coordinates import YinYangSphericalCoords, coordinates_dict
+    for name in ("forward", "get_optparam_groups", "save", "load", "get_kwargs", "update_coarse_sigma_grid", "upsample_volume_grid",
+                 "up_sampling_VM", "updateAlphaMask", "getDenseAlpha", "compute_alpha", "vector_comp_diffs", "density_L1",
+                 "TV_loss_density", "TV_loss_app", "feature2density", "compute_densityfeature", "compute_coarse_densityfeature",
+                 "compute_appfeature", "update_stepSize", "init_svd_volume", "init_one_svd"):
+        assert callable(getattr(EgoNeRF, name)), name
+    fwd = list(inspect.signature(EgoNeRF.forward).parameters)
+    assert fwd[1:13] == ["rays_chunk", "white_bg", "is_train", "ndc_ray", "n_coarse", "n_fine", "exp_sampling", "pretrain_envmap",
+                         "pivotal_sample_th", "resampling", "use_coarse_sample", "interval_th"]            # EgoNeRF.py:491-495
+    assert list(inspect.signature(EgoNeRF.compute_alpha).parameters)[1:] == ["norm_locs", "length"]        # tensorBase.py:421
+    assert list(inspect.signature(EgoNeRF.up_sampling_VM).parameters)[1:] == ["plane_coef", "line_coef", "res_target"]
+    assert list(inspect.signature(YinYangAlphaGridMask.__init__).parameters)[1:] == ["device", "alpha_volume_yin", "alpha_volume_yang"]
+    for name in ("N_to_reso", "set_resolution", "update_aabb", "up_sampling_VM", "normalize_r"):
+        assert callable(getattr(YinYangSphericalCoords, name)), name
+    assert list(inspect.signature(YinYangSphericalCoords.__init__).parameters)[1:] == ["device", "aabb", "exp_r", "N_voxel", "r0",
+                                                                                      "interval_th"]     # train.py:122-124
+    assert list(inspect.signature(YinYangSphericalCoords.up_sampling_VM).parameters)[1:] == ["weights", "res_target", "ids"]
+    # both ladder flavours construct on the host (no GPU needed for the ladders)
+    aabb = torch.tensor([[-15.5] * 3, [15.5] * 3])
+    for ith in (True, False):
+        co = coordinates_dict["yinyang"]("cpu", aabb, exp_r=True, N_voxel=40 ** 3, r0=0.03, interval_th=ith)
+        assert co.r_knots().shape[0] == co.N_r + (1 if ith else 3)
+        co.set_resolution(co.N_to_reso(64 ** 3, aabb))
+        assert co.r0 == 0.05                                       # the reference's set_resolution default (coordinates.py:214)
