@@ -44,13 +44,13 @@ class YinYangAlphaGridMask(torch.nn.Module):
         self.alpha_volume_yang = alpha_volume_yang.view(1, 1, *alpha_volume_yang.shape[-3:])
 
     def sample_alpha(self, norm_samples):
-        alpha_vals = torch.empty_like(norm_samples[:, 0])
-        is_yin = norm_samples[:, -1] == 0
-        alpha_vals[is_yin] = F.grid_sample(self.alpha_volume_yin, norm_samples[is_yin][:, :3].view(1, -1, 1, 1, 3),
-                                           align_corners=True).view(-1)
-        alpha_vals[~is_yin] = F.grid_sample(self.alpha_volume_yang, norm_samples[~is_yin][:, 3:6].view(1, -1, 1, 1, 3),
-                                            align_corners=True).view(-1)
-        return alpha_vals
+        """(M,7) normalised coordinates -> (M,) occupancy of the active hemisphere (column 6: 0 = Yin, 1 = Yang)."""
+        out = torch.empty_like(norm_samples[:, 0])
+        yang = norm_samples[:, -1] != 0
+        for sel, vol, c0 in ((~yang, self.alpha_volume_yin, 0), (yang, self.alpha_volume_yang, 3)):
+            pts = norm_samples[sel][:, c0:c0 + 3].view(1, -1, 1, 1, 3)          # x = r -> W, y = polar -> H, z = azimuth -> D
+            out[sel] = F.grid_sample(vol, pts, align_corners=True).view(-1)
+        return out
 
 
 class _VolumeRender(torch.autograd.Function):
