@@ -4,12 +4,16 @@ made by oracle/make_golden.py).  This is the parity pin of the oracle — the re
 Tolerances: the oracle is an independent fp32 restatement (explicit taps instead of F.grid_sample, gathers instead of
 boolean-mask compaction), so sums are associated differently: 2e-6 on O(1) quantities, 1e-5 on rgb after 256-term sums.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import egn_oracle as O
-from tests.helpers import RENDER_CASES, TINY, T, checksum, load_golden, oracle_cfg, scene_for, stable_rays
+from tests.helpers import GOLDEN, RENDER_CASES, TINY, T, checksum, load_golden, oracle_cfg, scene_for, stable_rays
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 FAST = [n for n in RENDER_CASES if "tiny" in n]
 SLOW = [n for n in RENDER_CASES if "tiny" not in n]
@@ -212,3 +216,23 @@ def test_plain_ladder_coordinates():
         ok = torch.isfinite(act[:, 0])                      # the origin: log(0) -> the reference itself yields r/r0 = 0
         assert ok.all()
         assert (torch.stack([rn, an, bn], -1) - act).abs().max() <= 2e-6, key
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
+    """Re-runs oracle/make_golden.py (the UNMODIFIED reference, imported from /root/reference) into a scratch directory and
+    compares every array of every committed fixture bit for bit: the goldens are reproducible reference outputs, not
+    hand-edited numbers.  Never runs on the GPU box (no reference tree there)."""
+    import subprocess
+    import sys
+    code = ("import sys, warnings; warnings.simplefilter('ignore'); sys.path.insert(0, %r);"
+            "import oracle.make_golden as G; G.OUT = %r; G.main()") % (ROOT, str(tmp_path))
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stderr[-2000:]
+    committed = sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    assert committed == sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))
+    for f in committed:
+        a, b = np.load(os.path.join(GOLDEN, f)), np.load(os.path.join(str(tmp_path), f))
+        assert set(a.files) == set(b.files), f
+        for k in a.files:
+            assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f"), (f, k)
