@@ -67,6 +67,16 @@ class YinYangSphericalCoords:
         self.update_aabb(aabb)
         self.set_resolution(self.N_to_reso(N_voxel, aabb), r0=r0)
 
+    def __setstate__(self, state):
+        """Unpickling: also accepts the attribute set of the REFERENCE's object (center, device, near, far, inv_diff, exp_r,
+        interval_th, N_r, N_theta, N_phi, r0, ratio) — `EgoNeRF.save` pickles the coordinates object into `kwargs`
+        (EgoNeRF.py:158-160, tensorBase.py:241-268) and `train.py:155-160` rebuilds the model from it."""
+        self.__dict__.update(state)
+        self.__dict__.setdefault("aabb", None)
+        self._knots = None
+        if not self.exp_r:
+            raise NotImplementedError("egonerf_b200 implements the exponential-r Yin-Yang grid only")
+
     # ---- scalars (coordinates.py:187-204, 500-505) --------------------------------------------------
     def _get_max_r(self, aabb):
         lo, hi = aabb.tolist()

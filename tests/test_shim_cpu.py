@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -77,3 +78,32 @@ def test_surface_train_py_touches_exists_with_reference_signatures():
         assert co.r_knots().shape[0] == co.N_r + (1 if ith else 3)
         co.set_resolution(co.N_to_reso(64 ** 3, aabb))
         assert co.r0 == 0.05                                       # the reference's set_resolution default (coordinates.py:214)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_reference_checkpoint_kwargs_unpickle_through_the_shim(tmp_path):
+    """A reference checkpoint pickles its coordinates and envmap OBJECTS into `kwargs` (tensorBase.py:241-268); loaded with
+    shim/ on the path they must come back as the drop-in classes, carrying the reference's scalars and ladders."""
+    path = str(tmp_path / "kwargs.th")
+    make = ("import sys, types, torch; sys.dont_write_bytecode = True; sys.path.insert(0, %r);"
+            "from oracle import ref_harness; cd, *_ = ref_harness.import_reference();"
+            "from models.envmap import EnvironmentMap;"
+            "aabb = torch.tensor([[-15.5] * 3, [15.5] * 3]);"
+            "co = cd['yinyang']('cpu', aabb, exp_r=True, N_voxel=40 ** 3, r0=0.03, interval_th=True);"
+            "assert type(co).__module__ == 'models.coordinates';"
+            "torch.save({'kwargs': {'coordinates': co, 'envmap': EnvironmentMap(h=4, init_strategy='zero', device='cpu')}}, %r)"
+            ) % (ROOT, path)
+    run = subprocess.run([sys.executable, "-c", make], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-1500:]
+    load = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "kw = torch.load(%r, map_location='cpu', weights_only=False)['kwargs'];"
+            "from egonerf_b200.models.coordinates import YinYangSphericalCoords; from egonerf_b200.models.envmap import EnvironmentMap;"
+            "from oracle import egn_oracle as O;"
+            "co = kw['coordinates']; assert type(co) is YinYangSphericalCoords, type(co);"
+            "assert type(kw['envmap']) is EnvironmentMap and tuple(kw['envmap'].emission.shape) == (3, 8, 4);"
+            "assert [co.N_r, co.N_theta, co.N_phi] == [20, 22, 64] and co.r0 == 0.03 and co.interval_th;"
+            "aabb = torch.tensor([[-15.5] * 3, [15.5] * 3]);"
+            "assert torch.equal(co.r_knots(), O.r_reference_grid(O.max_corner_radius(aabb), 0.03, 20)); print('ok')"
+            ) % (ROOT, os.path.join(ROOT, "shim"), path)
+    run = subprocess.run([sys.executable, "-c", load], capture_output=True, text=True)
+    assert run.returncode == 0 and "ok" in run.stdout, run.stderr[-1500:]
