@@ -107,3 +107,31 @@ def test_reference_checkpoint_kwargs_unpickle_through_the_shim(tmp_path):
             ) % (ROOT, os.path.join(ROOT, "shim"), path)
     run = subprocess.run([sys.executable, "-c", load], capture_output=True, text=True)
     assert run.returncode == 0 and "ok" in run.stdout, run.stderr[-1500:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_checkpoint_saved_by_the_reference_loads_like_train_py_does(tmp_path):
+    """`model.save` of the UNMODIFIED reference (EgoNeRF.py:158-172), then the load sequence of train.py:155-160 with shim/
+    on the path: torch.load -> kwargs -> EgoNeRF(**kwargs) -> model.load(ckpt).  Parameters, envmap and scalars arrive."""
+    path = str(tmp_path / "ref.th")
+    save = ("import sys, torch; sys.dont_write_bytecode = True; sys.path.insert(0, %r);"
+            "from oracle import ref_harness; ref_harness.import_reference();"
+            "from oracle.make_golden import build_reference; from egonerf_b200.synthetic import make_scene;"
+            "scene = make_scene(n_voxels=40 ** 3, seed=8, envmap_h=16, near_far=(0.1, 300.), r0=0.05, density_shift=-10.);"
+            "co, model = build_reference(scene); assert type(model).__module__ == 'models.EgoNeRF'; model.save(%r, global_step=123)"
+            ) % (ROOT, path)
+    run = subprocess.run([sys.executable, "-c", save], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-1500:]
+    load = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from models.EgoNeRF import EgoNeRF;"
+            "ckpt = torch.load(%r, map_location='cpu', weights_only=False);"
+            "kwargs = ckpt['kwargs']; kwargs.update({'device': 'cpu'});"
+            "model = EgoNeRF(**kwargs); assert model.load(ckpt) == 123 and type(model).__module__ == 'egonerf_b200.models.EgoNeRF';"
+            "from egonerf_b200.synthetic import make_scene;"
+            "scene = make_scene(n_voxels=40 ** 3, seed=8, envmap_h=16, near_far=(0.1, 300.), r0=0.05, density_shift=-10.);"
+            "sd = model.state_dict(); assert all(torch.equal(sd[k], v) for k, v in scene.state_dict.items());"
+            "assert torch.equal(model.envmap.emission.detach(), scene.emission);"
+            "assert model.near_far == [0.1, 300.0] and model.density_shift == -10.0 and model.coordinates.r0 == 0.05;"
+            "assert model.gridSize.tolist() == scene.grid; print('ok')") % (ROOT, os.path.join(ROOT, "shim"), path)
+    run = subprocess.run([sys.executable, "-c", load], capture_output=True, text=True)
+    assert run.returncode == 0 and "ok" in run.stdout, run.stderr[-1500:]
