@@ -135,3 +135,33 @@ def test_checkpoint_saved_by_the_reference_loads_like_train_py_does(tmp_path):
             "assert model.gridSize.tolist() == scene.grid; print('ok')") % (ROOT, os.path.join(ROOT, "shim"), path)
     run = subprocess.run([sys.executable, "-c", load], capture_output=True, text=True)
     assert run.returncode == 0 and "ok" in run.stdout, run.stderr[-1500:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("interval_th", [True, False])
+def test_upsampling_positions_match_the_reference_ladders(interval_th):
+    """Host half of the coarse-to-fine step: the source positions handed to `egn_resample_factor` for the r axis equal the
+    grid_sample coordinates the reference builds in GenericSphericalCoords.up_sampling_VM (coordinates.py:238-250), with and
+    without interval_th; angular axes follow F.interpolate's align_corners rule."""
+    code = ("import sys, torch; sys.dont_write_bytecode = True; sys.path.insert(0, %r);"
+            "from oracle import ref_harness; cd, *_ = ref_harness.import_reference();"
+            "from extra.test_exp_r import index2r;"
+            "aabb = torch.tensor([[-15.5] * 3, [15.5] * 3]); ith = %r;"
+            "co = cd['yinyang']('cpu', aabb, exp_r=True, N_voxel=40 ** 3, r0=0.03, interval_th=ith);"
+            "n = 34; ratio = pow(co.far[0] / co.r0, 1 / (n - 1));"
+            "g = index2r(co.r0, ratio, torch.arange(n));"
+            "iv = g[1:] - g[:-1]; cum = torch.cumsum(iv, 0); k = int((iv <= co.r0).sum());"
+            "gi = g.clone(); gi[:k + 1] = torch.arange(k + 1) * co.r0; gi[k + 1:] = g[k + 1:] + co.r0 * k - cum[k - 1];"
+            "un = torch.zeros(n); un[1:] = co.r0 * torch.pow(ratio, torch.arange(n - 1));"
+            "rs = co.normalize_r(gi if ith else un) * 2 - 1;"
+            "print(' '.join(repr(float(v)) for v in ((rs + 1) / 2) * (co.N_r - 1)))") % (ROOT, interval_th)
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-1500:]
+    ref = torch.tensor([float(v) for v in run.stdout.split()])
+    from egonerf_b200.models.coordinates import YinYangSphericalCoords
+    aabb = torch.tensor([[-15.5] * 3, [15.5] * 3])
+    co = YinYangSphericalCoords("cpu", aabb, exp_r=True, N_voxel=40 ** 3, r0=0.03, interval_th=interval_th)
+    mine = co.up_sampling_positions(0, co.N_r, 34)
+    assert mine.shape == ref.shape and (mine - ref).abs().max() <= 2e-5, (mine - ref).abs().max()
+    ang = co.up_sampling_positions(1, co.N_theta, 37)
+    assert ang[0] == 0 and abs(float(ang[-1]) - (co.N_theta - 1)) < 1e-5 and torch.all(ang[1:] > ang[:-1])
