@@ -165,3 +165,34 @@ def test_upsampling_positions_match_the_reference_ladders(interval_th):
     assert mine.shape == ref.shape and (mine - ref).abs().max() <= 2e-5, (mine - ref).abs().max()
     ang = co.up_sampling_positions(1, co.N_theta, 37)
     assert ang[0] == 0 and abs(float(ang[-1]) - (co.N_theta - 1)) < 1e-5 and torch.all(ang[1:] > ang[:-1])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_regularisers_equal_the_reference_values():
+    """vector_comp_diffs / density_L1 / TV_loss_density / TV_loss_app (EgoNeRF.py:189-230 with TVLoss of
+    utils.py:155-171) are plain torch on the Parameters — same numbers as the unmodified reference on the same state dict."""
+    code = ("import sys, torch; sys.dont_write_bytecode = True; sys.path.insert(0, %r);"
+            "from oracle import ref_harness; ref_harness.import_reference();"
+            "from oracle.make_golden import build_reference; from egonerf_b200.synthetic import make_scene;"
+            "from utils import TVLoss;"
+            "co, m = build_reference(make_scene(n_voxels=40 ** 3, seed=7)); tv = TVLoss();"
+            "print(repr(float(m.vector_comp_diffs())), repr(float(m.density_L1())), repr(float(m.TV_loss_density(tv))),"
+            " repr(float(m.TV_loss_app(tv))))") % ROOT
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-1500:]
+    ref = [float(v) for v in run.stdout.strip().splitlines()[-1].split()]
+    from egonerf_b200.scene_io import model_from_scene
+    from egonerf_b200.synthetic import make_scene
+
+    class TV(torch.nn.Module):                                  # TVLoss, utils.py:155-171 (restated)
+        def forward(self, x):
+            n_h = x[:, :, 1:, :].numel() // x.shape[0]
+            n_w = x[:, :, :, 1:].numel() // x.shape[0]
+            dh = ((x[:, :, 1:, :] - x[:, :, :-1, :]) ** 2).sum()
+            dw = ((x[:, :, :, 1:] - x[:, :, :, :-1]) ** 2).sum()
+            return 2 * (dh / n_h + dw / n_w) / x.shape[0]
+
+    m = model_from_scene(make_scene(n_voxels=40 ** 3, seed=7), "cpu")
+    mine = [float(m.vector_comp_diffs()), float(m.density_L1()), float(m.TV_loss_density(TV())), float(m.TV_loss_app(TV()))]
+    for a, b in zip(mine, ref):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (mine, ref)
