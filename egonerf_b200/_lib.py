@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegn_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -27,6 +27,7 @@ class EgnConfig(C.Structure):
         ("exp_sampling", C.c_int32), ("far_plane", C.c_float), ("step_size", C.c_float), ("aabb", C.c_float * 6), ("bwd_tc", C.c_int32),
         ("plain_ladders", C.c_int32), ("jitter_ratio", C.c_float), ("jitter_r0", C.c_float),
         ("r_knots", C.c_void_p), ("r_knots_coarse", C.c_void_p), ("z_coarse", C.c_void_p), ("tables_bf16", C.c_void_p),
+        ("tables_h", C.c_void_p),
     ]
 
 
@@ -49,7 +50,7 @@ class EgnOutputs(C.Structure):
 
 SHADING = {"MLP_Fea": 0, "MLP": 1, "RGB": 2, "SH": 3}
 ACT = {"softplus": 0, "relu": 1}
-MLP_MODE = {"fp32": 0, "tc_split": 1, "tc_bf16": 2}   # EGN_MLP_* (include/egn.h)
+MLP_MODE = {"fp32": 0, "tc_split": 1, "tc_f16": 2, "tc_bf16": 2}   # EGN_MLP_* (include/egn.h); tc_bf16 = pre-ABI-7 name of tc_f16
 
 # name -> (restype, argtypes); every symbol include/egn.h declares
 PROTOTYPES = {
@@ -60,8 +61,10 @@ PROTOTYPES = {
     "egn_pack_tables": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p]),
     "egn_table_bf16_elems": (C.c_int64, [C.POINTER(EgnConfig)]),
     "egn_pack_tables_bf16": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "egn_table_h_bytes": (C.c_int64, [C.POINTER(EgnConfig)]),
+    "egn_pack_tables_h": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     "egn_adam_tables": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnGrads), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "egn_unpack_table_grads": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.POINTER(EgnGrads), C.c_void_p]),
     "egn_workspace_bytes": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),
     "egn_workspace_bytes_eval": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),

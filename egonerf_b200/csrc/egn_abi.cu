@@ -90,6 +90,11 @@ static EgnKernelCfg make_kcfg(const EgnConfig* c, const float* tables, bool rend
     k.step_size = c->step_size; k.far_plane = c->far_plane;
     for (int i = 0; i < 6; ++i) k.aabb[i] = c->aabb[i];
     k.tables_bf16 = c->tables_bf16;
+    k.tables_h = c->tables_h;
+    const EgnLayoutH LH = egn_make_layout_h(c->grid);
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) { k.texp[h][i] = LH.texp[h][i]; k.texl[h][i] = LH.texl[h][i]; }
+    k.dens_byte_offset = LH.dens_byte_offset;
     return k;
 }
 
@@ -121,9 +126,21 @@ extern "C" int32_t egn_pack_tables_bf16(const EgnConfig* c, const float* tables,
     return e ? cuda_fail("egn_pack_tables_bf16", e) : 0;
 }
 
+extern "C" int64_t egn_table_h_bytes(const EgnConfig* c) {
+    if (validate(c, false)) return -1;
+    return egn_make_layout_h(c->grid).total_bytes;
+}
+
+extern "C" int32_t egn_pack_tables_h(const EgnConfig* c, const float* tables, void* tables_h, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!tables || !tables_h) return fail("null argument");
+    int e = egn_launch_pack_h(c, tables, tables_h, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_pack_tables_h", e) : 0;
+}
+
 extern "C" int32_t egn_adam_tables(const EgnConfig* c, const EgnGrads* params_out, const float* d_tables, float* exp_avg,
-                                   float* exp_avg_sq, float* tables, void* tables_bf16, float lr, float beta1, float beta2,
-                                   float eps, int32_t step, void* stream) {
+                                   float* exp_avg_sq, float* tables, void* tables_bf16, void* tables_h, float lr, float beta1,
+                                   float beta2, float eps, int32_t step, void* stream) {
     if (validate(c, false)) return 1;
     if (!params_out || !d_tables || !exp_avg || !exp_avg_sq || !tables) return fail("null argument");
     if (step < 1) return fail("Adam step counts from 1");
@@ -131,8 +148,8 @@ extern "C" int32_t egn_adam_tables(const EgnConfig* c, const EgnGrads* params_ou
         for (int i = 0; i < 3; ++i)
             if (!params_out->density_plane[h][i] || !params_out->density_line[h][i] || !params_out->app_plane[h][i] ||
                 !params_out->app_line[h][i]) return fail("missing factor tensor h=%d i=%d", h, i);
-    int e = egn_launch_adam_tables(c, params_out, d_tables, exp_avg, exp_avg_sq, tables, tables_bf16, lr, beta1, beta2, eps, step,
-                                   (cudaStream_t)stream);
+    int e = egn_launch_adam_tables(c, params_out, d_tables, exp_avg, exp_avg_sq, tables, tables_bf16, tables_h, lr, beta1, beta2,
+                                   eps, step, (cudaStream_t)stream);
     return e ? cuda_fail("egn_adam_tables", e) : 0;
 }
 
@@ -148,7 +165,10 @@ static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
 #define EGN_BWD_SUB_RAYS 4096
 struct WsPlan { long long z, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, eval_total, total; };
-static bool is_fused(const EgnConfig* c) { return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_BF16; }
+// the fused fine pass keeps the r ladder in shared memory (EGN_FUSED_MAX_KNOTS entries); larger grids take the unfused kernels
+static bool is_fused(const EgnConfig* c) {
+    return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_F16 && c->grid[0] + 3 <= EGN_FUSED_MAX_KNOTS;
+}
 static bool tc_backward(const EgnConfig* c) {
     return c->shading == EGN_SHADE_MLP_FEA && c->view_pe == 2 && c->fea_pe == 2 && (c->mlp_mode == EGN_MLP_TC_BF16 || c->bwd_tc);
 }
@@ -226,7 +246,8 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     if (z_vals && z_vals != z)
         if ((e = (int)cudaMemcpyAsync(z, z_vals, sizeof(float) * n * k.S, cudaMemcpyDeviceToDevice, st))) return cuda_fail("z copy", e);
     mark(se, 1, st);
-    const bool fused = c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_BF16;
+    const bool fused = is_fused(c);
+    if (fused && !c->tables_h) return fail("EGN_MLP_TC_F16 needs EgnConfig.tables_h (egn_pack_tables_h)");
     if (fused) {
         // throughput mode: one warp-specialised kernel for gather + basis + MLP; the app feature is only written
         // when a backward pass will read it (full training workspace)

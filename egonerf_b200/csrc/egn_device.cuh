@@ -10,6 +10,7 @@
 #define EGN_CF (EGN_CS + EGN_CA)   // interleaved channels per texel: one tap = 256 contiguous bytes
 #define EGN_FEAT_STRIDE 28   // app feature row (27 used) padded to a multiple of 16 bytes
 #define EGN_MAX_KNOTS 1024
+#define EGN_FUSED_MAX_KNOTS 512   // r-ladder entries the fused fine pass keeps in shared memory
 #define EGN_HID 128
 
 // matMode [[0,1],[0,2],[1,2]] / vecMode [2,1,0] (EgoNeRF.py:30-33): plane i is indexed x = c[MX[i]] (width),
@@ -48,6 +49,33 @@ static inline EgnLayout egn_make_layout(const int32_t grid[3]) {
     return L;
 }
 
+// "Half" tables of the throughput mode (fused fine pass): every fine texel of the 12 plane / line sections gets ONE global
+// texel index (sections in the order [h][i] plane, line), and two arrays indexed by it:
+//   app  [texel][64] fp16 : the 48 appearance channels + 16 halfs of zero padding = one aligned 128-byte line per tap
+//   dens [texel][16] fp32 : the density channels, exact (alpha stays inside the 1e-4 parity bound)
+// laid out as [app array][dens array] in one buffer.
+#define EGN_APP_TEXEL_HALFS 64
+struct EgnLayoutH {
+    int texp[2][3];       // first global texel of fine plane [h][i]
+    int texl[2][3];       // first global texel of fine line  [h][i]
+    long long n_texels;
+    long long dens_byte_offset;   // = n_texels * 128
+    long long total_bytes;        // = n_texels * (128 + 64)
+};
+static inline EgnLayoutH egn_make_layout_h(const int32_t grid[3]) {
+    EgnLayoutH L;
+    long long t = 0;
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) {
+            L.texp[h][i] = (int)t; t += (long long)grid[egn_my(i)] * grid[egn_mx(i)];
+            L.texl[h][i] = (int)t; t += grid[egn_vl(i)];
+        }
+    L.n_texels = t;
+    L.dens_byte_offset = t * (EGN_APP_TEXEL_HALFS * 2);
+    L.total_bytes = t * (EGN_APP_TEXEL_HALFS * 2 + EGN_CS * 4);
+    return L;
+}
+
 // Everything a render kernel needs, passed by value.
 struct EgnKernelCfg {
     EgnLayout lay;
@@ -68,6 +96,9 @@ struct EgnKernelCfg {
     int march;                // 1: uniform march (TensorBase.sample_ray) instead of the exponential schedule
     float step_size, far_plane, aabb[6];
     const void* tables_bf16;  // optional bf16 copy of the fine tables (same element offsets)
+    const void* tables_h;     // half tables of the fused fine pass (EgnLayoutH), or NULL
+    int texp[2][3], texl[2][3];   // EgnLayoutH section starts (global texel indices)
+    long long dens_byte_offset;
 };
 
 #ifdef __CUDACC__

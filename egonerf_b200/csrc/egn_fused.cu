@@ -1,18 +1,28 @@
-// Fused fine pass (throughput mode, EGN_MLP_TC_BF16): Yin-Yang coordinates -> 18-tap factor gather -> VM products
+// Fused fine pass (throughput mode, EGN_MLP_TC_F16): Yin-Yang coordinates -> 18-tap factor gather -> VM products
 // -> basis contraction -> positional encoding -> 3-layer MLP -> sample colour, in ONE persistent warp-specialised kernel.
 // Replaces egn_gather_kernel + egn_mlp_*_kernel for one ray chunk (EgoNeRF.py:544-556: from_cartesian / normalize_coord,
 // compute_densityfeature, compute_appfeature, renderModule).  One CTA per SM, 512 threads:
 //
-//   warps 8..15  GATHER group   per 128-sample tile: coordinates, taps (fp32 or bf16 tables, 128-bit loads), P*L
-//                               products; the 144 appearance products of a sample go straight into shared memory as a
-//                               bf16 row of the tcgen05 A operand V (canonical K-major layout), sigma feature -> HBM.
+//   warps 8..15  GATHER group   per 128-sample tile, each warp owns 16 rows and runs three phases on them:
+//                  1. ADDRESS   one lane per sample: coordinates (every second tile for two tiles at once, all 32 lanes busy),
+//                               then per-axis texel indices + tap weights -> the 18 global texel indices and 18 fp32 weights
+//                               of the sample go to a 144-byte record in shared memory.  Done ONCE per sample instead of
+//                               once per lane of the sample (the r01 kernel spent half its gather instructions here).
+//                  2. DENSITY   4 lanes per sample, 8 samples per pass: 16 fp32 channels per tap (exact: alpha stays inside the
+//                               parity bound), FFMA interpolation, relu-sum -> sigma feature.
+//                  3. APPEARANCE 8 lanes per sample (6 active), 4 samples per pass: 48 fp16 channels per tap = one aligned
+//                               128-byte line, packed half2 interpolation (HFMA2: two channels per instruction, no unpacking),
+//                               the 144 products P*L go straight into shared memory as an fp16 row of the tcgen05 A operand V.
 //                               V is double buffered: tile i+1 is gathered while tile i runs through the MLP.
 //   warps 0..7   MLP group      feat2 = V [B_yin | B_yang]^T (tcgen05, N = 64; the epilogue picks the sample's
 //                               hemisphere) -> PE -> X -> D1 -> relu -> H1 -> D2 -> relu . W3 -> sigmoid   (as egn_mlp_tc.cu)
 //   thread 0                    issues every tcgen05.mma; completions come back through tcgen05.commit -> mbarrier
 //
+// All MMA operands are FP16 (fp32 accumulate in TMEM): against bf16 the rounding error of every operand is 8x smaller, which
+// brings rgb to ~1e-5 of the exact render (scripts/error_budget.py) at the same bytes and tensor throughput.
 // Nothing of size (samples x features) touches HBM in between: per sample the kernel reads 24 B of ray, 4 B of depth and
 // its taps, and writes 4 B (sigma feature) + 12 B (colour) [+ 112 B app feature when the backward pass will need it].
+#include <cuda_fp16.h>
 #include "egn_tc.cuh"
 #include "egn_host.h"
 #include "egn_shared.cuh"
@@ -21,12 +31,15 @@
 #define FU_GROUP 256
 #define FU_VK (3 * EGN_CA)                   // 144
 #define FU_VCHUNKS (FU_VK / 8)               // 18
-// K-chunk stride of the V operand: 2048 B of data + 64 B of padding.  The 6 appearance lanes of a sample store chunks
-// kc, kc+1, .. of the SAME row; with a 2048 B stride they all fall into one 16-byte bank group (6-way conflict), with
-// 2112 B consecutive chunks alternate between two groups and the 24 lanes of a store spread 3 per group = the minimum.
-#define FU_VCHUNK (TC_CHUNK + 64)
-#define FU_VBYTES (FU_VCHUNKS * FU_VCHUNK)   // 38 016
+// K-chunk stride of the V operand: 2048 B of data + 16 B of padding.  The 6 appearance lanes of a sample store chunks
+// kc, kc+1, .. of the SAME row; with a 2048 B stride they would all fall into one 16-byte bank group (6-way conflict), with
+// 2064 B consecutive chunks land in consecutive bank groups: conflict-free.
+#define FU_VCHUNK (TC_CHUNK + 16)
+#define FU_VBYTES (FU_VCHUNKS * FU_VCHUNK)   // 37 152
 #define FU_BB_CHUNK 1024                     // basis operand: 64 rows x 16 B per K chunk
+#define FU_REC_WORDS 36                      // address record of one sample: 3 x {4 plane texels, 2 line texels, 4 + 2 weights}
+#define FU_IDESC_128x128 0x08200010u         // kind::f16: D fp32, A/B fp16, both K-major, N = 128, M = 128
+#define FU_IDESC_128x64  0x08100010u         // same, N = 64
 
 struct FuLayout {
     static constexpr int W1 = 0;
@@ -34,145 +47,142 @@ struct FuLayout {
     static constexpr int BB = W2 + (EGN_HID / 8) * TC_CHUNK;          // + 32 768
     static constexpr int A = BB + FU_VCHUNKS * FU_BB_CHUNK;           // + 18 432
     static constexpr int V = A + (TC_K1 / 8) * TC_CHUNK;              // + 40 960 ; two buffers
-    static constexpr int YANG = V + 2 * FU_VBYTES;                    // 4 x 128 bytes
+    static constexpr int REC = V + 2 * FU_VBYTES;                     // address records: 128 samples x 144 B
+    static constexpr int YANG = REC + TC_TM * FU_REC_WORDS * 4;       // 4 x 128 bytes
     static constexpr int KNOTS = YANG + 4 * TC_TM;
-    static constexpr int MBAR = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
+    static constexpr int MBAR = KNOTS + ((EGN_FUSED_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
     static constexpr int TMEM = MBAR + 8 * 8;
     static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4
     static constexpr int TOTAL = PART + TC_TM * 16;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
 
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// two floats -> packed fp16 pair (first value in the low half), round to nearest, saturating instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void store_chunk_h(unsigned char* base, int chunk, int row, const float* v) {
+    uint4 h;
+    h.x = pack_h2(v[0], v[1]); h.y = pack_h2(v[2], v[3]); h.z = pack_h2(v[4], v[5]); h.w = pack_h2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(base + chunk * TC_CHUNK + row * 16) = h;
+}
+__device__ __forceinline__ void store_elem_h(unsigned char* base, int row, int kk, float x, int chunk_bytes = TC_CHUNK) {
+    *reinterpret_cast<__half*>(base + (kk >> 3) * chunk_bytes + row * 16 + (kk & 7) * 2) = __float2half_rn(x);
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
-// one lane's share of a tap is kept as loaded (4 registers): 8 bf16 channels or 4 fp32 channels
-template <bool BF16>
-__device__ __forceinline__ float tap_val(const uint4& q, int ch) {
-    if constexpr (BF16) {
-        const uint32_t w = (ch >> 1) == 0 ? q.x : (ch >> 1) == 1 ? q.y : (ch >> 1) == 2 ? q.z : q.w;
-        return (ch & 1) ? bf_hi(w) : bf_lo(w);
-    } else {
-        return __uint_as_float(ch == 0 ? q.x : ch == 1 ? q.y : ch == 2 ? q.z : q.w);
+// ---------------------------------------------------------------------------------------------------------------
+// GATHER group, phase 1: address record of the sample with index-space coordinate `cc` (EgoNeRF.py:291-347 / 349-413 tap
+// geometry, F.grid_sample bilinear / zeros / align_corners=True).  Out-of-range taps get weight 0 and a clamped in-range
+// texel, so every later load is unconditional.  Record layout per factor pair i (12 words):
+//   [t00 t01 t10 t11] [l0 l1 w00 w01] [w10 w11 u0 u1]     t*, l*: global texel indices (EgnLayoutH); w*, u*: fp32 weights
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fused_address_record(const EgnKernelCfg& k, const YYCoord& cc, uint4* __restrict__ rec) {
+    unsigned j0[3], j1[3];
+    float wa0[3], wa1[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int G = k.lay.G[a];
+        const float ix = egn_unnorm(cc.c[a], G);
+        const float fl = floorf(ix);
+        const float fr = ix - fl;
+        const int i0 = (int)fminf(fmaxf(fl, -2.f), (float)G + 1.f);
+        wa0[a] = ((i0 >= 0) & (i0 < G)) ? 1.f - fr : 0.f;
+        wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G)) ? fr : 0.f;
+        j0[a] = (unsigned)min(max(i0, 0), G - 1);
+        j1[a] = (unsigned)min(max(i0 + 1, 0), G - 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+        const unsigned W = (unsigned)k.lay.G[ax];
+        const unsigned pb = (unsigned)k.texp[cc.yang][i], lb = (unsigned)k.texl[cc.yang][i];
+        const unsigned ra = pb + j0[ay] * W, rb = pb + j1[ay] * W;
+        rec[3 * i] = make_uint4(ra + j0[ax], ra + j1[ax], rb + j0[ax], rb + j1[ax]);
+        rec[3 * i + 1] = make_uint4(lb + j0[al], lb + j1[al], __float_as_uint(wa0[ax] * wa0[ay]), __float_as_uint(wa1[ax] * wa0[ay]));
+        rec[3 * i + 2] = make_uint4(__float_as_uint(wa0[ax] * wa1[ay]), __float_as_uint(wa1[ax] * wa1[ay]),
+                                    __float_as_uint(wa0[al]), __float_as_uint(wa1[al]));
+    }
+}
+
+// phase 2: density of 8 samples (rows r8 .. r8+7 of the warp's records), 4 lanes x 4 fp32 channels per sample.
+// All 18 taps are requested before the first use: one L2 round trip per pass (the shared memory of this kernel leaves no L1).
+__device__ __forceinline__ float fused_density_pass(const float4* __restrict__ dens, const uint4* __restrict__ recs, int r8, int lane) {
+    const unsigned sub = lane & 3;
+    const uint4* rec = recs + (r8 + (lane >> 2)) * (FU_REC_WORDS / 4);
+    float4 t[3][6];
+    uint4 wq[3][2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint4 a = rec[3 * i], b = rec[3 * i + 1];
+        wq[i][1] = rec[3 * i + 2];
+        wq[i][0] = b;
+        t[i][0] = __ldg(dens + (a.x * 4u + sub)); t[i][1] = __ldg(dens + (a.y * 4u + sub));
+        t[i][2] = __ldg(dens + (a.z * 4u + sub)); t[i][3] = __ldg(dens + (a.w * 4u + sub));
+        t[i][4] = __ldg(dens + (b.x * 4u + sub)); t[i][5] = __ldg(dens + (b.y * 4u + sub));
+    }
+    float f = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float w0 = __uint_as_float(wq[i][0].z), w1 = __uint_as_float(wq[i][0].w);
+        const float w2 = __uint_as_float(wq[i][1].x), w3 = __uint_as_float(wq[i][1].y);
+        const float u0 = __uint_as_float(wq[i][1].z), u1 = __uint_as_float(wq[i][1].w);
+        float4 P = make_float4(w0 * t[i][0].x, w0 * t[i][0].y, w0 * t[i][0].z, w0 * t[i][0].w);
+        P = f4fma(w1, t[i][1], P); P = f4fma(w2, t[i][2], P); P = f4fma(w3, t[i][3], P);
+        float4 Lv = make_float4(u0 * t[i][4].x, u0 * t[i][4].y, u0 * t[i][4].z, u0 * t[i][4].w);
+        Lv = f4fma(u1, t[i][5], Lv);
+        float s = fmaf(P.w, Lv.w, fmaf(P.z, Lv.z, fmaf(P.y, Lv.y, P.x * Lv.x)));
+        s += __shfl_xor_sync(FULL, s, 1);
+        s += __shfl_xor_sync(FULL, s, 2);
+        f += fmaxf(s, 0.f);                                   // relu per factor pair (EgoNeRF.py:346)
+    }
+    return f;                                                 // all four lanes of the sample hold it
+}
+
+// phase 3: appearance products of 4 samples (rows r4 .. r4+3), lanes 0..5 of each quarter-warp x 8 fp16 channels; all 18 taps
+// in flight before the first use
+__device__ __forceinline__ void fused_app_pass(const uint4* __restrict__ app, const uint4* __restrict__ recs, int r4, int row0,
+                                               int lane, unsigned char* __restrict__ vbuf) {
+    const unsigned q = lane & 7;
+    if (q >= 6) return;                                       // the 128-byte texel line holds 96 bytes of channels
+    const int rl = r4 + (lane >> 3);
+    const uint4* rec = recs + rl * (FU_REC_WORDS / 4);
+    unsigned char* vrow = vbuf + (row0 + rl) * 16 + q * FU_VCHUNK;
+    uint4 t[3][6];
+    uint4 wq[3][2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint4 a = rec[3 * i], b = rec[3 * i + 1];
+        wq[i][1] = rec[3 * i + 2];
+        wq[i][0] = b;
+        t[i][0] = __ldg(app + (a.x * 8u + q)); t[i][1] = __ldg(app + (a.y * 8u + q));
+        t[i][2] = __ldg(app + (a.z * 8u + q)); t[i][3] = __ldg(app + (a.w * 8u + q));
+        t[i][4] = __ldg(app + (b.x * 8u + q)); t[i][5] = __ldg(app + (b.y * 8u + q));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const __half2 w0 = as_h2(pack_h2(__uint_as_float(wq[i][0].z), __uint_as_float(wq[i][0].z)));
+        const __half2 w1 = as_h2(pack_h2(__uint_as_float(wq[i][0].w), __uint_as_float(wq[i][0].w)));
+        const __half2 w2 = as_h2(pack_h2(__uint_as_float(wq[i][1].x), __uint_as_float(wq[i][1].x)));
+        const __half2 w3 = as_h2(pack_h2(__uint_as_float(wq[i][1].y), __uint_as_float(wq[i][1].y)));
+        const __half2 u0 = as_h2(pack_h2(__uint_as_float(wq[i][1].z), __uint_as_float(wq[i][1].z)));
+        const __half2 u1 = as_h2(pack_h2(__uint_as_float(wq[i][1].w), __uint_as_float(wq[i][1].w)));
+        uint4 o;
+#define FU_PL(m) { __half2 P = __hmul2(w0, as_h2(t[i][0].m)); P = __hfma2(w1, as_h2(t[i][1].m), P); P = __hfma2(w2, as_h2(t[i][2].m), P); \
+                   P = __hfma2(w3, as_h2(t[i][3].m), P); const __half2 Lv = __hfma2(u1, as_h2(t[i][5].m), __hmul2(u0, as_h2(t[i][4].m))); \
+                   o.m = as_u32(__hmul2(P, Lv)); }
+        FU_PL(x) FU_PL(y) FU_PL(z) FU_PL(w)
+#undef FU_PL
+        *reinterpret_cast<uint4*>(vrow + i * (EGN_CA / 8) * FU_VCHUNK) = o;     // K index i*48 + q*8 .. +7
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GATHER group: the warp's 16 samples (rows row0 .. row0+15 of the tile) -> V rows + sigma features + hemisphere flags
-// ---------------------------------------------------------------------------------------------------------------
-template <bool BF16>
-__device__ __forceinline__ void fused_gather_rows(const EgnKernelCfg& k, const void* __restrict__ tab, const float* __restrict__ knots,
-                                                  const float* __restrict__ rays, const float* __restrict__ zs, long long M,
-                                                  long long m_base, int row0, int lane, unsigned char* vbuf,
-                                                  unsigned char* yang_out, float* __restrict__ fsig) {
-    constexpr int NCH = BF16 ? 8 : 4;              // channels per lane
-    constexpr int LPS = EGN_CF / NCH;              // lanes per sample: 8 / 16
-    constexpr int SPI = 32 / LPS;                  // samples per iteration: 4 / 2
-    constexpr int DL = EGN_CS / NCH;               // density lanes per sample: 2 / 4
-    // ---- coordinates of sample (lane & 15) ----
-    const long long m = m_base + row0 + (lane & 15);
-    YYCoord cc;
-    cc.c[0] = cc.c[1] = cc.c[2] = -3.f;            // out of range -> every tap reads zero
-    cc.yang = 0;
-    if (m < M) {
-        const long long ray = m / k.S;
-        const float z = zs[m];
-        const float* ry = rays + ray * 6;
-        cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, knots);
-    }
-    if (lane < 16) yang_out[row0 + lane] = (unsigned char)cc.yang;
-    const int sub = lane % LPS;
-    float myf = 0.f;
-#pragma unroll 1
-    for (int it = 0; it < 16 / SPI; ++it) {
-        const int src = SPI * it + lane / LPS;
-        float c[3];
-        c[0] = __shfl_sync(FULL, cc.c[0], src);
-        c[1] = __shfl_sync(FULL, cc.c[1], src);
-        c[2] = __shfl_sync(FULL, cc.c[2], src);
-        const int yang = __shfl_sync(FULL, cc.yang, src);
-        // per axis: clamped texel indices and tap weights with the zero padding of F.grid_sample folded in — an
-        // out-of-range tap gets weight 0 and reads a clamped in-range texel, so every load is unconditional
-        unsigned j0[3], j1[3];
-        float wa0[3], wa1[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int G = k.lay.G[a];
-            const float ix = egn_unnorm(c[a], G);
-            const float fl = floorf(ix);
-            const float fr = ix - fl;
-            const int i0 = (int)fminf(fmaxf(fl, -2.f), (float)G + 1.f);
-            wa0[a] = ((i0 >= 0) & (i0 < G)) ? 1.f - fr : 0.f;
-            wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G)) ? fr : 0.f;
-            j0[a] = (unsigned)min(max(i0, 0), G - 1);
-            j1[a] = (unsigned)min(max(i0 + 1, 0), G - 1);
-        }
-        constexpr unsigned ES = BF16 ? 2u : 4u;                 // bytes per table element
-        const char* tabc = reinterpret_cast<const char*>(tab);
-        uint4 t[3][4], l[3][2];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
-            const unsigned W = (unsigned)k.lay.G[ax];
-            const unsigned pbase = (unsigned)k.lay.pf[yang][i] + sub * NCH, lbase = (unsigned)k.lay.lf[yang][i] + sub * NCH;
-            const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
-            t[i][0] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (ra + j0[ax]) * EGN_CF) * ES));
-            t[i][1] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (ra + j1[ax]) * EGN_CF) * ES));
-            t[i][2] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (rb + j0[ax]) * EGN_CF) * ES));
-            t[i][3] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(pbase + (rb + j1[ax]) * EGN_CF) * ES));
-            l[i][0] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(lbase + j0[al] * EGN_CF) * ES));
-            l[i][1] = __ldg(reinterpret_cast<const uint4*>(tabc + (size_t)(lbase + j1[al] * EGN_CF) * ES));
-        }
-        float f = 0.f;
-        const int row = row0 + src;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
-            const float w0 = wa0[ax] * wa0[ay], w1 = wa1[ax] * wa0[ay], w2 = wa0[ax] * wa1[ay], w3 = wa1[ax] * wa1[ay];
-            const float u0 = wa0[al], u1 = wa1[al];
-            float prod[NCH];
-            float s = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                float P = w0 * tap_val<BF16>(t[i][0], ch);
-                P = fmaf(w1, tap_val<BF16>(t[i][1], ch), P);
-                P = fmaf(w2, tap_val<BF16>(t[i][2], ch), P);
-                P = fmaf(w3, tap_val<BF16>(t[i][3], ch), P);
-                const float Lv = fmaf(u1, tap_val<BF16>(l[i][1], ch), u0 * tap_val<BF16>(l[i][0], ch));
-                prod[ch] = P * Lv;
-                s += prod[ch];
-            }
-            // density: sum over the 16 density channels = DL lanes, then relu (EgoNeRF.py:346)
-#pragma unroll
-            for (int d = 1; d < DL; d <<= 1) s += __shfl_xor_sync(FULL, s, d);
-            f += fmaxf(s, 0.f);
-            if (sub >= DL) {                                   // appearance lanes: bf16 row of the A operand
-                const int kk = i * EGN_CA + (sub - DL) * NCH;  // first K index of this lane's products
-                unsigned char* dst = vbuf + (kk >> 3) * FU_VCHUNK + row * 16 + (kk & 7) * 2;
-                if constexpr (BF16) {
-                    uint4 q;
-                    q.x = pack_hi(prod[0], prod[1]); q.y = pack_hi(prod[2], prod[3]);
-                    q.z = pack_hi(prod[4], prod[5]); q.w = pack_hi(prod[6], prod[7]);
-                    *reinterpret_cast<uint4*>(dst) = q;
-                } else {
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi(prod[0], prod[1]), pack_hi(prod[2], prod[3]));
-                }
-            }
-        }
-        // the density lanes of sample `src` all hold f; hand it to the lane that owns the sample's coordinate slot
-#pragma unroll
-        for (int q = 0; q < SPI; ++q) {
-            const float fq2 = __shfl_sync(FULL, f, q * LPS);
-            if ((lane & 15) == SPI * it + q) myf = fq2;
-        }
-    }
-    if (lane < 16 && m < M) fsig[m] = myf;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-template <bool BF16>
 __global__ void __launch_bounds__(FU_THREADS, 1)
-egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __restrict__ tab, const float* __restrict__ basis0,
+egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
                       const float* __restrict__ basis1, const float* __restrict__ w1, const float* __restrict__ b1,
                       const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                       const float* __restrict__ b3, const float* __restrict__ rays, long long M,
@@ -209,13 +219,13 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
     for (int i = tid; i < EGN_HID * TC_K1; i += FU_THREADS) {
         const int n = i / TC_K1, kk = i % TC_K1;
         const int src = tc_input_index(kk, AD);
-        store_elem(w1s, nullptr, false, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
+        store_elem_h(w1s, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
     }
-    for (int i = tid; i < EGN_HID * EGN_HID; i += FU_THREADS) store_elem(w2s, nullptr, false, i / EGN_HID, i % EGN_HID, w2[i]);
+    for (int i = tid; i < EGN_HID * EGN_HID; i += FU_THREADS) store_elem_h(w2s, i / EGN_HID, i % EGN_HID, w2[i]);
     for (int i = tid; i < 64 * FU_VK; i += FU_THREADS) {            // rows 0..31: basis_mat_yin, 32..63: basis_mat_yang
         const int n = i / FU_VK, kk = i % FU_VK, o = n & 31;
         const float* B = (n >> 5) ? basis1 : basis0;
-        store_elem(bbs, nullptr, false, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
+        store_elem_h(bbs, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
     }
     for (int i = tid; i <= k.knots_last; i += FU_THREADS) s_knots[i] = k.r_knots[i];
     fence_async_smem();
@@ -228,13 +238,51 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
 
     if (warp >= 8) {
         // =========================== GATHER group ===========================
-        const int gwarp = warp - 8;
+        const int gwarp = warp - 8, row0 = 16 * gwarp;
+        uint4* recs = reinterpret_cast<uint4*>(smem + L::REC) + row0 * (FU_REC_WORDS / 4);
+        const uint4* app = reinterpret_cast<const uint4*>(k.tables_h);
+        const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
+        YYCoord held;                                                // coordinates computed one tile ahead (lanes 16..31)
+        held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const uint32_t b = it & 1, u = it >> 1;
+            // ---- phase 1a: coordinates.  Even iterations: lanes 0..15 take this tile's rows, lanes 16..31 the same rows of
+            // the CTA's next tile (kept in `held`); odd iterations just fetch them ----
+            YYCoord cc;
+            if (b == 0) {
+                const long long m = (lane < 16 ? tile : tile + gridDim.x) * TC_TM + row0 + (lane & 15);
+                cc.c[0] = cc.c[1] = cc.c[2] = -3.f;                  // out of range -> every tap gets weight zero
+                cc.yang = 0;
+                if (m < M) {
+                    const float z = zs[m];
+                    const float* ry = rays + (m / k.S) * 6;
+                    cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+                }
+                held = cc;
+            } else {
+                cc.c[0] = __shfl_sync(FULL, held.c[0], (lane & 15) + 16);
+                cc.c[1] = __shfl_sync(FULL, held.c[1], (lane & 15) + 16);
+                cc.c[2] = __shfl_sync(FULL, held.c[2], (lane & 15) + 16);
+                cc.yang = __shfl_sync(FULL, held.yang, (lane & 15) + 16);
+            }
+            // ---- phase 1b: address records of the warp's 16 rows ----
+            if (lane < 16) {
+                fused_address_record(k, cc, recs + lane * (FU_REC_WORDS / 4));
+                s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
+            }
+            __syncwarp();
+            // ---- phase 2: density (fp32), 2 passes x 8 samples ----
+#pragma unroll 1
+            for (int p = 0; p < 2; ++p) {
+                const float f = fused_density_pass(dens, recs, 8 * p, lane);
+                const long long m = tile * TC_TM + row0 + 8 * p + (lane >> 2);
+                if ((lane & 3) == 0 && m < M) fsig[m] = f;
+            }
+            // ---- phase 3: appearance (fp16) into the V operand, 4 passes x 4 samples ----
             ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);          // layer-0 MMAs of the tile that used this buffer are done
-            fused_gather_rows<BF16>(k, tab, s_knots, rays, zs, M, tile * TC_TM, 16 * gwarp, lane, vs + b * FU_VBYTES,
-                                    s_yang + (it & 3) * TC_TM, fsig);
+#pragma unroll 1
+            for (int p = 0; p < 4; ++p) fused_app_pass(app, recs, 4 * p, row0, lane, vs + b * FU_VBYTES);
             fence_async_smem();                                      // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(v_full0 + 8 * b);
@@ -255,7 +303,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
 #pragma unroll
             for (int ks = 0; ks < FU_VK / 16; ++ks)
                 tc_mma(tmem + 256, tc_desc(v_s + bb * FU_VBYTES + ks * 2 * FU_VCHUNK, FU_VCHUNK),
-                       tc_desc(bb_s + ks * 2 * FU_BB_CHUNK, FU_BB_CHUNK), TC_IDESC_128x64, ks > 0);
+                       tc_desc(bb_s + ks * 2 * FU_BB_CHUNK, FU_BB_CHUNK), FU_IDESC_128x64, ks > 0);
             tc_commit(v_empty0 + 8 * bb);
             tc_commit(feat_full);
         };
@@ -332,7 +380,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
                         v[5 * j + 3] = 2.f * s1 * c1; v[5 * j + 4] = 1.f - 2.f * s1 * s1;   // W1's padding columns are zero
                     }
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) store_chunk<false>(as, nullptr, 10 * half + 5 * pass + c, row, v + 8 * c);
+                    for (int c = 0; c < 5; ++c) store_chunk_h(as, 10 * half + 5 * pass + c, row, v + 8 * c);
                 }
             }
             fence_async_smem();
@@ -343,7 +391,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < TC_K1 / 16; ++ks)
-                    tc_mma(tmem, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w1_s + ks * 2 * TC_CHUNK), TC_IDESC_128x128, ks > 0);
+                    tc_mma(tmem, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w1_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
                 tc_commit(d1_full);
             }
             if (it > 0) layer3(gm_prev);
@@ -359,7 +407,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]), 0.f);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_chunk<false>(as, nullptr, (col >> 3) + c, row, v + 8 * c);
+                for (int c = 0; c < 4; ++c) store_chunk_h(as, (col >> 3) + c, row, v + 8 * c);
             }
             fence_async_smem();
             tc_fence_before();
@@ -369,7 +417,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const void* __rest
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < EGN_HID / 16; ++ks)
-                    tc_mma(tmem + 128, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w2_s + ks * 2 * TC_CHUNK), TC_IDESC_128x128, ks > 0);
+                    tc_mma(tmem + 128, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w2_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
                 tc_commit(d2_full);
                 if (tile + gridDim.x < tiles) issue_layer0(it + 1);
             }
@@ -390,16 +438,9 @@ int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float
     const long long M = n * k.S;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     const int blocks = (int)(tiles < 148 ? tiles : 148);
-    if (k.tables_bf16 != nullptr) {
-        cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
-        egn_fused_fine_kernel<true><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
-            k, k.tables_bf16, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2],
-            p->mlp_b[2], rays, M, z, fsig, feat_out, rgbs);
-    } else {
-        cudaFuncSetAttribute(egn_fused_fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
-        egn_fused_fine_kernel<false><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
-            k, k.tables, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2],
-            p->mlp_b[2], rays, M, z, fsig, feat_out, rgbs);
-    }
+    cudaFuncSetAttribute(egn_fused_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
+    egn_fused_fine_kernel<<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
+        k, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, z,
+        fsig, feat_out, rgbs);
     return (int)cudaGetLastError();
 }

@@ -30,8 +30,9 @@ int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* ra
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                           float* fsig, float* feat_out, float* rgbs, cudaStream_t st);
 int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables, float* m, float* v,
-                           float* tables, void* tables_bf16, float lr, float beta1, float beta2, float eps, int step,
-                           cudaStream_t st);
+                           float* tables, void* tables_bf16, void* tables_h, float lr, float beta1, float beta2, float eps,
+                           int step, cudaStream_t st);
+int egn_launch_pack_h(const EgnConfig* cfg, const float* tables, void* tables_h, cudaStream_t st);
 int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st);
 int egn_launch_resample_factor(const float* src, int C, int H, int W, const float* ypos, int H2, const float* xpos, int W2,
                                float* dst, cudaStream_t st);

@@ -3,6 +3,7 @@
 // models/EgoNeRF.py:124-133), and the inverse scatter of table gradients back to NCHW.
 #include "egn_device.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include "egn_host.h"
 
@@ -12,6 +13,7 @@ struct PackJob {
     float* dst_d;         // unpack: destination grads
     float* dst_a;
     long long off;        // section offset in the table buffer
+    int tex0;             // first global texel of the section in the half tables (EgnLayoutH); fine sections only
     int H, W;             // source extents (W = 1 for lines)
     int type;             // 0 fine plane/line (interleave), 1 coarse plane (2x2 mean), 2 coarse line (2 mean)
 };
@@ -80,18 +82,19 @@ __global__ void __launch_bounds__(256) egn_unpack_kernel(const __grid_constant__
 
 static int fill_jobs(const EgnConfig* cfg, const EgnParams* p, const EgnGrads* g, PackJobs& jobs, bool with_coarse) {
     EgnLayout L = egn_make_layout(cfg->grid);
+    EgnLayoutH LH = egn_make_layout_h(cfg->grid);
     int n = 0;
     for (int h = 0; h < 2; ++h)
         for (int i = 0; i < 3; ++i) {
             PackJob a{};   // fine plane
             a.src_d = p ? p->density_plane[h][i] : nullptr; a.src_a = p ? p->app_plane[h][i] : nullptr;
             a.dst_d = g ? g->density_plane[h][i] : nullptr; a.dst_a = g ? g->app_plane[h][i] : nullptr;
-            a.off = L.pf[h][i]; a.H = L.G[egn_my(i)]; a.W = L.G[egn_mx(i)]; a.type = 0;
+            a.off = L.pf[h][i]; a.H = L.G[egn_my(i)]; a.W = L.G[egn_mx(i)]; a.type = 0; a.tex0 = LH.texp[h][i];
             jobs.j[n++] = a;
             PackJob b{};   // fine line
             b.src_d = p ? p->density_line[h][i] : nullptr; b.src_a = p ? p->app_line[h][i] : nullptr;
             b.dst_d = g ? g->density_line[h][i] : nullptr; b.dst_a = g ? g->app_line[h][i] : nullptr;
-            b.off = L.lf[h][i]; b.H = L.G[egn_vl(i)]; b.W = 1; b.type = 0;
+            b.off = L.lf[h][i]; b.H = L.G[egn_vl(i)]; b.W = 1; b.type = 0; b.tex0 = LH.texl[h][i];
             jobs.j[n++] = b;
             if (with_coarse) {
                 PackJob c = a; c.off = L.pc[h][i]; c.type = 1; jobs.j[n++] = c;
@@ -132,18 +135,54 @@ int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables
     return (int)cudaGetLastError();
 }
 
+// half tables of the fused fine pass (EgnLayoutH): thread = one float4 channel group of one fine texel of the fp32 tables;
+// density groups are copied as fp32, appearance groups converted to fp16 (round-to-nearest, saturating), and the 32 bytes of
+// padding behind the 48 appearance halfs are zeroed.
+__device__ __forceinline__ uint32_t egn_pack_h2(float a, float b) {             // a in the low half
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void egn_store_h_group(unsigned char* __restrict__ tab_h, long long dens_off, long long tex, int cg,
+                                                  float4 v) {
+    if (cg < EGN_CS / 4) {
+        reinterpret_cast<float4*>(tab_h + dens_off)[tex * (EGN_CS / 4) + cg] = v;
+    } else {
+        uint2* dst = reinterpret_cast<uint2*>(tab_h + tex * (EGN_APP_TEXEL_HALFS * 2)) + (cg - EGN_CS / 4);
+        *dst = make_uint2(egn_pack_h2(v.x, v.y), egn_pack_h2(v.z, v.w));
+        if (cg >= EGN_CF / 4 - 4) dst[4] = make_uint2(0u, 0u);               // the last four groups also clear the padding
+    }
+}
+__global__ void __launch_bounds__(256) egn_pack_h_kernel(const __grid_constant__ PackJobs jobs, const float* __restrict__ tables,
+                                                         unsigned char* __restrict__ tab_h, long long dens_off) {
+    const PackJob& J = jobs.j[blockIdx.y];
+    const long long n = (long long)J.H * J.W * (EGN_CF / 4);
+    const float4* src = reinterpret_cast<const float4*>(tables + J.off);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        egn_store_h_group(tab_h, dens_off, J.tex0 + t / (EGN_CF / 4), (int)(t % (EGN_CF / 4)), src[t]);
+}
+int egn_launch_pack_h(const EgnConfig* cfg, const float* tables, void* tables_h, cudaStream_t st) {
+    PackJobs jobs{};
+    const int n = fill_jobs(cfg, nullptr, nullptr, jobs, false);
+    const EgnLayoutH LH = egn_make_layout_h(cfg->grid);
+    dim3 grid(148 * 2, n);
+    egn_pack_h_kernel<<<grid, 256, 0, st>>>(jobs, tables, reinterpret_cast<unsigned char*>(tables_h), LH.dens_byte_offset);
+    return (int)cudaGetLastError();
+}
+
 // =================================================================================================
 // Adam step of the factor tensors in render-table space (optimiser of train.py:172-186 = torch.optim.Adam
 // without weight decay / amsgrad).  One pass reads the table-layout gradient egn_render_backward produced (no unpack), the
 // moments (kept in table layout) and the current value (the fp32 table IS the parameter, texel-interleaved), and writes
-// moments, the fp32 table, its bf16 copy and — through a shared-memory transpose, coalesced along texels — the NCHW
+// moments, the fp32 table, its bf16 copy, the half tables of the fused fine pass and — through a shared-memory transpose, coalesced along texels — the NCHW
 // parameter tensors.  Replaces egn_unpack_kernel + the framework's Adam + egn_pack_kernel (fine) + egn_pack_bf16_kernel.
 // =================================================================================================
 struct AdamHp { float lr, beta1, beta2, eps, bc1, bc2_sqrt; };
 
 __global__ void __launch_bounds__(256)
 egn_adam_tables_kernel(const __grid_constant__ PackJobs jobs, const float* __restrict__ d_tab, float* __restrict__ m_tab,
-                       float* __restrict__ v_tab, float* __restrict__ tab, __nv_bfloat162* __restrict__ tab16, AdamHp hp) {
+                       float* __restrict__ v_tab, float* __restrict__ tab, __nv_bfloat162* __restrict__ tab16,
+                       unsigned char* __restrict__ tab_h, long long dens_off, AdamHp hp) {
     __shared__ float tile[EGN_CF][33];
     const PackJob& J = jobs.j[blockIdx.y];
     const long long HW = (long long)J.H * J.W;
@@ -177,6 +216,7 @@ egn_adam_tables_kernel(const __grid_constant__ PackJobs jobs, const float* __res
                     tab16[2 * e4] = __floats2bfloat162_rn(pp[0], pp[1]);
                     tab16[2 * e4 + 1] = __floats2bfloat162_rn(pp[2], pp[3]);
                 }
+                if (tab_h) egn_store_h_group(tab_h, dens_off, J.tex0 + tex0 + tx, cg, make_float4(pp[0], pp[1], pp[2], pp[3]));
             }
         }
         __syncthreads();
@@ -195,8 +235,8 @@ egn_adam_tables_kernel(const __grid_constant__ PackJobs jobs, const float* __res
 }
 
 int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables, float* m, float* v,
-                           float* tables, void* tables_bf16, float lr, float beta1, float beta2, float eps, int step,
-                           cudaStream_t st) {
+                           float* tables, void* tables_bf16, void* tables_h, float lr, float beta1, float beta2, float eps,
+                           int step, cudaStream_t st) {
     PackJobs jobs{};
     const int n = fill_jobs(cfg, nullptr, params_out, jobs, false);
     AdamHp hp;
@@ -204,7 +244,9 @@ int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, con
     hp.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     hp.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     dim3 grid(148, n);
-    egn_adam_tables_kernel<<<grid, 256, 0, st>>>(jobs, d_tables, m, v, tables, reinterpret_cast<__nv_bfloat162*>(tables_bf16), hp);
+    egn_adam_tables_kernel<<<grid, 256, 0, st>>>(jobs, d_tables, m, v, tables, reinterpret_cast<__nv_bfloat162*>(tables_bf16),
+                                                 reinterpret_cast<unsigned char*>(tables_h),
+                                                 egn_make_layout_h(cfg->grid).dens_byte_offset, hp);
     int e = (int)cudaGetLastError();
     if (e) return e;
     // pooled coarse tables from the updated density parameters (EgoNeRF.update_coarse_sigma_grid, EgoNeRF.py:124-133)

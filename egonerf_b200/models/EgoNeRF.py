@@ -179,13 +179,16 @@ class EgoNeRF(torch.nn.Module):
         self._sched = {}
         self._cfg_static = None
         # arithmetic of the colour-decode MLP inside libegn_b200: "fp32" (exact FFMA), "tc_split" (tcgen05, 3-term bf16
-        # split: fp32-equivalent) or "tc_bf16" (tcgen05, plain bf16).  Not a reference kwarg: set the attribute.
+        # split: fp32-equivalent) or "tc_f16" (throughput mode: one fused tcgen05 kernel, fp16 operands + fp32 density;
+        # "tc_bf16" is its pre-ABI-7 name).  Not a reference kwarg: set the attribute.
         self.mlp_mode = os.environ.get("EGN_MLP_MODE", "tc_split")
-        # "bf16": the fused fine pass of mlp_mode "tc_bf16" gathers from a bf16 copy of the render tables (half the bytes)
+        # "bf16": the tcgen05 BACKWARD kernels re-gather from a bf16 copy of the render tables (half the bytes); the
+        # throughput-mode forward always reads the half tables (`_tables_h`: fp16 appearance + fp32 density)
         self.table_dtype = os.environ.get("EGN_TABLE_DTYPE", "f32")
         # True: backward on the tcgen05 kernels (bf16 operands) even when the forward runs in a parity mode
         self.tc_backward = os.environ.get("EGN_TC_BACKWARD", "0") == "1"
         self._tables_bf16 = None
+        self._tables_h = None
 
     # ---- parameters (EgoNeRF.py:96-122) -------------------------------------------------------------
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
@@ -356,13 +359,22 @@ class EgoNeRF(torch.nn.Module):
             _lib.check(lib.egn_pack_tables(cfg, self._params_struct(), self._tables.data_ptr(), _stream()))
             self._tables_key = key
             self._tables_bf16 = None
-        if self.table_dtype == "bf16" and self.mlp_mode == "tc_bf16" and self._tables_bf16 is None:
+            self._tables_h = None
+        if self._fused_mode() and getattr(self, "_tables_h", None) is None:
+            lib = _lib.load()
+            cfg = self._config(None)
+            self._tables_h = torch.empty(int(lib.egn_table_h_bytes(cfg)), device=fp[0].device, dtype=torch.uint8)
+            _lib.check(lib.egn_pack_tables_h(cfg, self._tables.data_ptr(), self._tables_h.data_ptr(), _stream()))
+        if self.table_dtype in ("bf16", "f16") and self._fused_mode() and self._tables_bf16 is None:
             lib = _lib.load()
             cfg = self._config(None)
             ne = int(lib.egn_table_bf16_elems(cfg))
             self._tables_bf16 = torch.empty(ne, device=fp[0].device, dtype=torch.bfloat16)
             _lib.check(lib.egn_pack_tables_bf16(cfg, self._tables.data_ptr(), self._tables_bf16.data_ptr(), _stream()))
         return self._tables
+
+    def _fused_mode(self):
+        return self.mlp_mode in ("tc_f16", "tc_bf16")
 
     def _static_config(self):
         """Scalars that never change after construction, read back from the device ONCE (a `.cpu()` per forward would be
@@ -398,8 +410,10 @@ class EgoNeRF(torch.nn.Module):
         tc_ok = self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
         cfg.mlp_mode = _lib.MLP_MODE[self.mlp_mode] if tc_ok else 0
         cfg.bwd_tc = int(bool(self.tc_backward) and tc_ok)
-        use_bf16 = self.table_dtype == "bf16" and self.mlp_mode == "tc_bf16" and self._tables_bf16 is not None
+        use_bf16 = self.table_dtype in ("bf16", "f16") and self._fused_mode() and self._tables_bf16 is not None
         cfg.tables_bf16 = self._tables_bf16.data_ptr() if use_bf16 else None
+        use_h = self._fused_mode() and tc_ok and getattr(self, "_tables_h", None) is not None
+        cfg.tables_h = self._tables_h.data_ptr() if use_h else None
         cfg.env_h = self.envmap.emission.shape[2] if self.envmap is not None else 0
         cfg.center[:] = st["center"]
         cfg.near_plane = self.near_far[0]
@@ -537,7 +551,7 @@ class EgoNeRF(torch.nn.Module):
         self.gridSize = torch.LongTensor(res_target).to(self.gridSize.device)
         self.update_stepSize(res_target)
         # everything derived from the old resolution: render tables, ladders, cached scalars, table-space optimiser state
-        self._tables = self._tables_key = self._tables_bf16 = self._cfg_static = None
+        self._tables = self._tables_key = self._tables_bf16 = self._tables_h = self._cfg_static = None
         self._sched = {}
         self._table_opt = None
         self._bucket = None
@@ -592,7 +606,7 @@ class EgoNeRF(torch.nn.Module):
         """Kernels of libegn_b200 launched by one `forward` (sampler, gather, [MLP], composite)."""
         if not isinstance(self.renderModule, torch.nn.Module):
             return 3
-        fused = self.mlp_mode == "tc_bf16" and self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
+        fused = self._fused_mode() and self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
         return 3 if fused else 4
 
     def launches_per_train_step(self, n_rays):

@@ -68,8 +68,9 @@ class TableAdam:
             P = m._grads_struct([p.detach() for p in plist])        # destinations: the NCHW parameter tensors themselves
             tables = m._render_tables()                              # current tables (== current parameters)
             t16 = m._tables_bf16.data_ptr() if m._tables_bf16 is not None else None
+            th = m._tables_h.data_ptr() if getattr(m, "_tables_h", None) is not None else None
             _lib.check(lib.egn_adam_tables(cfg, P, self.d_tables.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                           tables.data_ptr(), t16, float(self.factor_group['lr']), float(self.betas[0]),
+                                           tables.data_ptr(), t16, th, float(self.factor_group['lr']), float(self.betas[0]),
                                            float(self.betas[1]), float(self.eps), self.step_count,
                                            torch.cuda.current_stream().cuda_stream))
             self.tables_fresh = True        # parameters were written through raw pointers: torch versions did not move

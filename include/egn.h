@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 6
+#define EGN_ABI_VERSION 7
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -32,8 +32,11 @@ enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH
 enum { EGN_ACT_SOFTPLUS = 0, EGN_ACT_RELU = 1 };
 /* MLP arithmetic: EGN_MLP_FP32 exact fp32 FFMA; EGN_MLP_TC_SPLIT tcgen05 tensor cores with a 3-term bf16 split
  * (fp32-equivalent, inside the 1e-4 parity bound); EGN_MLP_TC_BF16 throughput mode: gather + basis + MLP fused into one
- * warp-specialised tcgen05 kernel with bf16 operands (PSNR-gated, not bit-parity) */
-enum { EGN_MLP_FP32 = 0, EGN_MLP_TC_SPLIT = 1, EGN_MLP_TC_BF16 = 2 };
+ * warp-specialised tcgen05 kernel.  Since ABI 7 its forward pass computes with FP16 operands (appearance tables, packed
+ * half2 interpolation, MMA operands; fp32 accumulate) and keeps the density channels, alpha and compositing in fp32: rgb stays
+ * inside the 1e-4 bound (the bf16 operands of ABI 6 gave 1e-3).  The name EGN_MLP_TC_BF16 is kept as an alias; the tcgen05
+ * backward kernels still use bf16 operands (gradients need the exponent range). */
+enum { EGN_MLP_FP32 = 0, EGN_MLP_TC_SPLIT = 1, EGN_MLP_TC_BF16 = 2, EGN_MLP_TC_F16 = 2 };
 
 /* Static description of one model / scene.  Scalars mirror the constructor arguments of
  * EgoNeRF / TensorBase (models/tensorBase.py:133-139) and YinYangSphericalCoords
@@ -80,8 +83,11 @@ typedef struct EgnConfig {
                                  coordinates.py:137-139); ignored (may be NULL) otherwise: interval_th ignores `downsample` */
     const float* z_coarse;    /* device, n_coarse : r schedule of sample_ray_exp WITHOUT near (EgoNeRF.py:69-76);
                                  the kernels add near_plane and, in train mode, the interval jitter (:78-82) */
-    const void*  tables_bf16; /* device, optional: bf16 copy of the fine render tables (egn_pack_tables_bf16), read by the
-                                 fused fine pass of EGN_MLP_TC_BF16 instead of the fp32 tables; NULL = gather from fp32 */
+    const void*  tables_bf16; /* device, optional: bf16 copy of the fine render tables (egn_pack_tables_bf16), re-gathered by the
+                                 tcgen05 backward kernels instead of the fp32 tables; NULL = re-gather from fp32 */
+    const void*  tables_h;    /* device: "half" tables of the fused fine pass (egn_pack_tables_h): per fine texel 48 fp16
+                                 appearance channels in one aligned 128-byte line + 16 fp32 density channels.  Required by
+                                 EGN_MLP_TC_F16 forward passes */
 } EgnConfig;
 
 /* Parameters in the REFERENCE layout (contiguous NCHW fp32, shapes of EgoNeRF.init_one_svd,
@@ -141,11 +147,14 @@ int32_t egn_pack_tables(const EgnConfig* cfg, const EgnParams* params, float* ta
  * (optional) and the pooled coarse tables (EgoNeRF.update_coarse_sigma_grid, models/EgoNeRF.py:124-133).  step counts from 1. */
 int32_t egn_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables /*device*/,
                         float* exp_avg /*device*/, float* exp_avg_sq /*device*/, float* tables /*device*/,
-                        void* tables_bf16 /*device, nullable*/, float lr, float beta1, float beta2, float eps, int32_t step,
-                        void* stream);
+                        void* tables_bf16 /*device, nullable*/, void* tables_h /*device, nullable*/, float lr, float beta1,
+                        float beta2, float eps, int32_t step, void* stream);
 /* bf16 copy of the fine sections (same element offsets; egn_table_bf16_elems elements of 2 bytes) for the throughput mode */
 int64_t egn_table_bf16_elems(const EgnConfig* cfg);
 int32_t egn_pack_tables_bf16(const EgnConfig* cfg, const float* tables /*device*/, void* tables_bf16 /*device*/, void* stream);
+/* half tables of the fused fine pass (EgnConfig.tables_h): egn_table_h_bytes bytes, built from the fp32 render tables */
+int64_t egn_table_h_bytes(const EgnConfig* cfg);
+int32_t egn_pack_tables_h(const EgnConfig* cfg, const float* tables /*device*/, void* tables_h /*device*/, void* stream);
 /* inverse scatter for training: writes d(tables) (table layout) into the reference-layout factor grads
  * (overwrites grads->{density,app}_{plane,line}; the other members are untouched) */
 int32_t egn_unpack_table_grads(const EgnConfig* cfg, const float* d_tables /*device*/, const EgnGrads* grads,
