@@ -66,6 +66,9 @@ PROTOTYPES = {
     "egn_adam_tables": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnGrads), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "egn_unpack_table_grads": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.POINTER(EgnGrads), C.c_void_p]),
+    "egn_pack_table_grads": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnGrads), C.c_void_p, C.c_void_p]),
+    "egn_regularize_tables": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p]),
     "egn_workspace_bytes": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),
     "egn_workspace_bytes_eval": (C.c_int64, [C.POINTER(EgnConfig), C.c_int64]),
     "egn_render_forward": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
@@ -81,6 +84,9 @@ PROTOTYPES = {
     "egn_render_backward": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(EgnGrads), C.c_void_p]),
+    "egn_render_backward_sparse_env": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.POINTER(EgnGrads), C.c_void_p, C.c_void_p]),
     "egn_density_feature": (C.c_int32, [C.POINTER(EgnConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_void_p, C.c_void_p]),
     "egn_app_feature": (C.c_int32, [C.POINTER(EgnConfig), C.POINTER(EgnParams), C.c_void_p, C.c_void_p, C.c_int64,

@@ -160,6 +160,21 @@ extern "C" int32_t egn_unpack_table_grads(const EgnConfig* c, const float* d_tab
     return e ? cuda_fail("egn_unpack_table_grads", e) : 0;
 }
 
+extern "C" int32_t egn_pack_table_grads(const EgnConfig* c, const EgnGrads* g, float* d_tables, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!d_tables || !g) return fail("null argument");
+    int e = egn_launch_pack_grads(c, g, d_tables, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_pack_table_grads", e) : 0;
+}
+
+extern "C" int32_t egn_regularize_tables(const EgnConfig* c, const float* tables, float* d_tables, float tv_density, float tv_app,
+                                         float l1_density, float* losses, void* stream) {
+    if (validate(c, false)) return 1;
+    if (!tables || !d_tables) return fail("null argument");
+    int e = egn_launch_regularize(c, tables, d_tables, tv_density, tv_app, l1_density, losses, (cudaStream_t)stream);
+    return e ? cuda_fail("egn_regularize_tables", e) : 0;
+}
+
 // ---- workspace ----------------------------------------------------------------------------------
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
@@ -323,6 +338,13 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
                                        int64_t n, const void* workspace, const float* d_rgb, const float* d_bg,
                                        const float* d_env, const float* d_alpha, float* d_tables, const EgnGrads* g,
                                        void* stream) {
+    return egn_render_backward_sparse_env(c, p, tables, rays, n, workspace, d_rgb, d_bg, d_env, d_alpha, d_tables, g, nullptr, stream);
+}
+
+extern "C" int32_t egn_render_backward_sparse_env(const EgnConfig* c, const EgnParams* p, const float* tables, const float* rays,
+                                                  int64_t n, const void* workspace, const float* d_rgb, const float* d_bg,
+                                                  const float* d_env, const float* d_alpha, float* d_tables, const EgnGrads* g,
+                                                  float* d_env_rays, void* stream) {
     if (validate(c, true)) return 1;
     if (n <= 0) return 0;
     if (!p || !tables || !rays || !workspace || !d_tables || !g) return fail("null argument");
@@ -331,7 +353,7 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
     if (mlp)
         for (int l = 0; l < 3; ++l)
             if (!p->mlp_w[l] || !p->mlp_b[l] || !g->mlp_w[l] || !g->mlp_b[l]) return fail("MLP weights / gradient buffers missing");
-    if (c->env_h > 0 && (!p->emission || !g->emission)) return fail("envmap configured but emission / its gradient missing");
+    if (c->env_h > 0 && (!p->emission || (!g->emission && !d_env_rays))) return fail("envmap configured but emission / its gradient missing");
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     EgnKernelCfg k = make_kcfg(c, tables, true);
@@ -347,7 +369,7 @@ extern "C" int32_t egn_render_backward(const EgnConfig* c, const EgnParams* p, c
     float* d_feat = (float*)(base + w.d_feat);
     int e;
     if ((e = egn_launch_composite_bwd(k, p, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs,
-                                      d_fsig, d_feat, g->emission, st))) return cuda_fail("composite backward", e);
+                                      d_fsig, d_feat, g->emission, c->env_h > 0 ? d_env_rays : nullptr, st))) return cuda_fail("composite backward", e);
     if (mlp && tc_backward(c)) {
         if ((e = egn_launch_mlp_bwd_tc(k, p, rays, n, feat, rgbs, d_rgbs, d_feat, g, st))) return cuda_fail("mlp backward (tcgen05)", e);
     } else if (mlp) {

@@ -20,7 +20,8 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                          const float* __restrict__ fsig, const float* __restrict__ feat, const float* __restrict__ rgbs,
                          const float* __restrict__ rgbpre, const float* __restrict__ d_rgb, const float* __restrict__ d_bg,
                          const float* __restrict__ d_env, const float* __restrict__ d_alpha, float* __restrict__ d_rgbs,
-                         float* __restrict__ d_fsig, float* __restrict__ d_feat, float* __restrict__ d_emission) {
+                         float* __restrict__ d_fsig, float* __restrict__ d_feat, float* __restrict__ d_emission,
+                         float* __restrict__ d_env_rays) {
     const int lane = threadIdx.x & 31;
     const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (ray >= n) return;
@@ -83,7 +84,9 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             dbgw = fmaf(gb, e[ch], dbgw);
             de[ch] = gb * Tend + (d_env ? d_env[ray * 3 + ch] : 0.f);
         }
-        if (lane == 0 && d_emission) {
+        if (lane == 0 && d_env_rays) {            // sparse form: the per-ray gradient w.r.t. the env radiance; the caller scatters
+            d_env_rays[ray * 3] = de[0]; d_env_rays[ray * 3 + 1] = de[1]; d_env_rays[ray * 3 + 2] = de[2];
+        } else if (lane == 0 && d_emission) {
             const EnvTap t = egn_env_tap(dx, dy, dz, k.env_h);
             const int W = k.env_h, H = 2 * k.env_h;
             const float w[4] = {(1.f - t.fx) * (1.f - t.fy), t.fx * (1.f - t.fy), (1.f - t.fx) * t.fy, t.fx * t.fy};
@@ -150,10 +153,10 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,
                              const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
-                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, cudaStream_t st) {
+                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, float* d_env_rays, cudaStream_t st) {
     long long threads = n * 32;
     egn_composite_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        k, p->emission, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs, d_fsig, d_feat, d_emission);
+        k, p->emission, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs, d_fsig, d_feat, d_emission, d_env_rays);
     return (int)cudaGetLastError();
 }
 

@@ -79,8 +79,14 @@ __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast
 // geometry, F.grid_sample bilinear / zeros / align_corners=True).  Out-of-range taps get weight 0 and a clamped in-range
 // texel, so every later load is unconditional.  Record layout per factor pair i (12 words):
 //   [t00 t01 t10 t11] [l0 l1 w00 w01] [w10 w11 u0 u1]     t*, l*: global texel indices (EgnLayoutH); w*, u*: fp32 weights
+// TAP REUSE: consecutive samples of a ray mostly fall into the same texel cells (measured: 59 % of all taps of the cfg2
+// workload equal the previous sample's, profiles/r02_locality.md).  The SIGN BIT of a weight (weights are >= 0) says "this tap
+// reads the same texel as the same tap of the previous row"; the gather passes walk consecutive rows in the same lanes, keep
+// the taps in registers and skip the load when the bit is set.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fused_address_record(const EgnKernelCfg& k, const YYCoord& cc, uint4* __restrict__ rec) {
+struct FuRecord { unsigned idx[3][6]; float w[3][6]; };
+
+__device__ __forceinline__ void fused_address_record(const EgnKernelCfg& k, const YYCoord& cc, FuRecord& R) {
     unsigned j0[3], j1[3];
     float wa0[3], wa1[3];
 #pragma unroll
@@ -101,35 +107,60 @@ __device__ __forceinline__ void fused_address_record(const EgnKernelCfg& k, cons
         const unsigned W = (unsigned)k.lay.G[ax];
         const unsigned pb = (unsigned)k.texp[cc.yang][i], lb = (unsigned)k.texl[cc.yang][i];
         const unsigned ra = pb + j0[ay] * W, rb = pb + j1[ay] * W;
-        rec[3 * i] = make_uint4(ra + j0[ax], ra + j1[ax], rb + j0[ax], rb + j1[ax]);
-        rec[3 * i + 1] = make_uint4(lb + j0[al], lb + j1[al], __float_as_uint(wa0[ax] * wa0[ay]), __float_as_uint(wa1[ax] * wa0[ay]));
-        rec[3 * i + 2] = make_uint4(__float_as_uint(wa0[ax] * wa1[ay]), __float_as_uint(wa1[ax] * wa1[ay]),
-                                    __float_as_uint(wa0[al]), __float_as_uint(wa1[al]));
+        R.idx[i][0] = ra + j0[ax]; R.idx[i][1] = ra + j1[ax]; R.idx[i][2] = rb + j0[ax]; R.idx[i][3] = rb + j1[ax];
+        R.idx[i][4] = lb + j0[al]; R.idx[i][5] = lb + j1[al];
+        R.w[i][0] = wa0[ax] * wa0[ay]; R.w[i][1] = wa1[ax] * wa0[ay]; R.w[i][2] = wa0[ax] * wa1[ay]; R.w[i][3] = wa1[ax] * wa1[ay];
+        R.w[i][4] = wa0[al]; R.w[i][5] = wa1[al];
+    }
+}
+// marks the taps that equal the previous lane's (= previous row's), then stores the record (lanes < 16)
+__device__ __forceinline__ void fused_store_record(FuRecord& R, int lane, uint4* __restrict__ rec) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const unsigned prev = __shfl_up_sync(FULL, R.idx[i][t], 1);
+            if (prev == R.idx[i][t] && lane > 0) R.w[i][t] = __uint_as_float(__float_as_uint(R.w[i][t]) | 0x80000000u);
+        }
+    if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            rec[3 * i] = make_uint4(R.idx[i][0], R.idx[i][1], R.idx[i][2], R.idx[i][3]);
+            rec[3 * i + 1] = make_uint4(R.idx[i][4], R.idx[i][5], __float_as_uint(R.w[i][0]), __float_as_uint(R.w[i][1]));
+            rec[3 * i + 2] = make_uint4(__float_as_uint(R.w[i][2]), __float_as_uint(R.w[i][3]), __float_as_uint(R.w[i][4]),
+                                        __float_as_uint(R.w[i][5]));
+        }
     }
 }
 
-// phase 2: density of 8 samples (rows r8 .. r8+7 of the warp's records), 4 lanes x 4 fp32 channels per sample.
-// All 18 taps are requested before the first use: one L2 round trip per pass (the shared memory of this kernel leaves no L1).
-__device__ __forceinline__ float fused_density_pass(const float4* __restrict__ dens, const uint4* __restrict__ recs, int r8, int lane) {
+// one tap: keep the registers when the record says "same texel as the previous row" and this lane group did gather that row
+template <typename T>
+__device__ __forceinline__ void fused_tap(T& reg, const T* __restrict__ base, unsigned elem, unsigned wbits, bool may_reuse) {
+    if (!(may_reuse && (int)wbits < 0)) reg = __ldg(base + elem);
+}
+
+// phase 2: density of 8 samples, 4 lanes x 4 fp32 channels per sample; lane group h = lane >> 2 walks rows 2h, 2h+1 in passes
+// p = 0, 1.  Every tap that is needed is requested before the first use: one L2 round trip per pass (the shared memory of
+// this kernel leaves no L1).  `t` holds the taps of the group's previous row.
+__device__ __forceinline__ float fused_density_pass(const float4* __restrict__ dens, const uint4* __restrict__ recs, int p, int lane,
+                                                    float4 (&t)[3][6]) {
     const unsigned sub = lane & 3;
-    const uint4* rec = recs + (r8 + (lane >> 2)) * (FU_REC_WORDS / 4);
-    float4 t[3][6];
-    uint4 wq[3][2];
+    const uint4* rec = recs + (2 * (lane >> 2) + p) * (FU_REC_WORDS / 4);
+    const bool re = false;   // (density reuse disabled: spills)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const uint4 a = rec[3 * i], b = rec[3 * i + 1];
-        wq[i][1] = rec[3 * i + 2];
-        wq[i][0] = b;
-        t[i][0] = __ldg(dens + (a.x * 4u + sub)); t[i][1] = __ldg(dens + (a.y * 4u + sub));
-        t[i][2] = __ldg(dens + (a.z * 4u + sub)); t[i][3] = __ldg(dens + (a.w * 4u + sub));
-        t[i][4] = __ldg(dens + (b.x * 4u + sub)); t[i][5] = __ldg(dens + (b.y * 4u + sub));
+        const uint4 a = rec[3 * i], b = rec[3 * i + 1], c = rec[3 * i + 2];
+        fused_tap(t[i][0], dens, a.x * 4u + sub, b.z, re); fused_tap(t[i][1], dens, a.y * 4u + sub, b.w, re);
+        fused_tap(t[i][2], dens, a.z * 4u + sub, c.x, re); fused_tap(t[i][3], dens, a.w * 4u + sub, c.y, re);
+        fused_tap(t[i][4], dens, b.x * 4u + sub, c.z, re); fused_tap(t[i][5], dens, b.y * 4u + sub, c.w, re);
     }
     float f = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float w0 = __uint_as_float(wq[i][0].z), w1 = __uint_as_float(wq[i][0].w);
-        const float w2 = __uint_as_float(wq[i][1].x), w3 = __uint_as_float(wq[i][1].y);
-        const float u0 = __uint_as_float(wq[i][1].z), u1 = __uint_as_float(wq[i][1].w);
+        const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];       // weights again: cheaper than 24 live registers
+        const float w0 = fabsf(__uint_as_float(b.z)), w1 = fabsf(__uint_as_float(b.w));
+        const float w2 = fabsf(__uint_as_float(c.x)), w3 = fabsf(__uint_as_float(c.y));
+        const float u0 = fabsf(__uint_as_float(c.z)), u1 = fabsf(__uint_as_float(c.w));
         float4 P = make_float4(w0 * t[i][0].x, w0 * t[i][0].y, w0 * t[i][0].z, w0 * t[i][0].w);
         P = f4fma(w1, t[i][1], P); P = f4fma(w2, t[i][2], P); P = f4fma(w3, t[i][3], P);
         float4 Lv = make_float4(u0 * t[i][4].x, u0 * t[i][4].y, u0 * t[i][4].z, u0 * t[i][4].w);
@@ -142,34 +173,34 @@ __device__ __forceinline__ float fused_density_pass(const float4* __restrict__ d
     return f;                                                 // all four lanes of the sample hold it
 }
 
-// phase 3: appearance products of 4 samples (rows r4 .. r4+3), lanes 0..5 of each quarter-warp x 8 fp16 channels; all 18 taps
-// in flight before the first use
-__device__ __forceinline__ void fused_app_pass(const uint4* __restrict__ app, const uint4* __restrict__ recs, int r4, int row0,
-                                               int lane, unsigned char* __restrict__ vbuf) {
+// phase 3: appearance products of 4 samples, lanes 0..5 of each quarter-warp x 8 fp16 channels; quarter g = lane >> 3 walks
+// rows 4g .. 4g+3 in passes p = 0 .. 3
+__device__ __forceinline__ void fused_app_pass(const uint4* __restrict__ app, const uint4* __restrict__ recs, int p, int row0,
+                                               int lane, unsigned char* __restrict__ vbuf, uint4 (&t)[3][6]) {
     const unsigned q = lane & 7;
     if (q >= 6) return;                                       // the 128-byte texel line holds 96 bytes of channels
-    const int rl = r4 + (lane >> 3);
-    const uint4* rec = recs + rl * (FU_REC_WORDS / 4);
-    unsigned char* vrow = vbuf + (row0 + rl) * 16 + q * FU_VCHUNK;
-    uint4 t[3][6];
-    uint4 wq[3][2];
+    const int rloc = 4 * (lane >> 3) + p;
+    const uint4* rec = recs + rloc * (FU_REC_WORDS / 4);
+    unsigned char* vrow = vbuf + (row0 + rloc) * 16 + q * FU_VCHUNK;
+    const bool re = p > 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const uint4 a = rec[3 * i], b = rec[3 * i + 1];
-        wq[i][1] = rec[3 * i + 2];
-        wq[i][0] = b;
-        t[i][0] = __ldg(app + (a.x * 8u + q)); t[i][1] = __ldg(app + (a.y * 8u + q));
-        t[i][2] = __ldg(app + (a.z * 8u + q)); t[i][3] = __ldg(app + (a.w * 8u + q));
-        t[i][4] = __ldg(app + (b.x * 8u + q)); t[i][5] = __ldg(app + (b.y * 8u + q));
+        const uint4 a = rec[3 * i], b = rec[3 * i + 1], c = rec[3 * i + 2];
+        // registers are kept across passes only for the ANGULAR taps (plane 2 = theta x phi, line 0 = phi, line 1 = theta:
+        // 69 / 78 / 82 % of them repeat the previous sample's texel); keeping all 18 (72 registers) spills
+        const bool rp = re && i == 2, rl = re && i < 2;
+        fused_tap(t[i][0], app, a.x * 8u + q, b.z, rp); fused_tap(t[i][1], app, a.y * 8u + q, b.w, rp);
+        fused_tap(t[i][2], app, a.z * 8u + q, c.x, rp); fused_tap(t[i][3], app, a.w * 8u + q, c.y, rp);
+        fused_tap(t[i][4], app, b.x * 8u + q, c.z, rl); fused_tap(t[i][5], app, b.y * 8u + q, c.w, rl);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const __half2 w0 = as_h2(pack_h2(__uint_as_float(wq[i][0].z), __uint_as_float(wq[i][0].z)));
-        const __half2 w1 = as_h2(pack_h2(__uint_as_float(wq[i][0].w), __uint_as_float(wq[i][0].w)));
-        const __half2 w2 = as_h2(pack_h2(__uint_as_float(wq[i][1].x), __uint_as_float(wq[i][1].x)));
-        const __half2 w3 = as_h2(pack_h2(__uint_as_float(wq[i][1].y), __uint_as_float(wq[i][1].y)));
-        const __half2 u0 = as_h2(pack_h2(__uint_as_float(wq[i][1].z), __uint_as_float(wq[i][1].z)));
-        const __half2 u1 = as_h2(pack_h2(__uint_as_float(wq[i][1].w), __uint_as_float(wq[i][1].w)));
+        const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];
+        const float f0 = fabsf(__uint_as_float(b.z)), f1 = fabsf(__uint_as_float(b.w));
+        const float f2 = fabsf(__uint_as_float(c.x)), f3 = fabsf(__uint_as_float(c.y));
+        const float g0 = fabsf(__uint_as_float(c.z)), g1 = fabsf(__uint_as_float(c.w));
+        const __half2 w0 = as_h2(pack_h2(f0, f0)), w1 = as_h2(pack_h2(f1, f1)), w2 = as_h2(pack_h2(f2, f2)), w3 = as_h2(pack_h2(f3, f3));
+        const __half2 u0 = as_h2(pack_h2(g0, g0)), u1 = as_h2(pack_h2(g1, g1));
         uint4 o;
 #define FU_PL(m) { __half2 P = __hmul2(w0, as_h2(t[i][0].m)); P = __hfma2(w1, as_h2(t[i][1].m), P); P = __hfma2(w2, as_h2(t[i][2].m), P); \
                    P = __hfma2(w3, as_h2(t[i][3].m), P); const __half2 Lv = __hfma2(u1, as_h2(t[i][5].m), __hmul2(u0, as_h2(t[i][4].m))); \
@@ -266,23 +297,31 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 cc.c[2] = __shfl_sync(FULL, held.c[2], (lane & 15) + 16);
                 cc.yang = __shfl_sync(FULL, held.yang, (lane & 15) + 16);
             }
-            // ---- phase 1b: address records of the warp's 16 rows ----
-            if (lane < 16) {
-                fused_address_record(k, cc, recs + lane * (FU_REC_WORDS / 4));
-                s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
+            // ---- phase 1b: address records of the warp's 16 rows (lane = row; lanes 16..31 run along on their held values) ----
+            {
+                FuRecord R;
+                fused_address_record(k, cc, R);
+                fused_store_record(R, lane, recs + (lane & 15) * (FU_REC_WORDS / 4));
+                if (lane < 16) s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
             }
             __syncwarp();
             // ---- phase 2: density (fp32), 2 passes x 8 samples ----
-#pragma unroll 1
-            for (int p = 0; p < 2; ++p) {
-                const float f = fused_density_pass(dens, recs, 8 * p, lane);
-                const long long m = tile * TC_TM + row0 + 8 * p + (lane >> 2);
-                if ((lane & 3) == 0 && m < M) fsig[m] = f;
+            {
+                float4 t[3][6];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const float f = fused_density_pass(dens, recs, p, lane, t);
+                    const long long m = tile * TC_TM + row0 + 2 * (lane >> 2) + p;
+                    if ((lane & 3) == 0 && m < M) fsig[m] = f;
+                }
             }
             // ---- phase 3: appearance (fp16) into the V operand, 4 passes x 4 samples ----
             ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);          // layer-0 MMAs of the tile that used this buffer are done
-#pragma unroll 1
-            for (int p = 0; p < 4; ++p) fused_app_pass(app, recs, 4 * p, row0, lane, vs + b * FU_VBYTES);
+            {
+                uint4 t[3][6];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) fused_app_pass(app, recs, p, row0, lane, vs + b * FU_VBYTES, t);
+            }
             fence_async_smem();                                      // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(v_full0 + 8 * b);

@@ -32,6 +32,9 @@ int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float
 int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables, float* m, float* v,
                            float* tables, void* tables_bf16, void* tables_h, float lr, float beta1, float beta2, float eps,
                            int step, cudaStream_t st);
+int egn_launch_pack_grads(const EgnConfig* cfg, const EgnGrads* grads, float* d_tables, cudaStream_t st);
+int egn_launch_regularize(const EgnConfig* cfg, const float* tables, float* d_tables, float tv_density, float tv_app,
+                          float l1_density, float* losses, cudaStream_t st);
 int egn_launch_pack_h(const EgnConfig* cfg, const float* tables, void* tables_h, cudaStream_t st);
 int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables_bf16, cudaStream_t st);
 int egn_launch_resample_factor(const float* src, int C, int H, int W, const float* ypos, int H2, const float* xpos, int W2,
@@ -41,7 +44,7 @@ int egn_launch_erp_rays(int H, int W, int row0, int n_rows, const float* c2w_hos
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,
                              const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
-                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, cudaStream_t st);
+                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, float* d_env_rays, cudaStream_t st);
 // MLP backward of a sub-chunk of n rays: recomputes the hidden activations into scratch (h1, h2, dz1, dz2: n*S x 128 floats)
 int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                        const float* rgbs, const float* d_rgbs, float* d_feat, float* h1, float* h2, float* dz1,

@@ -135,6 +135,137 @@ int egn_launch_pack_bf16(const EgnConfig* cfg, const float* tables, void* tables
     return (int)cudaGetLastError();
 }
 
+// Gradients that reached the NCHW parameter tensors by another road than egn_render_backward (plain-torch regularisers,
+// anything autograd wrote into `.grad`) -> ADDED to the table-layout gradient: the transpose of egn_unpack_kernel.  A tensor
+// without such a gradient is passed as NULL and skipped.
+__global__ void __launch_bounds__(256) egn_pack_grads_kernel(const __grid_constant__ PackJobs jobs, float* __restrict__ d_tables) {
+    const PackJob& J = jobs.j[blockIdx.y];
+    if (J.src_d == nullptr && J.src_a == nullptr) return;
+    const long long HW = (long long)J.H * J.W;
+    float4* dst = reinterpret_cast<float4*>(d_tables + J.off);
+    const long long n = HW * (EGN_CF / 4);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long texel = t / (EGN_CF / 4);
+        const int c = (int)(t % (EGN_CF / 4)) * 4;
+        const float* s = (c < EGN_CS) ? J.src_d : J.src_a;
+        if (s == nullptr) continue;
+        s += (long long)(c < EGN_CS ? c : c - EGN_CS) * HW;
+        float4 v = dst[t];
+        v.x += s[texel]; v.y += s[texel + HW]; v.z += s[texel + 2 * HW]; v.w += s[texel + 3 * HW];
+        dst[t] = v;
+    }
+}
+int egn_launch_pack_grads(const EgnConfig* cfg, const EgnGrads* grads, float* d_tables, cudaStream_t st) {
+    PackJobs jobs{};
+    EgnParams src{};
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) {
+            src.density_plane[h][i] = grads->density_plane[h][i]; src.density_line[h][i] = grads->density_line[h][i];
+            src.app_plane[h][i] = grads->app_plane[h][i]; src.app_line[h][i] = grads->app_line[h][i];
+        }
+    const int n = fill_jobs(cfg, &src, nullptr, jobs, false);
+    dim3 grid(148 * 2, n);
+    egn_pack_grads_kernel<<<grid, 256, 0, st>>>(jobs, d_tables);
+    return (int)cudaGetLastError();
+}
+
+// =================================================================================================
+// Regularisers of the factor tensors in table space: total variation of the 12 planes (utils.py:155-171 through
+// EgoNeRF.TV_loss_density / TV_loss_app, models/EgoNeRF.py:213-229: sum over planes of 1e-2 * 2 * (h_tv / count_h + w_tv / count_w))
+// and the L1 norm of the density planes and lines (EgoNeRF.density_L1, :204-211: sum of mean |x|).  One pass over the fp32 render
+// tables: every thread owns one float4 channel group of one texel, reads its four plane neighbours, ADDS the weighted
+// gradient to the table-layout gradient that egn_render_backward produced (so the regularisers need no NCHW gradient
+// tensors, no transposes and no extra optimiser traffic) and contributes to the three loss values
+// (losses[0] = TV_loss_density(reg), [1] = TV_loss_app(reg), [2] = density_L1(), unweighted, as train.py:293-305 logs them).
+// =================================================================================================
+struct RegWeights { float tv_density, tv_app, l1_density; };
+
+__global__ void __launch_bounds__(256) egn_regularize_kernel(const __grid_constant__ PackJobs jobs, const float* __restrict__ tables,
+                                                             float* __restrict__ d_tables, RegWeights rw, float* __restrict__ losses) {
+    const PackJob& J = jobs.j[blockIdx.y];
+    const int H = J.H, W = J.W;
+    const bool plane = W > 1;
+    const long long HW = (long long)H * W;
+    const float4* src = reinterpret_cast<const float4*>(tables + J.off);
+    float4* dst = reinterpret_cast<float4*>(d_tables + J.off);
+    // TVLoss: count_h = C (H-1) W, count_w = C H (W-1) with C = channels of the TENSOR (16 density / 48 appearance)
+    float acc_tv_d = 0.f, acc_tv_a = 0.f, acc_l1 = 0.f;
+    const long long n = HW * (EGN_CF / 4);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long texel = t / (EGN_CF / 4);
+        const int cg = (int)(t % (EGN_CF / 4));
+        const bool dens = cg < EGN_CS / 4;
+        const float C = dens ? (float)EGN_CS : (float)EGN_CA;
+        const float4 x = src[t];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float wtv = dens ? rw.tv_density : rw.tv_app;
+        if (plane) {
+            const int y = (int)(texel / W), xx = (int)(texel % W);
+            const float inv_h = 1.f / (C * (float)(H - 1) * (float)W), inv_w = 1.f / (C * (float)H * (float)(W - 1));
+            const float kh = wtv * 1e-2f * 2.f * 2.f * inv_h, kw = wtv * 1e-2f * 2.f * 2.f * inv_w;   // d/dx of 1e-2 * 2 * sum(diff^2) / count
+            float sh = 0.f, sw = 0.f;
+            if (y > 0) {
+                const float4 o = src[t - (long long)W * (EGN_CF / 4)];
+                const float4 d = make_float4(x.x - o.x, x.y - o.y, x.z - o.z, x.w - o.w);
+                sh += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+                g.x += kh * d.x; g.y += kh * d.y; g.z += kh * d.z; g.w += kh * d.w;
+            }
+            if (y < H - 1) {
+                const float4 o = src[t + (long long)W * (EGN_CF / 4)];
+                g.x -= kh * (o.x - x.x); g.y -= kh * (o.y - x.y); g.z -= kh * (o.z - x.z); g.w -= kh * (o.w - x.w);
+            }
+            if (xx > 0) {
+                const float4 o = src[t - (EGN_CF / 4)];
+                const float4 d = make_float4(x.x - o.x, x.y - o.y, x.z - o.z, x.w - o.w);
+                sw += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+                g.x += kw * d.x; g.y += kw * d.y; g.z += kw * d.z; g.w += kw * d.w;
+            }
+            if (xx < W - 1) {
+                const float4 o = src[t + (EGN_CF / 4)];
+                g.x -= kw * (o.x - x.x); g.y -= kw * (o.y - x.y); g.z -= kw * (o.z - x.z); g.w -= kw * (o.w - x.w);
+            }
+            const float tv = 1e-2f * 2.f * (sh * inv_h + sw * inv_w);
+            if (dens) acc_tv_d += tv; else acc_tv_a += tv;
+        }
+        if (dens) {                                            // density_L1: mean |x| over the tensor (planes and lines)
+            const float inv_n = 1.f / ((float)EGN_CS * (float)HW);
+            acc_l1 += (fabsf(x.x) + fabsf(x.y) + fabsf(x.z) + fabsf(x.w)) * inv_n;
+            const float kl = rw.l1_density * inv_n;
+            auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+            g.x += kl * sgn(x.x); g.y += kl * sgn(x.y); g.z += kl * sgn(x.z); g.w += kl * sgn(x.w);
+        }
+        if ((plane && wtv != 0.f) || (dens && rw.l1_density != 0.f)) {
+            float4 d = dst[t];
+            d.x += g.x; d.y += g.y; d.z += g.z; d.w += g.w;
+            dst[t] = d;
+        }
+    }
+    // block reduction of the three loss values, one atomic per block and value
+    __shared__ float red[3][8];
+    float v[3] = {acc_tv_d, acc_tv_a, acc_l1};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && losses != nullptr) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        if (s != 0.f) atomicAdd(losses + threadIdx.x, s);
+    }
+}
+int egn_launch_regularize(const EgnConfig* cfg, const float* tables, float* d_tables, float tv_density, float tv_app,
+                          float l1_density, float* losses, cudaStream_t st) {
+    PackJobs jobs{};
+    const int n = fill_jobs(cfg, nullptr, nullptr, jobs, false);
+    RegWeights rw{tv_density, tv_app, l1_density};
+    dim3 grid(148, n);
+    egn_regularize_kernel<<<grid, 256, 0, st>>>(jobs, tables, d_tables, rw, losses);
+    return (int)cudaGetLastError();
+}
+
 // half tables of the fused fine pass (EgnLayoutH): thread = one float4 channel group of one fine texel of the fp32 tables;
 // density groups are copied as fp32, appearance groups converted to fp16 (round-to-nearest, saturating), and the 32 bytes of
 // padding behind the 48 appearance halfs are zeroed.

@@ -27,6 +27,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on(t):
+    """Every ctypes launch runs under the device of its tensors (the reference supports `device='cuda:1'` while the current
+    device is 0): the kernels launch on the CURRENT device's stream, so make the tensors' device current."""
+    return torch.cuda.device(t.device)
+
+
 def _need_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"egonerf_b200: {what} must be a CUDA tensor — there is no CPU fallback")
@@ -60,6 +66,12 @@ class _VolumeRender(torch.autograd.Function):
     def forward(ctx, model, opts, rays, u_coarse, u_fine, z_vals, *params):
         lib = _lib.load()
         n = rays.shape[0]
+        ctx.dev_guard = _on(rays)
+        with ctx.dev_guard:
+            return _VolumeRender._forward(ctx, lib, n, model, opts, rays, u_coarse, u_fine, z_vals)
+
+    @staticmethod
+    def _forward(ctx, lib, n, model, opts, rays, u_coarse, u_fine, z_vals):
         tables = model._render_tables()          # (re)packs fp32 / bf16 tables if the parameters changed; before _config
         cfg = model._config(opts)
         S = lib.egn_samples_per_ray(cfg)
@@ -102,6 +114,11 @@ class _VolumeRender(torch.autograd.Function):
         lib = _lib.load()
         model, opts = ctx.model, ctx.opts
         rays, ws, tables = ctx.saved_tensors
+        with _on(rays):
+            return _VolumeRender._backward(ctx, lib, model, opts, rays, ws, tables, douts)
+
+    @staticmethod
+    def _backward(ctx, lib, model, opts, rays, ws, tables, douts):
         if ctx.has_env:
             d_rgb, _, d_bg, d_env, d_alpha = douts
         else:
@@ -125,9 +142,17 @@ class _VolumeRender(torch.autograd.Function):
             grads.append(flat[off:off + sz].view_as(p) if sz else None)
             off += sz
         G = model._grads_struct(grads)
-        _lib.check(lib.egn_render_backward(cfg, model._params_struct(), tables.data_ptr(), rays.data_ptr(), ctx.n,
-                                           ws.data_ptr(), _lib.ptr(d_rgb), _lib.ptr(d_bg), _lib.ptr(d_env),
-                                           _lib.ptr(d_alpha), d_tables.data_ptr(), G, _stream()))
+        # ray-sharded training exchanges the envmap gradient in sparse form (24 B per ray instead of the dense (3, 2h, h)
+        # tensor): the kernel then writes d(loss)/d(env radiance) per ray and `allreduce_gradients` scatters all ranks' rays
+        env_rays = None
+        if ctx.has_env and getattr(model, "sparse_env_grad", False):
+            env_rays = torch.empty(ctx.n, 3, device=tables.device, dtype=torch.float32)
+            model._env_rays.append((rays[:, 3:6].contiguous(), env_rays))
+        _lib.check(lib.egn_render_backward_sparse_env(cfg, model._params_struct(), tables.data_ptr(), rays.data_ptr(), ctx.n,
+                                                      ws.data_ptr(), _lib.ptr(d_rgb), _lib.ptr(d_bg), _lib.ptr(d_env),
+                                                      _lib.ptr(d_alpha), d_tables.data_ptr(), G, _lib.ptr(env_rays), _stream()))
+        if env_rays is not None:
+            grads[-1] = None                      # the dense emission gradient is produced by allreduce_gradients
         if table_opt is not None:
             table_opt.accumulate(d_tables)
         else:
@@ -171,6 +196,7 @@ class EgoNeRF(torch.nn.Module):
             else:
                 self.envmap = EnvironmentMap(h=envmap.emission.shape[2], init_strategy='zero', device=device)
                 self.envmap.load_envmap(envmap.emission, device=device)
+        self._check_envelope()
         self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
         self.init_svd_volume(gridSize[0], device)
         self.update_stepSize(list(gridSize))
@@ -189,6 +215,26 @@ class EgoNeRF(torch.nn.Module):
         self.tc_backward = os.environ.get("EGN_TC_BACKWARD", "0") == "1"
         self._tables_bf16 = None
         self._tables_h = None
+        # ray-sharded training only (set by the multi-GPU launcher): keep the envmap gradient per ray until
+        # `allreduce_gradients` has gathered every rank's rays (see `_VolumeRender.backward`)
+        self.sparse_env_grad = False
+        self._env_rays = []
+
+    def _check_envelope(self):
+        """What libegn_b200 is built for (egn_abi.cu `validate`; INTEGRATION.md "Supported envelope"): fail at construction
+        with the reason, not at the first forward."""
+        if self.density_n_comp != [16] * 3 or self.app_n_comp != [48] * 3:
+            raise NotImplementedError(f"libegn_b200 is built for n_lamb_sigma=[16,16,16], n_lamb_sh=[48,48,48] (every shipped "
+                                      f"EgoNeRF config); got {self.density_n_comp}, {self.app_n_comp}")
+        if not 1 <= self.app_dim <= 27:
+            raise NotImplementedError(f"app_dim={self.app_dim}: libegn_b200 supports 1..27")
+        if self.shadingMode in ('MLP_Fea', 'MLP'):
+            if self.featureC != 128:
+                raise NotImplementedError(f"featureC={self.featureC}: libegn_b200 supports 128")
+            in_dim = self.app_dim + 3 + 6 * self.view_pe + (2 * self.fea_pe * self.app_dim if self.shadingMode == 'MLP_Fea' else 0)
+            if in_dim > 152:
+                raise NotImplementedError(f"MLP input width {in_dim} (view_pe={self.view_pe}, fea_pe={self.fea_pe}) exceeds the 152 "
+                                          "libegn_b200 supports; the shipped configs use view_pe = fea_pe = 2 (150)")
 
     # ---- parameters (EgoNeRF.py:96-122) -------------------------------------------------------------
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
@@ -338,13 +384,17 @@ class EgoNeRF(torch.nn.Module):
         """Reference: AvgPool refresh of the coarse density grid (EgoNeRF.py:124-133, called every iteration by
         train.py:356-357).  Here: re-pack the render tables (interleaved fine tables + pooled coarse tables).  With a
         table-space optimiser attached the tables are already up to date after its step (it writes them itself)."""
-        if getattr(self, "_table_opt", None) is not None and self._table_opt.tables_fresh:
-            return
+        if getattr(self, "_table_opt", None) is not None:
+            return          # its step wrote parameters AND tables; any other parameter change moves the (data_ptr, version) key
         self._tables_key = None
 
     def _render_tables(self):
         fp = self._factor_params()
         _need_cuda(fp[0], "model parameters")
+        with _on(fp[0]):
+            return self._render_tables_on_device(fp)
+
+    def _render_tables_on_device(self, fp):
         key = tuple((p.data_ptr(), p._version) for p in fp)
         if self._tables is None or key != self._tables_key:
             lib = _lib.load()
@@ -470,8 +520,9 @@ class EgoNeRF(torch.nn.Module):
         z = torch.empty(n, S, device=rays.device)
         uc = u_coarse.contiguous().float() if u_coarse is not None else None
         uf = u_fine.contiguous().float() if u_fine is not None else None
-        _lib.check(lib.egn_sample_rays(cfg, self._render_tables().data_ptr(), rays.data_ptr(), n, int(is_train),
-                                       _lib.ptr(uc), _lib.ptr(uf), int(seed), int(ray_index0), z.data_ptr(), _stream()))
+        with _on(rays):
+            _lib.check(lib.egn_sample_rays(cfg, self._render_tables().data_ptr(), rays.data_ptr(), n, int(is_train),
+                                           _lib.ptr(uc), _lib.ptr(uf), int(seed), int(ray_index0), z.data_ptr(), _stream()))
         return z
 
     def _gather(self, coords_sampled, coarse=False, want_app=False):
@@ -480,14 +531,15 @@ class EgoNeRF(torch.nn.Module):
         c7 = coords_sampled.detach().reshape(-1, 7).contiguous().float()
         m = c7.shape[0]
         cfg = self._config(None)
-        tables = self._render_tables()
         sig = torch.empty(m, device=c7.device)
-        if want_app:
-            feat = torch.empty(m, 28, device=c7.device)
-            _lib.check(lib.egn_app_feature(cfg, self._params_struct(), tables.data_ptr(), c7.data_ptr(), m,
-                                           sig.data_ptr(), feat.data_ptr(), _stream()))
-            return feat[:, :self.app_dim].reshape(*coords_sampled.shape[:-1], self.app_dim)
-        _lib.check(lib.egn_density_feature(cfg, tables.data_ptr(), c7.data_ptr(), m, int(coarse), sig.data_ptr(), _stream()))
+        with _on(c7):
+            tables = self._render_tables()
+            if want_app:
+                feat = torch.empty(m, 28, device=c7.device)
+                _lib.check(lib.egn_app_feature(cfg, self._params_struct(), tables.data_ptr(), c7.data_ptr(), m,
+                                               sig.data_ptr(), feat.data_ptr(), _stream()))
+                return feat[:, :self.app_dim].reshape(*coords_sampled.shape[:-1], self.app_dim)
+            _lib.check(lib.egn_density_feature(cfg, tables.data_ptr(), c7.data_ptr(), m, int(coarse), sig.data_ptr(), _stream()))
         return sig.view(coords_sampled.shape[:-1])
 
     def compute_densityfeature(self, coords_sampled):
@@ -618,11 +670,14 @@ class EgoNeRF(torch.nn.Module):
     def allreduce_gradients(self, group=None, average=False):
         """Ray-sharded data parallelism: ONE all-reduce (sum) over all parameter gradients, through a
         persistent flat bucket (egonerf_b200/sharding.py)."""
-        from ..sharding import GradientBucket
+        from ..sharding import GradientBucket, gather_env_gradient
         ps = self._param_list()
         if getattr(self, "_table_opt", None) is not None:        # factor gradients live in table layout: one buffer already
             self._table_opt.allreduce(group, average)
             ps = ps[24:]
+        if self.envmap is not None and self.sparse_env_grad:     # 24 B / ray all-gather + local scatter instead of 88 MB
+            gather_env_gradient(self, group, average)
+            ps = ps[:-1]
         if getattr(self, "_bucket", None) is None or [id(p) for p in self._bucket.params] != [id(p) for p in ps]:
             self._bucket = GradientBucket(ps)
         self._bucket.gather_from_params()

@@ -56,3 +56,44 @@ class GradientBucket:
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         if average:
             self.flat.div_(dist.get_world_size(group))
+
+
+def gather_env_gradient(model, group=None, average=False):
+    """Envmap gradient of a ray-sharded step without the dense all-reduce: the backward pass left, per ray, the gradient
+    w.r.t. its env radiance (`model._env_rays`, filled when `model.sparse_env_grad` is set); ranks all-gather directions +
+    gradients (24 B / ray; 0.4 MB per rank at 16 384 rays against 88 MB for the dense (3, 3840, 1920) tensor) and every rank
+    scatters ALL rays into its own dense gradient with `egn_envmap_backward` -- the same sum, computed locally."""
+    from . import _lib
+    em = model.envmap.emission
+    if not model._env_rays:
+        packed = torch.zeros(0, 6, device=em.device)
+    else:
+        packed = torch.cat([torch.cat([d, g], 1) for d, g in model._env_rays], 0).contiguous()
+    model._env_rays = []
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        n_local = torch.tensor([packed.shape[0]], device=em.device, dtype=torch.int64)
+        counts = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(counts, n_local, group=group)
+        counts = [int(c.item()) for c in counts]
+        n_max = max(counts)
+        if n_max == 0:
+            em.grad = torch.zeros_like(em)
+            return
+        padded = torch.zeros(n_max, 6, device=em.device)
+        padded[:packed.shape[0]] = packed                      # padding rows carry zero gradient: they scatter nothing
+        gathered = torch.empty(world * n_max, 6, device=em.device)
+        dist.all_gather_into_tensor(gathered, padded, group=group)
+        packed = gathered
+    d_em = torch.zeros_like(em)
+    if packed.shape[0] > 0:
+        lib = _lib.load()
+        cfg = _lib.EgnConfig()
+        cfg.env_h = em.shape[2]
+        dirs, g = packed[:, :3].contiguous(), packed[:, 3:].contiguous()
+        with torch.cuda.device(em.device):
+            _lib.check(lib.egn_envmap_backward(cfg, em.data_ptr(), dirs.data_ptr(), dirs.shape[0], g.data_ptr(), d_em.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+    if average:
+        d_em.div_(world)
+    em.grad = d_em

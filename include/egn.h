@@ -160,6 +160,16 @@ int32_t egn_pack_tables_h(const EgnConfig* cfg, const float* tables /*device*/, 
 int32_t egn_unpack_table_grads(const EgnConfig* cfg, const float* d_tables /*device*/, const EgnGrads* grads,
                                void* stream);
 
+/* the reverse direction: gradients that sit in reference-layout tensors (written by autograd for losses that do not go through
+ * egn_render_backward) are ADDED to the table-layout gradient; NULL members are skipped */
+int32_t egn_pack_table_grads(const EgnConfig* cfg, const EgnGrads* grads, float* d_tables /*device*/, void* stream);
+/* Regularisers of the factor tensors in table space: adds the gradients of
+ *   tv_density * EgoNeRF.TV_loss_density(TVLoss()) + tv_app * EgoNeRF.TV_loss_app(TVLoss()) + l1_density * EgoNeRF.density_L1()
+ * (utils.py:155-171, models/EgoNeRF.py:204-229, as train.py:288-305 weights them) to d_tables, and ADDS the three unweighted
+ * loss values to losses[0..2] (device, caller-zeroed, nullable). */
+int32_t egn_regularize_tables(const EgnConfig* cfg, const float* tables /*device*/, float* d_tables /*device*/, float tv_density,
+                              float tv_app, float l1_density, float* losses /*device, 3 floats*/, void* stream);
+
 /* ---- whole path -------------------------------------------------------------------------------
  * egn_render_forward replaces EgoNeRF.forward (models/EgoNeRF.py:491-602) for one ray chunk, i.e.
  * sample_ray_exp (:56-87), YinYangSphericalCoords.from_cartesian / normalize_coord
@@ -212,6 +222,15 @@ int32_t egn_render_backward(const EgnConfig* cfg, const EgnParams* params, const
                             const float* rays, int64_t n_rays, const void* workspace,
                             const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
                             float* d_tables, const EgnGrads* grads, void* stream);
+
+/* Same, with the envmap gradient in SPARSE form: when d_env_rays (device, (n,3)) is given, the gradient w.r.t. each ray's env
+ * radiance (the sigmoid output of EnvironmentMap.get_radiance) is written there and grads->emission is not touched; the caller
+ * scatters it with egn_envmap_backward.  For ray-sharded training: ranks exchange 24 B per ray (direction +
+ * this gradient) instead of all-reducing the dense (3, 2h, h) envmap gradient (88 MB at h = 1920). */
+int32_t egn_render_backward_sparse_env(const EgnConfig* cfg, const EgnParams* params, const float* tables,
+                                       const float* rays, int64_t n_rays, const void* workspace,
+                                       const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
+                                       float* d_tables, const EgnGrads* grads, float* d_env_rays /*device, nullable*/, void* stream);
 
 /* ---- stand-alone operators --------------------------------------------------------------------
  * coords: device (m,7) normalised Yin-Yang coordinates [r,theta,phi | r,theta,phi | Y] as produced by

@@ -248,6 +248,32 @@ def main():
     print("mask occupancy", float(model.alphaMask.alpha_volume_yin.mean()), float(model.alphaMask.alpha_volume_yang.mean()),
           "rejected samples", float((masked_alpha == 0).float().mean()))
 
+    # ---- 6. regularisers (utils.py:155-183, EgoNeRF.py:189-229): values and the gradient of the weighted sum the
+    # Ricoh configs train with (train.py:288-305; ricoh/common.txt:12-13 TV 0.1 / 0.01) plus an L1 term, w.r.t. all 24 factors
+    from utils import TVLoss, ray_entropy_loss                       # the reference's own (import_reference left it in sys.modules)
+    co, model = build_reference(tiny)
+    tv = TVLoss()
+    vals = [model.TV_loss_density(tv), model.TV_loss_app(tv), model.density_L1(), model.vector_comp_diffs()]
+    w_reg = (0.1, 0.01, 0.05)
+    (w_reg[0] * vals[0] + w_reg[1] * vals[1] + w_reg[2] * vals[2]).backward()
+    g6 = torch.Generator().manual_seed(21)
+    alpha_in = torch.rand(64, 257, generator=g6)
+    reg_grads = {"grad:" + k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in model.named_parameters()
+                 if "plane" in k or "line" in k}
+    npz("regularisers_tiny.npz", weights=np.array(w_reg), values=torch.stack([v.detach() for v in vals]), alpha=alpha_in,
+        ray_entropy=ray_entropy_loss(alpha_in), checksum=sd_checksum(tiny.state_dict), **reg_grads)
+
+    # ---- 7. equirectangular rays (dataLoader/ray_utils.py:24-40,85-113 + dataset_omniblender.py:42-43) -------
+    from dataLoader.ray_utils import get_ray_directions_360, get_rays
+    H, W = 24, 48
+    g7 = torch.Generator().manual_seed(31)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g7))
+    c2w = torch.cat([q, torch.tensor([[0.3], [-0.1], [0.2]])], 1).float()
+    directions = get_ray_directions_360(H, W)
+    directions = directions / torch.norm(directions, dim=-1, keepdim=True)
+    rays_o, rays_d = get_rays(directions, c2w)
+    npz("erp_rays_ref.npz", H=H, W=W, c2w=c2w, rays=torch.cat([rays_o, rays_d], 1))
+
 
 if __name__ == "__main__":
     main()

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import RENDER_CASES, T, load_golden, oracle_cfg, scene_for
+from tests.helpers import RENDER_CASES, T, TINY, checksum, load_golden, oracle_cfg, scene_for
 
 pytestmark = pytest.mark.gpu
 GRAD_CASES = ["render_tiny_train_grad", "render_tiny_env_train_grad", "render_tiny_plain_train_grad"]
@@ -259,3 +259,90 @@ def test_adam_tables_kernel_is_exact():
     ca, cb = ref.compute_coarse_densityfeature(c7.cuda()), tab.compute_coarse_densityfeature(c7.cuda())
     assert float((ca - cb).abs().max()) <= 1e-5, "pooled coarse tables"
     assert float((ref._tables_bf16.float() - tab._tables_bf16.float()).abs().max()) <= 8e-3, "bf16 tables"
+
+
+def _unpack(model, d_tables):
+    from egonerf_b200 import _lib
+    lib = _lib.load()
+    grads = [torch.zeros_like(p) for p in model._param_list()]
+    _lib.check(lib.egn_unpack_table_grads(model._config(None), d_tables.data_ptr(), model._grads_struct(grads),
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return grads[:24]
+
+
+def test_table_space_regularisers_match_the_reference_fixture():
+    """`egn_regularize_tables` (TV of the 12 planes + L1 of the density factors, gradients added to the
+    table-layout gradient in one pass) against tests/golden/regularisers_tiny.npz = values and `.grad` of
+    0.1 * TV_loss_density(TVLoss()) + 0.01 * TV_loss_app(TVLoss()) + 0.05 * density_L1() computed by the UNMODIFIED reference
+    (utils.py:155-171, models/EgoNeRF.py:204-229)."""
+    from egonerf_b200.optim import TableAdam
+    from egonerf_b200.scene_io import model_from_scene
+    g = load_golden("regularisers_tiny")
+    model = model_from_scene(scene_for(TINY))
+    assert np.allclose(checksum(scene_for(TINY).state_dict), g["checksum"], rtol=1e-6)
+    opt = TableAdam(model, 0.02, 0.001)
+    w = [float(x) for x in g["weights"]]
+    losses = opt.regularize(tv_density=w[0], tv_app=w[1], l1_density=w[2]).cpu().numpy()
+    assert np.abs(losses - g["values"][:3]).max() <= 2e-5 * np.abs(g["values"][:3]).max(), (losses, g["values"])
+    grads = _unpack(model, opt.d_tables)
+    names = [f"{kind}_{h}.{i}" for h in ("yin", "yang") for kind in ("density_plane", "density_line", "app_plane", "app_line")
+             for i in range(3)]
+    for name, gr in zip(names, grads):
+        ref = g["grad:" + name]
+        err = np.abs(gr.cpu().numpy() - ref).max()
+        assert err <= 2e-5 * max(np.abs(ref).max(), 1e-12) + 1e-12, (name, err, np.abs(ref).max())
+    # the plain-torch mirror of the same methods (what an unchanged train.py calls) gives the same numbers
+    tv = lambda x: 2 * (torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum() / x[:, :, 1:, :].numel()
+                        + torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum() / x[:, :, :, 1:].numel()) / x.shape[0]
+    mine = torch.stack([model.TV_loss_density(tv), model.TV_loss_app(tv), model.density_L1(), model.vector_comp_diffs()])
+    assert np.abs(mine.detach().cpu().numpy() - g["values"]).max() <= 2e-5 * np.abs(g["values"]).max()
+
+
+@pytest.mark.parametrize("fused_reg", [False, True])
+def test_table_adam_keeps_regulariser_gradients(fused_reg):
+    """with TableAdam attached, gradients that reach the factor Parameters through plain-torch losses
+    (TV / L1 / ortho of train.py:288-305) must be applied, not dropped, and must not pile up in `p.grad`.  3 steps of
+    render loss + regularisers: TableAdam (torch regularisers folded by egn_pack_table_grads, or the fused table-space
+    `regularize`) against torch.optim.Adam on the reference's parameter groups."""
+    from egonerf_b200.optim import TableAdam
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays
+    scene = scene_for(TINY)
+    rays = make_rays(128, 'isotropic', seed=3).cuda()
+    target = torch.rand(128, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    tv = lambda x: 2 * (torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum() / x[:, :, 1:, :].numel()
+                        + torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum() / x[:, :, :, 1:].numel()) / x.shape[0]
+    W_TVD, W_TVA, W_L1, W_ORTHO = 5.0, 2.0, 0.5, 0.3           # large: the regularisers must visibly move the factors
+
+    def run(kind):
+        model = model_from_scene(scene)
+        model.mlp_mode = "fp32"
+        opt = TableAdam(model, 0.02, 0.001) if kind != "torch" else \
+            torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+        for it in range(3):
+            opt.zero_grad()
+            rgb = model(rays, is_train=True, seed=it, **RENDER_KW)[0]
+            loss = ((rgb - target) ** 2).mean() + W_ORTHO * model.vector_comp_diffs()
+            if kind == "table+fused":
+                opt.regularize(tv_density=W_TVD, tv_app=W_TVA, l1_density=W_L1)
+            else:
+                loss = loss + W_TVD * model.TV_loss_density(tv) + W_TVA * model.TV_loss_app(tv) + W_L1 * model.density_L1()
+            loss.backward()
+            opt.step()
+            model.update_coarse_sigma_grid()
+        if kind != "torch":
+            opt.zero_grad()
+            assert all(p.grad is None for p in model._factor_params())
+        return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    ref = run("torch")
+    tab = run("table+fused" if fused_reg else "table+torch")
+    base = {k: v.cuda() for k, v in scene.state_dict.items()}
+    for k in ref:
+        if "plane" not in k and "line" not in k:
+            continue
+        moved = float((ref[k] - base[k]).abs().mean())
+        d = float((ref[k] - tab[k]).abs().mean())
+        assert moved > 1e-3, (k, moved)                          # 3 Adam steps of lr 0.02 did move the tensor
+        assert d <= 0.02 * moved, (k, d, moved)                  # and both optimisers moved it the same way

@@ -37,6 +37,18 @@ def test_erp_rays_match_reference_formula():
     assert abs(float(out[:, 3:].norm(dim=-1).mean()) - 1.0) < 1e-6
 
 
+def test_erp_rays_match_the_reference_fixture():
+    """tests/golden/erp_rays_ref.npz: `get_ray_directions_360` + normalisation + `get_rays` of the UNMODIFIED reference
+    (dataLoader/ray_utils.py:24-40,85-113; dataset_omniblender.py:42-43), frozen by oracle/make_golden.py."""
+    import os
+    from egonerf_b200.raybank import erp_rays
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "erp_rays_ref.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    out = erp_rays(H, W, torch.from_numpy(g["c2w"])).cpu().numpy()
+    assert out.shape == g["rays"].shape
+    assert np.abs(out - g["rays"]).max() <= 2e-6
+
+
 def test_raybank_epoch_semantics():
     from egonerf_b200.raybank import RayBank
     n, batch = 1000, 96

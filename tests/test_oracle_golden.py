@@ -236,3 +236,26 @@ def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
         assert set(a.files) == set(b.files), f
         for k in a.files:
             assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f"), (f, k)
+
+
+def test_regulariser_mirror_matches_the_reference_fixture():
+    """regularisers_tiny.npz (values + gradients from the unmodified reference, utils.py:155-183, EgoNeRF.py:189-229): the
+    plain-torch regulariser methods of the drop-in module -- what an unchanged train.py:288-305 calls -- give the same values
+    and, through autograd, the same gradients on the same state dict."""
+    from egonerf_b200.scene_io import model_from_scene
+    from tests.helpers import TINY, scene_for, checksum
+    g = load_golden("regularisers_tiny")
+    scene = scene_for(TINY)
+    assert np.allclose(checksum(scene.state_dict), g["checksum"], rtol=1e-6)
+    model = model_from_scene(scene, "cpu")
+    tv = lambda x: 2 * (torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum() / x[:, :, 1:, :].numel()
+                        + torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum() / x[:, :, :, 1:].numel()) / x.shape[0]
+    vals = [model.TV_loss_density(tv), model.TV_loss_app(tv), model.density_L1(), model.vector_comp_diffs()]
+    assert np.abs(torch.stack(vals).detach().numpy() - g["values"]).max() <= 1e-6 * np.abs(g["values"]).max() + 1e-9
+    w = g["weights"]
+    (float(w[0]) * vals[0] + float(w[1]) * vals[1] + float(w[2]) * vals[2]).backward()
+    for name, p in model.named_parameters():
+        if "plane" in name or "line" in name:
+            ref = g["grad:" + name]
+            got = np.zeros_like(ref) if p.grad is None else p.grad.numpy()
+            assert np.abs(got - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-12) + 1e-12, name
