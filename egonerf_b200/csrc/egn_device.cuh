@@ -10,7 +10,7 @@
 #define EGN_CF (EGN_CS + EGN_CA)   // interleaved channels per texel: one tap = 256 contiguous bytes
 #define EGN_FEAT_STRIDE 28   // app feature row (27 used) padded to a multiple of 16 bytes
 #define EGN_MAX_KNOTS 1024
-#define EGN_FUSED_MAX_KNOTS 512   // r-ladder entries the fused fine pass keeps in shared memory
+#define EGN_FUSED_MAX_KNOTS 384   // r-ladder entries the fused fine pass keeps in shared memory (N_r <= 381)
 #define EGN_HID 128
 
 // matMode [[0,1],[0,2],[1,2]] / vecMode [2,1,0] (EgoNeRF.py:30-33): plane i is indexed x = c[MX[i]] (width),

@@ -48,12 +48,13 @@ struct FuLayout {
     static constexpr int A = BB + FU_VCHUNKS * FU_BB_CHUNK;           // + 18 432
     static constexpr int V = A + (TC_K1 / 8) * TC_CHUNK;              // + 40 960 ; two buffers
     static constexpr int REC = V + 2 * FU_VBYTES;                     // address records: 128 samples x 144 B
-    static constexpr int YANG = REC + TC_TM * FU_REC_WORDS * 4;       // 4 x 128 bytes
+    static constexpr int YANG = REC + 8 * (16 * (FU_REC_WORDS / 4) + 1) * 16;   // 8 warps x (16 records + 1 swizzle slot); then 4 x 128 bytes
     static constexpr int KNOTS = YANG + 4 * TC_TM;
     static constexpr int MBAR = KNOTS + ((EGN_FUSED_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
     static constexpr int TMEM = MBAR + 8 * 8;
     static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4
-    static constexpr int TOTAL = PART + TC_TM * 16;
+    static constexpr int L3 = PART + TC_TM * 16;                      // layer 3: per hidden unit {b2, W3[0], W3[1], W3[2]}: 128 x float4
+    static constexpr int TOTAL = L3 + EGN_HID * 16;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
 
@@ -79,12 +80,16 @@ __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast
 // geometry, F.grid_sample bilinear / zeros / align_corners=True).  Out-of-range taps get weight 0 and a clamped in-range
 // texel, so every later load is unconditional.  Record layout per factor pair i (12 words):
 //   [t00 t01 t10 t11] [l0 l1 w00 w01] [w10 w11 u0 u1]     t*, l*: global texel indices (EgnLayoutH); w*, u*: fp32 weights
-// TAP REUSE: consecutive samples of a ray mostly fall into the same texel cells (measured: 59 % of all taps of the cfg2
-// workload equal the previous sample's, profiles/r02_locality.md).  The SIGN BIT of a weight (weights are >= 0) says "this tap
-// reads the same texel as the same tap of the previous row"; the gather passes walk consecutive rows in the same lanes, keep
-// the taps in registers and skip the load when the bit is set.
+// (Keeping taps of the previous row in registers was measured and dropped: 59 % of all taps of the cfg2 workload equal the
+// previous sample's (profiles/r02_locality.md), but holding even the 8 angular taps across passes cost more in lost L1-tag
+// coalescing and registers than the skipped loads saved -- profiles/r02_fused.md.)
 // ---------------------------------------------------------------------------------------------------------------
 struct FuRecord { unsigned idx[3][6]; float w[3][6]; };
+// slot (in uint4 units) of local row r of a warp's 16 records: 9 uint4 per record, rows 8..15 shifted by one uint4 so that
+// the rows a gather pass reads together (4g + p for the appearance quarters, 8p + h for the density groups) and the rows
+// a quarter-warp of phase 1 writes together sit in distinct 16-byte bank groups
+__device__ __forceinline__ int fu_rec_slot(int r) { return r * (FU_REC_WORDS / 4) + (r >> 3); }
+#define FU_REC_WARP_UINT4 (16 * (FU_REC_WORDS / 4) + 1)
 
 __device__ __forceinline__ void fused_address_record(const EgnKernelCfg& k, const YYCoord& cc, FuRecord& R) {
     unsigned j0[3], j1[3];
@@ -113,102 +118,69 @@ __device__ __forceinline__ void fused_address_record(const EgnKernelCfg& k, cons
         R.w[i][4] = wa0[al]; R.w[i][5] = wa1[al];
     }
 }
-// marks the taps that equal the previous lane's (= previous row's), then stores the record (lanes < 16)
-__device__ __forceinline__ void fused_store_record(FuRecord& R, int lane, uint4* __restrict__ rec) {
+__device__ __forceinline__ void fused_store_record(const FuRecord& R, uint4* __restrict__ rec) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int t = 0; t < 6; ++t) {
-            const unsigned prev = __shfl_up_sync(FULL, R.idx[i][t], 1);
-            if (prev == R.idx[i][t] && lane > 0) R.w[i][t] = __uint_as_float(__float_as_uint(R.w[i][t]) | 0x80000000u);
-        }
-    if (lane < 16) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            rec[3 * i] = make_uint4(R.idx[i][0], R.idx[i][1], R.idx[i][2], R.idx[i][3]);
-            rec[3 * i + 1] = make_uint4(R.idx[i][4], R.idx[i][5], __float_as_uint(R.w[i][0]), __float_as_uint(R.w[i][1]));
-            rec[3 * i + 2] = make_uint4(__float_as_uint(R.w[i][2]), __float_as_uint(R.w[i][3]), __float_as_uint(R.w[i][4]),
-                                        __float_as_uint(R.w[i][5]));
-        }
+    for (int i = 0; i < 3; ++i) {
+        rec[3 * i] = make_uint4(R.idx[i][0], R.idx[i][1], R.idx[i][2], R.idx[i][3]);
+        rec[3 * i + 1] = make_uint4(R.idx[i][4], R.idx[i][5], __float_as_uint(R.w[i][0]), __float_as_uint(R.w[i][1]));
+        rec[3 * i + 2] = make_uint4(__float_as_uint(R.w[i][2]), __float_as_uint(R.w[i][3]), __float_as_uint(R.w[i][4]),
+                                    __float_as_uint(R.w[i][5]));
     }
 }
 
-// one tap: keep the registers when the record says "same texel as the previous row" and this lane group did gather that row
-template <typename T>
-__device__ __forceinline__ void fused_tap(T& reg, const T* __restrict__ base, unsigned elem, unsigned wbits, bool may_reuse) {
-    if (!(may_reuse && (int)wbits < 0)) reg = __ldg(base + elem);
+// ---- phases 2 and 3 are software pipelines over (pass, factor pair) units: the six taps of a unit are requested one whole
+// pass ahead -- right after the previous pass has consumed the registers they land in -- so two to three units (12-18 loads
+// per lane) are in flight while a unit is being computed.  The shared memory of this kernel leaves no L1: every tap is an L2
+// round trip, and the gather warps are bound by how many of them they keep in flight.
+
+// density: 4 lanes x 4 fp32 channels per sample; lane group h = lane >> 2 takes row 8p + h in pass p (8 consecutive rows per
+// load instruction: identical texels of neighbouring samples are fetched once by the L1 tag stage)
+__device__ __forceinline__ void fused_density_issue(const float4* __restrict__ dens, const uint4* __restrict__ rec, int i, unsigned sub,
+                                                    float4 (&t)[6]) {
+    const uint4 a = rec[3 * i], b = rec[3 * i + 1];
+    t[0] = __ldg(dens + (a.x * 4u + sub)); t[1] = __ldg(dens + (a.y * 4u + sub));
+    t[2] = __ldg(dens + (a.z * 4u + sub)); t[3] = __ldg(dens + (a.w * 4u + sub));
+    t[4] = __ldg(dens + (b.x * 4u + sub)); t[5] = __ldg(dens + (b.y * 4u + sub));
+}
+__device__ __forceinline__ float fused_density_unit(const uint4* __restrict__ rec, int i, const float4 (&t)[6]) {
+    const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];
+    const float w0 = __uint_as_float(b.z), w1 = __uint_as_float(b.w);
+    const float w2 = __uint_as_float(c.x), w3 = __uint_as_float(c.y);
+    const float u0 = __uint_as_float(c.z), u1 = __uint_as_float(c.w);
+    float4 P = make_float4(w0 * t[0].x, w0 * t[0].y, w0 * t[0].z, w0 * t[0].w);
+    P = f4fma(w1, t[1], P); P = f4fma(w2, t[2], P); P = f4fma(w3, t[3], P);
+    float4 Lv = make_float4(u0 * t[4].x, u0 * t[4].y, u0 * t[4].z, u0 * t[4].w);
+    Lv = f4fma(u1, t[5], Lv);
+    float s = fmaf(P.w, Lv.w, fmaf(P.z, Lv.z, fmaf(P.y, Lv.y, P.x * Lv.x)));
+    s += __shfl_xor_sync(FULL, s, 1);
+    s += __shfl_xor_sync(FULL, s, 2);
+    return fmaxf(s, 0.f);                                     // relu per factor pair (EgoNeRF.py:346)
 }
 
-// phase 2: density of 8 samples, 4 lanes x 4 fp32 channels per sample; lane group h = lane >> 2 walks rows 2h, 2h+1 in passes
-// p = 0, 1.  Every tap that is needed is requested before the first use: one L2 round trip per pass (the shared memory of
-// this kernel leaves no L1).  `t` holds the taps of the group's previous row.
-__device__ __forceinline__ float fused_density_pass(const float4* __restrict__ dens, const uint4* __restrict__ recs, int p, int lane,
-                                                    float4 (&t)[3][6]) {
-    const unsigned sub = lane & 3;
-    const uint4* rec = recs + (2 * (lane >> 2) + p) * (FU_REC_WORDS / 4);
-    const bool re = false;   // (density reuse disabled: spills)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint4 a = rec[3 * i], b = rec[3 * i + 1], c = rec[3 * i + 2];
-        fused_tap(t[i][0], dens, a.x * 4u + sub, b.z, re); fused_tap(t[i][1], dens, a.y * 4u + sub, b.w, re);
-        fused_tap(t[i][2], dens, a.z * 4u + sub, c.x, re); fused_tap(t[i][3], dens, a.w * 4u + sub, c.y, re);
-        fused_tap(t[i][4], dens, b.x * 4u + sub, c.z, re); fused_tap(t[i][5], dens, b.y * 4u + sub, c.w, re);
-    }
-    float f = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];       // weights again: cheaper than 24 live registers
-        const float w0 = fabsf(__uint_as_float(b.z)), w1 = fabsf(__uint_as_float(b.w));
-        const float w2 = fabsf(__uint_as_float(c.x)), w3 = fabsf(__uint_as_float(c.y));
-        const float u0 = fabsf(__uint_as_float(c.z)), u1 = fabsf(__uint_as_float(c.w));
-        float4 P = make_float4(w0 * t[i][0].x, w0 * t[i][0].y, w0 * t[i][0].z, w0 * t[i][0].w);
-        P = f4fma(w1, t[i][1], P); P = f4fma(w2, t[i][2], P); P = f4fma(w3, t[i][3], P);
-        float4 Lv = make_float4(u0 * t[i][4].x, u0 * t[i][4].y, u0 * t[i][4].z, u0 * t[i][4].w);
-        Lv = f4fma(u1, t[i][5], Lv);
-        float s = fmaf(P.w, Lv.w, fmaf(P.z, Lv.z, fmaf(P.y, Lv.y, P.x * Lv.x)));
-        s += __shfl_xor_sync(FULL, s, 1);
-        s += __shfl_xor_sync(FULL, s, 2);
-        f += fmaxf(s, 0.f);                                   // relu per factor pair (EgoNeRF.py:346)
-    }
-    return f;                                                 // all four lanes of the sample hold it
+// appearance: lanes 0..5 of each quarter-warp x 8 fp16 channels (the 128-byte texel line holds 96 bytes of channels: lanes
+// 6, 7 shadow lane 5 -- same addresses, no extra wavefront, no divergent control flow -- and only skip the store); the four
+// quarters of pass p take the four consecutive rows 4p + g
+__device__ __forceinline__ void fused_app_issue(const uint4* __restrict__ app, const uint4* __restrict__ rec, int i, unsigned q,
+                                                uint4 (&t)[6]) {
+    const uint4 a = rec[3 * i], b = rec[3 * i + 1];
+    t[0] = __ldg(app + (a.x * 8u + q)); t[1] = __ldg(app + (a.y * 8u + q));
+    t[2] = __ldg(app + (a.z * 8u + q)); t[3] = __ldg(app + (a.w * 8u + q));
+    t[4] = __ldg(app + (b.x * 8u + q)); t[5] = __ldg(app + (b.y * 8u + q));
 }
-
-// phase 3: appearance products of 4 samples, lanes 0..5 of each quarter-warp x 8 fp16 channels; quarter g = lane >> 3 walks
-// rows 4g .. 4g+3 in passes p = 0 .. 3
-__device__ __forceinline__ void fused_app_pass(const uint4* __restrict__ app, const uint4* __restrict__ recs, int p, int row0,
-                                               int lane, unsigned char* __restrict__ vbuf, uint4 (&t)[3][6]) {
-    const unsigned q = lane & 7;
-    if (q >= 6) return;                                       // the 128-byte texel line holds 96 bytes of channels
-    const int rloc = 4 * (lane >> 3) + p;
-    const uint4* rec = recs + rloc * (FU_REC_WORDS / 4);
-    unsigned char* vrow = vbuf + (row0 + rloc) * 16 + q * FU_VCHUNK;
-    const bool re = p > 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint4 a = rec[3 * i], b = rec[3 * i + 1], c = rec[3 * i + 2];
-        // registers are kept across passes only for the ANGULAR taps (plane 2 = theta x phi, line 0 = phi, line 1 = theta:
-        // 69 / 78 / 82 % of them repeat the previous sample's texel); keeping all 18 (72 registers) spills
-        const bool rp = re && i == 2, rl = re && i < 2;
-        fused_tap(t[i][0], app, a.x * 8u + q, b.z, rp); fused_tap(t[i][1], app, a.y * 8u + q, b.w, rp);
-        fused_tap(t[i][2], app, a.z * 8u + q, c.x, rp); fused_tap(t[i][3], app, a.w * 8u + q, c.y, rp);
-        fused_tap(t[i][4], app, b.x * 8u + q, c.z, rl); fused_tap(t[i][5], app, b.y * 8u + q, c.w, rl);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];
-        const float f0 = fabsf(__uint_as_float(b.z)), f1 = fabsf(__uint_as_float(b.w));
-        const float f2 = fabsf(__uint_as_float(c.x)), f3 = fabsf(__uint_as_float(c.y));
-        const float g0 = fabsf(__uint_as_float(c.z)), g1 = fabsf(__uint_as_float(c.w));
-        const __half2 w0 = as_h2(pack_h2(f0, f0)), w1 = as_h2(pack_h2(f1, f1)), w2 = as_h2(pack_h2(f2, f2)), w3 = as_h2(pack_h2(f3, f3));
-        const __half2 u0 = as_h2(pack_h2(g0, g0)), u1 = as_h2(pack_h2(g1, g1));
-        uint4 o;
-#define FU_PL(m) { __half2 P = __hmul2(w0, as_h2(t[i][0].m)); P = __hfma2(w1, as_h2(t[i][1].m), P); P = __hfma2(w2, as_h2(t[i][2].m), P); \
-                   P = __hfma2(w3, as_h2(t[i][3].m), P); const __half2 Lv = __hfma2(u1, as_h2(t[i][5].m), __hmul2(u0, as_h2(t[i][4].m))); \
+__device__ __forceinline__ uint4 fused_app_unit(const uint4* __restrict__ rec, int i, const uint4 (&t)[6]) {
+    const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];
+    const float f0 = __uint_as_float(b.z), f1 = __uint_as_float(b.w);
+    const float f2 = __uint_as_float(c.x), f3 = __uint_as_float(c.y);
+    const float g0 = __uint_as_float(c.z), g1 = __uint_as_float(c.w);
+    const __half2 w0 = as_h2(pack_h2(f0, f0)), w1 = as_h2(pack_h2(f1, f1)), w2 = as_h2(pack_h2(f2, f2)), w3 = as_h2(pack_h2(f3, f3));
+    const __half2 u0 = as_h2(pack_h2(g0, g0)), u1 = as_h2(pack_h2(g1, g1));
+    uint4 o;
+#define FU_PL(m) { __half2 P = __hmul2(w0, as_h2(t[0].m)); P = __hfma2(w1, as_h2(t[1].m), P); P = __hfma2(w2, as_h2(t[2].m), P); \
+                   P = __hfma2(w3, as_h2(t[3].m), P); const __half2 Lv = __hfma2(u1, as_h2(t[5].m), __hmul2(u0, as_h2(t[4].m))); \
                    o.m = as_u32(__hmul2(P, Lv)); }
-        FU_PL(x) FU_PL(y) FU_PL(z) FU_PL(w)
+    FU_PL(x) FU_PL(y) FU_PL(z) FU_PL(w)
 #undef FU_PL
-        *reinterpret_cast<uint4*>(vrow + i * (EGN_CA / 8) * FU_VCHUNK) = o;     // K index i*48 + q*8 .. +7
-    }
+    return o;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -221,7 +193,9 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                       float* __restrict__ rgbs) {
     using L = FuLayout;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle from lane 0: the compiler then KNOWS it is warp-uniform, keeps the role branches uniform and
+    // the load descriptors in uniform registers (without it every LDG of the kernel was preceded by two R2UR moves)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int AD = k.app_dim;
     const int in_dim = 5 * AD + 15;
     unsigned char* w1s = smem + L::W1;
@@ -232,6 +206,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     unsigned char* s_yang = smem + L::YANG;
     float* s_knots = reinterpret_cast<float*>(smem + L::KNOTS);
     float* part = reinterpret_cast<float*>(smem + L::PART);
+    float4* l3s = reinterpret_cast<float4*>(smem + L::L3);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
     const uint32_t bar = smem_u32(smem + L::MBAR);
     const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48;
@@ -259,6 +234,8 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
         store_elem_h(bbs, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
     }
     for (int i = tid; i <= k.knots_last; i += FU_THREADS) s_knots[i] = k.r_knots[i];
+    // layer-3 operands next to the SM: this kernel's shared memory leaves no L1, a global load here is an L2 round trip
+    for (int i = tid; i < EGN_HID; i += FU_THREADS) l3s[i] = make_float4(b2[i], w3[i], w3[EGN_HID + i], w3[2 * EGN_HID + i]);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -270,7 +247,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     if (warp >= 8) {
         // =========================== GATHER group ===========================
         const int gwarp = warp - 8, row0 = 16 * gwarp;
-        uint4* recs = reinterpret_cast<uint4*>(smem + L::REC) + row0 * (FU_REC_WORDS / 4);
+        uint4* recs = reinterpret_cast<uint4*>(smem + L::REC) + gwarp * FU_REC_WARP_UINT4;
         const uint4* app = reinterpret_cast<const uint4*>(k.tables_h);
         const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
         YYCoord held;                                                // coordinates computed one tile ahead (lanes 16..31)
@@ -297,30 +274,58 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 cc.c[2] = __shfl_sync(FULL, held.c[2], (lane & 15) + 16);
                 cc.yang = __shfl_sync(FULL, held.yang, (lane & 15) + 16);
             }
-            // ---- phase 1b: address records of the warp's 16 rows (lane = row; lanes 16..31 run along on their held values) ----
-            {
+            // ---- phase 1b: address records of the warp's 16 rows (lane = row) ----
+            if (lane < 16) {
                 FuRecord R;
                 fused_address_record(k, cc, R);
-                fused_store_record(R, lane, recs + (lane & 15) * (FU_REC_WORDS / 4));
-                if (lane < 16) s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
+                fused_store_record(R, recs + fu_rec_slot(lane));
+                s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
             }
             __syncwarp();
-            // ---- phase 2: density (fp32), 2 passes x 8 samples ----
+            // ---- phase 2: density (fp32), 2 passes x 8 samples, pipelined per factor pair ----
             {
+                const unsigned sub = lane & 3;
+                const uint4* rec = recs + fu_rec_slot(lane >> 2);
                 float4 t[3][6];
 #pragma unroll
+                for (int i = 0; i < 3; ++i) fused_density_issue(dens, rec, i, sub, t[i]);
+#pragma unroll
                 for (int p = 0; p < 2; ++p) {
-                    const float f = fused_density_pass(dens, recs, p, lane, t);
-                    const long long m = tile * TC_TM + row0 + 2 * (lane >> 2) + p;
-                    if ((lane & 3) == 0 && m < M) fsig[m] = f;
+                    const uint4* nxt = recs + fu_rec_slot(8 * (p + 1) + (lane >> 2));
+                    float f = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        f += fused_density_unit(rec, i, t[i]);
+                        if (p == 0) fused_density_issue(dens, nxt, i, sub, t[i]);
+                    }
+                    const long long m = tile * TC_TM + row0 + 8 * p + (lane >> 2);
+                    if (sub == 0 && m < M) fsig[m] = f;
+                    rec = nxt;
                 }
             }
-            // ---- phase 3: appearance (fp16) into the V operand, 4 passes x 4 samples ----
-            ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);          // layer-0 MMAs of the tile that used this buffer are done
+            // ---- phase 3: appearance (fp16) into the V operand, 4 passes x 4 samples, pipelined per factor pair.  The first
+            // pass's taps are requested BEFORE waiting for the V buffer ----
             {
+                const unsigned q = min(lane & 7, 5);
+                const bool owner = (lane & 7) < 6;
+                const uint4* rec = recs + fu_rec_slot(lane >> 3);
+                unsigned char* vrow = vs + b * FU_VBYTES + (row0 + (lane >> 3)) * 16 + q * FU_VCHUNK;
                 uint4 t[3][6];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) fused_app_pass(app, recs, p, row0, lane, vs + b * FU_VBYTES, t);
+                for (int i = 0; i < 3; ++i) fused_app_issue(app, rec, i, q, t[i]);
+                ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);      // layer-0 MMAs of the tile that used this buffer are done
+#pragma unroll 1
+                for (int p = 0; p < 4; ++p) {
+                    const uint4* nxt = recs + fu_rec_slot(min(4 * (p + 1), 12) + (lane >> 3));
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const uint4 o = fused_app_unit(rec, i, t[i]);
+                        if (owner) *reinterpret_cast<uint4*>(vrow + i * (EGN_CA / 8) * FU_VCHUNK) = o;   // K index i*48 + q*8 .. +7
+                        if (p < 3) fused_app_issue(app, nxt, i, q, t[i]);
+                    }
+                    rec = nxt;
+                    vrow += 4 * 16;
+                }
             }
             fence_async_smem();                                      // generic-proxy stores -> visible to the tensor core
             __syncwarp();
@@ -355,16 +360,10 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 uint32_t r[32];
                 tmem_ld32(tmem_lane + 128 + col, r);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col) + q);
-                    const float4 wa = __ldg(reinterpret_cast<const float4*>(w3 + col) + q);
-                    const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + EGN_HID + col) + q);
-                    const float4 wc = __ldg(reinterpret_cast<const float4*>(w3 + 2 * EGN_HID + col) + q);
-                    const float h0 = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
-                    const float h2 = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
-                    p0 = fmaf(h0, wa.x, p0); p0 = fmaf(h1, wa.y, p0); p0 = fmaf(h2, wa.z, p0); p0 = fmaf(h3, wa.w, p0);
-                    p1 = fmaf(h0, wb.x, p1); p1 = fmaf(h1, wb.y, p1); p1 = fmaf(h2, wb.z, p1); p1 = fmaf(h3, wb.w, p1);
-                    p2 = fmaf(h0, wc.x, p2); p2 = fmaf(h1, wc.y, p2); p2 = fmaf(h2, wc.z, p2); p2 = fmaf(h3, wc.w, p2);
+                for (int j = 0; j < 32; ++j) {
+                    const float4 w = l3s[col + j];                     // broadcast LDS.128: {b2, W3[0], W3[1], W3[2]} of unit col + j
+                    const float h = fmaxf(__uint_as_float(r[j]) + w.x, 0.f);
+                    p0 = fmaf(h, w.y, p0); p1 = fmaf(h, w.z, p1); p2 = fmaf(h, w.w, p2);
                 }
             }
             tc_fence_before();

@@ -97,7 +97,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                          float* __restrict__ d_tab, float* __restrict__ d_basis0, float* __restrict__ d_basis1) {
     using L = GtLayout;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp-uniform
     const int row = tid & 127, q = tid >> 7;
     const int AD = k.app_dim;
     unsigned char* bbs = smem + L::BB;

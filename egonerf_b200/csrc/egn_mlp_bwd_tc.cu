@@ -53,7 +53,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                       float* __restrict__ dW3, float* __restrict__ db3) {
     using L = BtLayout;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp-uniform
     const int row = tid & 127, q = tid >> 7;
     const int AD = k.app_dim;
     const int in_dim = 5 * AD + 15;

@@ -57,7 +57,7 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
     constexpr int CPT = EGN_HID / NQ;              // hidden columns per thread (64 / 32)
     using L = TcLayout<SPLIT>;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // shuffle: provably warp-uniform (keeps descriptors in uniform registers)
     const int row = tid & 127, q = tid >> 7;
     const int AD = k.app_dim;
     const int in_dim = AD + 3 + 4 * AD + 12;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // retry budget would then expire without a lost arrive.  On expiry the caller traps.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+#pragma unroll 1                                             // keep the wait sites small: their code sits inside the hot loops
     for (uint32_t spin = 0; spin < 400u; ++spin) {           // the common case: a few parked waits, no timer traffic
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
