@@ -485,7 +485,7 @@ def main():
                             "tc_f16": "density channels, alpha, transmittance and compositing in fp32; appearance tables, packed-half2 "
                                       "interpolation and tcgen05 MMA operands in fp16 with fp32 accumulate (rgb within 1e-4 of the "
                                       "reference, tests/test_gpu_tc.py); backward: tcgen05 kernels with bf16 operands"}[args.mlp]
-    launches = (model.launches_per_forward() * (-(-n_rays // chunk)) if not train else model.launches_per_train_step(n_rays)) * args.steps
+    launches = (model.launches_per_forward(S) * (-(-n_rays // chunk)) if not train else model.launches_per_train_step(n_rays)) * args.steps
     e2e = {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
            "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world}
     if ms_e2e_alpha is not None:

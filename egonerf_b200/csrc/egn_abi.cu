@@ -266,8 +266,12 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     if (fused) {
         // throughput mode: one warp-specialised kernel for gather + basis + MLP; the app feature is only written
         // when a backward pass will read it (full training workspace)
-        if ((e = egn_launch_fused_fine(k, p, rays, n, z, fsig, save_feat ? feat : nullptr, rgbs, st))) return cuda_fail("fused fine pass", e);
+        // forward-only calls with whole 128-sample tiles per ray composite inside the kernel (no egn_composite_kernel launch)
+        const bool comp = !save_feat && k.S % 128 == 0;
+        if ((e = egn_launch_fused_fine(k, p, rays, n, z, fsig, save_feat ? feat : nullptr, rgbs, comp ? out : nullptr, st)))
+            return cuda_fail("fused fine pass", e);
         mark(se, 2, st);
+        if (comp) { mark(se, 3, st); mark(se, 4, st); return 0; }
     } else {
         if ((e = egn_launch_gather(k, p, rays, n, z, fsig, feat, st))) return cuda_fail("gather", e);
         mark(se, 2, st);

@@ -54,7 +54,8 @@ struct FuLayout {
     static constexpr int TMEM = MBAR + 8 * 8;
     static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4
     static constexpr int L3 = PART + TC_TM * 16;                      // layer 3: per hidden unit {b2, W3[0], W3[1], W3[2]}: 128 x float4
-    static constexpr int TOTAL = L3 + EGN_HID * 16;
+    static constexpr int RED = L3 + EGN_HID * 16;                     // fused compositing: 4 warp products + 4 x 5 warp sums
+    static constexpr int TOTAL = RED + 4 * 8 * 4;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
 
@@ -184,13 +185,20 @@ __device__ __forceinline__ uint4 fused_app_unit(const uint4* __restrict__ rec, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// COMP = true (forward-only calls with S a multiple of 128): compositing runs inside the kernel too (EgoNeRF.py:579-598,
+// tensorBase.py:22-27).  A CTA then walks whole rays (all tiles of a ray back to back); the density lanes turn the sigma
+// feature into alpha (the only per-sample output, 4 B) and write it to the caller's alpha tensor; the layer-3 epilogue reads
+// it back, runs the transmittance product scan over the tile's 128 rows (warp shuffles + 4 warp totals through shared
+// memory), carries T across the tiles of the ray and accumulates sum(w c), sum(w), sum(w z): sample colours, sigma
+// features and weights never leave the SM, and egn_composite_kernel is not launched.
+template <bool COMP>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
                       const float* __restrict__ basis1, const float* __restrict__ w1, const float* __restrict__ b1,
                       const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                       const float* __restrict__ b3, const float* __restrict__ rays, long long M,
                       const float* __restrict__ zs, float* __restrict__ fsig, float* __restrict__ feat_out,
-                      float* __restrict__ rgbs) {
+                      float* __restrict__ rgbs, const float* __restrict__ emission, EgnOutputs out) {
     using L = FuLayout;
     extern __shared__ __align__(128) unsigned char smem[];
     // warp index through a shuffle from lane 0: the compiler then KNOWS it is warp-uniform, keeps the role branches uniform and
@@ -243,6 +251,14 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     const uint32_t tmem = *s_tmem;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     bool ok = true;
+    // CTA-local iteration -> tile.  Plain: tiles strided over the CTAs.  COMP: rays strided over the CTAs, the tpr tiles of a
+    // ray consecutive (S = tpr * 128), so the transmittance can be carried from tile to tile.
+    const int tpr = COMP ? k.S / TC_TM : 1;
+    const long long n_local = COMP ? (((M / k.S) - blockIdx.x + gridDim.x - 1) / gridDim.x) * tpr
+                                   : (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    auto tile_of = [&](long long i) -> long long {
+        return COMP ? ((i / tpr) * gridDim.x + blockIdx.x) * tpr + i % tpr : blockIdx.x + i * (long long)gridDim.x;
+    };
 
     if (warp >= 8) {
         // =========================== GATHER group ===========================
@@ -252,17 +268,17 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
         const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
         YYCoord held;                                                // coordinates computed one tile ahead (lanes 16..31)
         held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < (uint32_t)n_local; ++it) {
+            const long long tile = tile_of(it);
             const uint32_t b = it & 1, u = it >> 1;
             // ---- phase 1a: coordinates.  Even iterations: lanes 0..15 take this tile's rows, lanes 16..31 the same rows of
             // the CTA's next tile (kept in `held`); odd iterations just fetch them ----
             YYCoord cc;
             if (b == 0) {
-                const long long m = (lane < 16 ? tile : tile + gridDim.x) * TC_TM + row0 + (lane & 15);
+                const long long m = (lane < 16 ? tile : tile_of(it + 1)) * TC_TM + row0 + (lane & 15);
                 cc.c[0] = cc.c[1] = cc.c[2] = -3.f;                  // out of range -> every tap gets weight zero
                 cc.yang = 0;
-                if (m < M) {
+                if (m < M && (lane < 16 || it + 1 < (uint32_t)n_local)) {
                     const float z = zs[m];
                     const float* ry = rays + (m / k.S) * 6;
                     cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
@@ -351,8 +367,27 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
             tc_commit(v_empty0 + 8 * bb);
             tc_commit(feat_full);
         };
-        // layer 3 + sigmoid of the tile whose D2 sits in TMEM (its layer-2 completion has been waited for)
+        // layer 3 + sigmoid of the tile whose D2 sits in TMEM (its layer-2 completion has been waited for); COMP: then the
+        // compositing of the tile's 128 samples (they belong to one ray), carried over the tiles of the ray
+        float carryT = 1.f, sum_w = 0.f, sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_z = 0.f;     // sums live in thread 0
+        float* red = reinterpret_cast<float*>(smem + L::RED);
+        const int acols = k.S + (k.env_h > 0 ? 1 : 0);
         auto layer3 = [&](long long gm3) {
+            // COMP: the upper-half threads (idle during the scan below) turn the row's sigma feature -- written by the gather
+            // group, read back through L2 -- into alpha (tensorBase.py:22-27 with the distances of EgoNeRF.py:541-542,553:
+            // z[j+1] - z[j], the last one repeated).  The loads are requested first and land behind the dot products.
+            float fs = 0.f, zrow = 0.f, znext = 0.f;
+            long long ray3 = 0;
+            int j3 = 0;
+            if constexpr (COMP) {
+                ray3 = gm3 / k.S;
+                j3 = (int)(gm3 - ray3 * k.S);
+                zrow = zs[gm3];
+                if (half == 1) {
+                    fs = __ldcg(fsig + gm3);
+                    znext = (j3 + 1 < k.S) ? zs[gm3 + 1] : zs[gm3 - 1];
+                }
+            }
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -367,19 +402,85 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 }
             }
             tc_fence_before();
-            if (half == 1) *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, 0.f);
+            if (half == 1) {
+                float a = 0.f;
+                if constexpr (COMP) {
+                    const float dist = ((j3 + 1 < k.S) ? (znext - zrow) : (zrow - znext)) * k.distance_scale;
+                    a = 1.f - expf(-egn_density_act(fs, k.density_shift, k.fea2dense) * dist);
+                    out.alpha[ray3 * acols + j3] = a;
+                }
+                *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, a);
+            }
             named_bar_sync(1, FU_GROUP);
             if (half == 0 && gm3 < M) {
                 const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
-                rgbs[gm3 * 3 + 0] = egn_sigmoid(p0 + q.x + bias3[0]);
-                rgbs[gm3 * 3 + 1] = egn_sigmoid(p1 + q.y + bias3[1]);
-                rgbs[gm3 * 3 + 2] = egn_sigmoid(p2 + q.z + bias3[2]);
+                const float alpha = q.w;
+                const float c0 = egn_sigmoid(p0 + q.x + bias3[0]), c1 = egn_sigmoid(p1 + q.y + bias3[1]), c2 = egn_sigmoid(p2 + q.z + bias3[2]);
+                if constexpr (!COMP) {
+                    rgbs[gm3 * 3 + 0] = c0; rgbs[gm3 * 3 + 1] = c1; rgbs[gm3 * 3 + 2] = c2;
+                } else {
+                    // transmittance: T_j = prod_{i<j} (1 - alpha_i + 1e-10) (tensorBase.py:24-26); rows = consecutive samples
+                    const int lane_ = tid & 31, w4 = tid >> 5;         // w4 in 0..3
+                    float incl = 1.f - alpha + 1e-10f;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const float o = __shfl_up_sync(FULL, incl, d);
+                        if (lane_ >= d) incl *= o;
+                    }
+                    float excl = __shfl_up_sync(FULL, incl, 1);
+                    if (lane_ == 0) excl = 1.f;
+                    if (lane_ == 31) red[w4] = incl;
+                    named_bar_sync(2, TC_TM);
+                    const float q0 = red[0], q1 = red[1], q2 = red[2], q3 = red[3];
+                    const float before = w4 == 0 ? 1.f : (w4 == 1 ? q0 : (w4 == 2 ? q0 * q1 : (q0 * q1) * q2));
+                    const float wgt = alpha * ((carryT * before) * excl);
+                    float v[5] = {wgt, wgt * c0, wgt * c1, wgt * c2, wgt * zrow};
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+                        for (int e = 0; e < 5; ++e) v[e] += __shfl_xor_sync(FULL, v[e], d);
+                    if (lane_ == 0) {
+#pragma unroll
+                        for (int e = 0; e < 5; ++e) red[4 + w4 * 5 + e] = v[e];
+                    }
+                    named_bar_sync(2, TC_TM);
+                    carryT *= ((q0 * q1) * q2) * q3;
+                    const long long ray = ray3;
+                    const bool last = j3 + TC_TM - row >= k.S;                     // this tile is the ray's last one
+                    if (tid == 0) {
+                        sum_w += (red[4] + red[9]) + (red[14] + red[19]);
+                        sum_r += (red[5] + red[10]) + (red[15] + red[20]);
+                        sum_g += (red[6] + red[11]) + (red[16] + red[21]);
+                        sum_b += (red[7] + red[12]) + (red[17] + red[22]);
+                        sum_z += (red[8] + red[13]) + (red[18] + red[23]);
+                        if (last) {
+                            const float* ry = rays + ray * 6;
+                            float cr = sum_r, cg = sum_g, cb = sum_b;
+                            if (k.env_h > 0) {                         // EgoNeRF.py:586-590
+                                float e[3];
+                                egn_env_radiance(emission, k.env_h, ry[3], ry[4], ry[5], e);
+                                const float b0 = carryT * e[0], b1 = carryT * e[1], b2v = carryT * e[2];
+                                out.env[ray * 3] = e[0]; out.env[ray * 3 + 1] = e[1]; out.env[ray * 3 + 2] = e[2];
+                                out.bg[ray * 3] = b0; out.bg[ray * 3 + 1] = b1; out.bg[ray * 3 + 2] = b2v;
+                                cr += b0; cg += b1; cb += b2v;
+                                out.alpha[ray * acols + k.S] = 1.f;     // EgoNeRF.py:587
+                            }
+                            out.rgb[ray * 3] = fminf(fmaxf(cr, 0.f), 1.f);
+                            out.rgb[ray * 3 + 1] = fminf(fmaxf(cg, 0.f), 1.f);
+                            out.rgb[ray * 3 + 2] = fminf(fmaxf(cb, 0.f), 1.f);
+                            out.depth[ray] = sum_z + (1.f - sum_w) * ry[5];     // EgoNeRF.py:598: rays_chunk[..., -1] is d_z
+                            sum_w = sum_r = sum_g = sum_b = sum_z = 0.f;
+                        }
+                    }
+                    if (last) carryT = 1.f;
+                }
             }
         };
-        if (tid == 0 && (long long)blockIdx.x < tiles) issue_layer0(0);
+        if (tid == 0 && n_local > 0) issue_layer0(0);
         uint32_t it = 0;
         long long gm_prev = M;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (; it < (uint32_t)n_local; ++it) {
+            const long long tile = tile_of(it);
             const long long gm = tile * TC_TM + row;
             const bool live = gm < M;
             // ---- layer 0 of this tile was issued one iteration ago ----
@@ -457,7 +558,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 for (int ks = 0; ks < EGN_HID / 16; ++ks)
                     tc_mma(tmem + 128, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w2_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
                 tc_commit(d2_full);
-                if (tile + gridDim.x < tiles) issue_layer0(it + 1);
+                if (it + 1 < (uint32_t)n_local) issue_layer0(it + 1);
             }
             ok &= mbar_wait(d2_full, it & 1);
             tc_fence_after();
@@ -472,13 +573,21 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 }
 
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
-                          float* fsig, float* feat_out, float* rgbs, cudaStream_t st) {
+                          float* fsig, float* feat_out, float* rgbs, const EgnOutputs* composite_out, cudaStream_t st) {
     const long long M = n * k.S;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
+    if (composite_out != nullptr) {           // compositing inside the kernel: CTAs walk whole rays
+        const int blocks = (int)(n < 148 ? n : 148);
+        cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
+        egn_fused_fine_kernel<true><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
+            k, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, z,
+            fsig, nullptr, rgbs, p->emission, *composite_out);
+        return (int)cudaGetLastError();
+    }
     const int blocks = (int)(tiles < 148 ? tiles : 148);
-    cudaFuncSetAttribute(egn_fused_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
-    egn_fused_fine_kernel<<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
+    cudaFuncSetAttribute(egn_fused_fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
+    egn_fused_fine_kernel<false><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
         k, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, z,
-        fsig, feat_out, rgbs);
+        fsig, feat_out, rgbs, nullptr, EgnOutputs{});
     return (int)cudaGetLastError();
 }

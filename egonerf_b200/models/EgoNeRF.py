@@ -654,18 +654,21 @@ class EgoNeRF(torch.nn.Module):
         total = float(vols[0].sum() + vols[1].sum())
         print("alpha rest %%%f" % (total / (2 * gridSize[0] * gridSize[1] * gridSize[2]) * 100))
 
-    def launches_per_forward(self):
-        """Kernels of libegn_b200 launched by one `forward` (sampler, gather, [MLP], composite)."""
+    def launches_per_forward(self, S=256, keep_for_backward=False):
+        """Kernels of libegn_b200 launched by one `forward`: sampler, gather, [MLP], composite -- or, in the throughput mode,
+        sampler + fused fine pass (+ composite only when the backward pass needs the per-sample state or S % 128 != 0)."""
         if not isinstance(self.renderModule, torch.nn.Module):
             return 3
         fused = self._fused_mode() and self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
-        return 3 if fused else 4
+        if fused:
+            return 2 if (not keep_for_backward and S % 128 == 0) else 3
+        return 4
 
     def launches_per_train_step(self, n_rays):
         """forward + backward (composite, per-sub-chunk MLP chain, gather) + gradient unpack + table re-pack."""
         mlp = isinstance(self.renderModule, torch.nn.Module)
         sub = -(-int(n_rays) // 4096)
-        return self.launches_per_forward() + 1 + (6 * sub if mlp else 0) + 1 + 1 + 1
+        return self.launches_per_forward(keep_for_backward=True) + 1 + (6 * sub if mlp else 0) + 1 + 1 + 1
 
     def allreduce_gradients(self, group=None, average=False):
         """Ray-sharded data parallelism: ONE all-reduce (sum) over all parameter gradients, through a
