@@ -120,7 +120,7 @@ def main():
         fine_train=fz_train, u_train=u_train)
 
     # ---- 3. whole-path renders ---------------------------------------------------------------------
-    def render_case(name, scene, rays, is_train, seed=1234, grads=False, **kw):
+    def render_case(name, scene, rays, is_train, seed=1234, grads=False, mse=False, **kw):
         co, model = build_reference(scene, kw.get("interval_th", True))
         N = rays.shape[0]
         u_c = u_f = None
@@ -142,6 +142,17 @@ def main():
         if grads:
             out = ref_render(model, rays, is_train, **kw)
             g2 = torch.Generator().manual_seed(seed + 1)
+        if grads and mse:
+            # the loss train.py:260 trains with: mean squared error against a target image (no sign cancellation between rays)
+            target = torch.rand(out[0].shape, generator=g2)
+            loss = torch.mean((out[0] - target) ** 2)
+            loss.backward()
+            store.update(target=target, loss=loss.detach())
+            for k, p in model.named_parameters():
+                store["grad:" + k] = p.grad if p.grad is not None else torch.zeros_like(p)
+            if scene.emission is not None:
+                store["grad:envmap.emission"] = model.envmap.emission.grad
+        elif grads:
             wr = torch.randn(out[0].shape, generator=g2)
             wa = torch.randn(out[4].shape, generator=g2) * 0.01
             loss = (out[0] * wr).sum() + (out[4] * wa).sum()
@@ -193,6 +204,8 @@ def main():
     # coordinates.py:132-156), coarse pass on the N_r/2 ladder
     render_case("render_tiny_plain_eval.npz", tiny, r64, False, interval_th=False)
     render_case("render_tiny_plain_train_grad.npz", tiny, r64p, True, grads=True, seed=78, interval_th=False)
+    render_case("render_tiny_train_mse_grad.npz", tiny, r64, True, grads=True, mse=True, seed=91)
+    render_case("render_tiny_env_train_mse_grad.npz", tiny_env, r64, True, grads=True, mse=True, seed=92)
     render_case("render_tiny_plain_noresample.npz", tiny, r64, False, resampling=False, n_fine=0, interval_th=False)
     co = coordinates_dict['yinyang']('cpu', tiny.aabb, exp_r=True, N_voxel=tiny.n_voxels, r0=tiny.r0, interval_th=False)
     gk = torch.Generator().manual_seed(6)

@@ -57,14 +57,17 @@ def test_full_size_properties_and_oracle_spot_check(setup):
     print(f"full size: oracle spot check rgb {err:.2e} on {int(ok.sum())} rays")
     assert err <= 1e-4
     # throughput mode: chunk independence and PSNR gate against the parity render of the whole batch
-    model.mlp_mode, model.table_dtype = "tc_bf16", "bf16"
+    model.mlp_mode, model.table_dtype = "tc_f16", "bf16"
     with torch.no_grad():
         fast = model(rays, is_train=False, **RENDER_KW)
         fparts = [model(rays[a:a + N // 4], is_train=False, ray_index0=a, **RENDER_KW) for a in range(0, N, N // 4)]
     assert torch.equal(fast[0], torch.cat([p[0] for p in fparts]))
     psnr_between = float(-10 * torch.log10(((fast[0] - rgb) ** 2).mean()))
-    print(f"full size: throughput vs parity render, PSNR between {psnr_between:.1f} dB, Linf {float((fast[0] - rgb).abs().max()):.2e}")
-    assert psnr_between >= 60.0
+    linf = float((fast[0] - rgb).abs().max())
+    err_fast = (fast[0][idx.cuda()].cpu() - ref[0]).abs()[ok].max().item()
+    print(f"full size: throughput vs parity render, PSNR between {psnr_between:.1f} dB, Linf {linf:.2e}; throughput vs oracle {err_fast:.2e}")
+    assert psnr_between >= 100.0 and linf <= 3e-5          # measured 110 dB / 1.0e-5 (profiles/r02_parity.md)
+    assert err_fast <= 1e-4                                # the headline mode itself is inside the north_star bound
 
 
 def test_full_size_weights_telescope_and_gradient_shards_add(setup):
