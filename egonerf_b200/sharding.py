@@ -58,11 +58,13 @@ class GradientBucket:
             self.flat.div_(dist.get_world_size(group))
 
 
-def gather_env_gradient(model, group=None, average=False):
+def gather_env_gradient(model, group=None, average=False, equal_counts=True):
     """Envmap gradient of a ray-sharded step without the dense all-reduce: the backward pass left, per ray, the gradient
     w.r.t. its env radiance (`model._env_rays`, filled when `model.sparse_env_grad` is set); ranks all-gather directions +
     gradients (24 B / ray; 0.4 MB per rank at 16 384 rays against 88 MB for the dense (3, 3840, 1920) tensor) and every rank
-    scatters ALL rays into its own dense gradient with `egn_envmap_backward` -- the same sum, computed locally."""
+    scatters ALL rays into its own dense gradient with `egn_envmap_backward` -- the same sum, computed locally.
+    `equal_counts` (the ray-sharded launcher's contract: every rank steps the same batch size) skips the exchange of the
+    per-rank ray counts, which would cost two host synchronisations per step."""
     from . import _lib
     em = model.envmap.emission
     if not model._env_rays:
@@ -72,17 +74,16 @@ def gather_env_gradient(model, group=None, average=False):
     model._env_rays = []
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     if world > 1:
-        n_local = torch.tensor([packed.shape[0]], device=em.device, dtype=torch.int64)
-        counts = [torch.zeros_like(n_local) for _ in range(world)]
-        dist.all_gather(counts, n_local, group=group)
-        counts = [int(c.item()) for c in counts]
-        n_max = max(counts)
-        if n_max == 0:
-            em.grad = torch.zeros_like(em)
-            return
-        padded = torch.zeros(n_max, 6, device=em.device)
-        padded[:packed.shape[0]] = packed                      # padding rows carry zero gradient: they scatter nothing
-        gathered = torch.empty(world * n_max, 6, device=em.device)
+        if equal_counts:
+            padded = packed
+        else:
+            n_local = torch.tensor([packed.shape[0]], device=em.device, dtype=torch.int64)
+            counts = [torch.zeros_like(n_local) for _ in range(world)]
+            dist.all_gather(counts, n_local, group=group)
+            n_max = max(int(c.item()) for c in counts)
+            padded = torch.zeros(n_max, 6, device=em.device)
+            padded[:packed.shape[0]] = packed                  # padding rows carry zero gradient: they scatter nothing
+        gathered = torch.empty(world * padded.shape[0], 6, device=em.device)
         dist.all_gather_into_tensor(gathered, padded, group=group)
         packed = gathered
     d_em = torch.zeros_like(em)

@@ -18,6 +18,8 @@ RENDER_CASES = {
     "render_tiny_env_eval": (TINY_ENV, {}),
     "render_tiny_env_train_grad": (TINY_ENV, {}),
     "render_tiny_train_grad": (TINY, {}),
+    "render_tiny_train_mse_grad": (TINY, {}),           # gradients of the MSE training loss (train.py:260)
+    "render_tiny_env_train_mse_grad": (TINY_ENV, {}),
     "render_tiny_noresample": (TINY, dict(resampling=False, n_fine=0)),
     "render_tiny_fineonly": (TINY, dict(use_coarse_sample=False)),
     "render_128_eval": (dict(n_voxels=128 ** 3), {}),

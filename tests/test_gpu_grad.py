@@ -346,3 +346,27 @@ def test_table_adam_keeps_regulariser_gradients(fused_reg):
         d = float((ref[k] - tab[k]).abs().mean())
         assert moved > 1e-3, (k, moved)                          # 3 Adam steps of lr 0.02 did move the tensor
         assert d <= 0.02 * moved, (k, d, moved)                  # and both optimisers moved it the same way
+
+
+def test_sparse_envmap_gradient_equals_the_dense_one():
+    """Ray-sharded training exchanges the envmap gradient as 24 B per ray (direction + d loss / d env radiance) and scatters
+    locally (`sharding.gather_env_gradient`) instead of all-reducing the dense (3, 2h, h) tensor: same gradient."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays
+    scene = scene_for(dict(n_voxels=40 ** 3, seed=8, envmap_h=32, near_far=(0.1, 300.), r0=0.05, density_shift=-10.))
+    rays = make_rays(512, 'isotropic', seed=3).cuda()
+    target = torch.rand(512, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    grads = {}
+    for sparse in (False, True):
+        model = model_from_scene(scene)
+        model.sparse_env_grad = sparse
+        out = model(rays, is_train=True, seed=7, **RENDER_KW)
+        (((out[0] - target) ** 2).mean() + out[3].mean() * 0.1 + out[2].sum() * 0.01).backward()
+        if sparse:
+            assert model.envmap.emission.grad is None
+            model.allreduce_gradients(average=False)            # world size 1: local scatter of the per-ray gradients
+        grads[sparse] = model.envmap.emission.grad.clone()
+        assert model._env_rays == []
+    ref = grads[False]
+    assert float(ref.abs().max()) > 0
+    assert float((grads[True] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
