@@ -179,7 +179,7 @@ extern "C" int32_t egn_regularize_tables(const EgnConfig* c, const float* tables
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
 #define EGN_BWD_SUB_RAYS 4096
-struct WsPlan { long long z, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, eval_total, total; };
+struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, eval_total, total; };
 // the fused fine pass keeps the r ladder in shared memory (EGN_FUSED_MAX_KNOTS entries); larger grids take the unfused kernels
 static bool is_fused(const EgnConfig* c) {
     return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_F16 && c->grid[0] + 3 <= EGN_FUSED_MAX_KNOTS;
@@ -193,7 +193,9 @@ static WsPlan plan_ws(const EgnConfig* c, long long n) {
     WsPlan w;
     long long off = 0;
     auto take = [&](long long floats) { long long o = off; off += align256(floats * 4); return o; };
-    w.z = take(M); w.fsig = take(M); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n); w.rgbpre = take(n * 3);
+    w.z = take(M);
+    w.image = off; off += align256(is_fused(c) ? egn_fused_image_bytes() : 0);       // MLP operand image of the fused fine pass
+    w.fsig = take(M); w.rgbs = take(M * 3); w.wgt = take(M); w.bgw = take(n); w.rgbpre = take(n * 3);
     // the fused fine pass never materialises the app feature in eval mode: 24 B/sample instead of 136
     const long long eval_fused = off;
     w.feat = take(M * EGN_FEAT_STRIDE);
@@ -268,7 +270,7 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
         // when a backward pass will read it (full training workspace)
         // forward-only calls with whole 128-sample tiles per ray composite inside the kernel (no egn_composite_kernel launch)
         const bool comp = !save_feat && k.S % 128 == 0;
-        if ((e = egn_launch_fused_fine(k, p, rays, n, z, fsig, save_feat ? feat : nullptr, rgbs, comp ? out : nullptr, st)))
+        if ((e = egn_launch_fused_fine(k, p, rays, n, z, fsig, save_feat ? feat : nullptr, rgbs, comp ? out : nullptr, base + w.image, st)))
             return cuda_fail("fused fine pass", e);
         mark(se, 2, st);
         if (comp) { mark(se, 3, st); mark(se, 4, st); return 0; }

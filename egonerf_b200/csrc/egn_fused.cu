@@ -45,7 +45,9 @@ struct FuLayout {
     static constexpr int W1 = 0;
     static constexpr int W2 = W1 + (TC_K1 / 8) * TC_CHUNK;            // 40 960
     static constexpr int BB = W2 + (EGN_HID / 8) * TC_CHUNK;          // + 32 768
-    static constexpr int A = BB + FU_VCHUNKS * FU_BB_CHUNK;           // + 18 432
+    static constexpr int L3 = BB + FU_VCHUNKS * FU_BB_CHUNK;          // + 18 432; layer 3: per hidden unit {b2, W3[0], W3[1], W3[2]}: 128 x float4
+    static constexpr int IMAGE = L3 + EGN_HID * 16;                   // W1 .. L3 = the operand image, one bulk copy (94 208 bytes)
+    static constexpr int A = IMAGE;
     static constexpr int V = A + (TC_K1 / 8) * TC_CHUNK;              // + 40 960 ; two buffers
     static constexpr int REC = V + 2 * FU_VBYTES;                     // address records: 128 samples x 144 B
     static constexpr int YANG = REC + 8 * (16 * (FU_REC_WORDS / 4) + 1) * 16;   // 8 warps x (16 records + 1 swizzle slot); then 4 x 128 bytes
@@ -53,8 +55,7 @@ struct FuLayout {
     static constexpr int MBAR = KNOTS + ((EGN_FUSED_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
     static constexpr int TMEM = MBAR + 8 * 8;
     static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4
-    static constexpr int L3 = PART + TC_TM * 16;                      // layer 3: per hidden unit {b2, W3[0], W3[1], W3[2]}: 128 x float4
-    static constexpr int RED = L3 + EGN_HID * 16;                     // fused compositing: 4 warp products + 4 x 5 warp sums
+    static constexpr int RED = PART + TC_TM * 16;                     // fused compositing: 4 warp products + 4 x 5 warp sums
     static constexpr int TOTAL = RED + 4 * 8 * 4;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
@@ -185,6 +186,34 @@ __device__ __forceinline__ uint4 fused_app_unit(const uint4* __restrict__ rec, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// Operand image of the MLP: W1 (bias folded in, PE column order), W2, [B_yin | B_yang] as fp16 canonical K-major tcgen05 tiles
+// and the layer-3 table, laid out exactly as the fused kernel keeps them in shared memory (FuLayout W1 .. L3).  Built once
+// per launch by this small kernel; every CTA then fetches it with ONE bulk copy (cp.async.bulk -> mbarrier, SASS UBLKCP)
+// instead of 512 threads converting ~46 000 scattered fp32 weights per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+egn_fused_image_kernel(int AD, const float* __restrict__ basis0, const float* __restrict__ basis1, const float* __restrict__ w1,
+                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                       const float* __restrict__ w3, unsigned char* __restrict__ img) {
+    using L = FuLayout;
+    const int in_dim = 5 * AD + 15;
+    const int nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i < EGN_HID * TC_K1; i += nthreads) {
+        const int n = i / TC_K1, kk = i % TC_K1;
+        const int src = tc_input_index(kk, AD);
+        store_elem_h(img + L::W1, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
+    }
+    for (int i = t0; i < EGN_HID * EGN_HID; i += nthreads) store_elem_h(img + L::W2, i / EGN_HID, i % EGN_HID, w2[i]);
+    for (int i = t0; i < 64 * FU_VK; i += nthreads) {               // rows 0..31: basis_mat_yin, 32..63: basis_mat_yang
+        const int n = i / FU_VK, kk = i % FU_VK, o = n & 31;
+        const float* B = (n >> 5) ? basis1 : basis0;
+        store_elem_h(img + L::BB, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
+    }
+    for (int i = t0; i < EGN_HID; i += nthreads)
+        reinterpret_cast<float4*>(img + L::L3)[i] = make_float4(b2[i], w3[i], w3[EGN_HID + i], w3[2 * EGN_HID + i]);
+}
+
 // COMP = true (forward-only calls with S a multiple of 128): compositing runs inside the kernel too (EgoNeRF.py:579-598,
 // tensorBase.py:22-27).  A CTA then walks whole rays (all tiles of a ray back to back); the density lanes turn the sigma
 // feature into alpha (the only per-sample output, 4 B) and write it to the caller's alpha tensor; the layer-3 epilogue reads
@@ -193,9 +222,7 @@ __device__ __forceinline__ uint4 fused_app_unit(const uint4* __restrict__ rec, i
 // features and weights never leave the SM, and egn_composite_kernel is not launched.
 template <bool COMP>
 __global__ void __launch_bounds__(FU_THREADS, 1)
-egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
-                      const float* __restrict__ basis1, const float* __restrict__ w1, const float* __restrict__ b1,
-                      const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned char* __restrict__ image,
                       const float* __restrict__ b3, const float* __restrict__ rays, long long M,
                       const float* __restrict__ zs, float* __restrict__ fsig, float* __restrict__ feat_out,
                       float* __restrict__ rgbs, const float* __restrict__ emission, EgnOutputs out) {
@@ -205,7 +232,6 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     // the load descriptors in uniform registers (without it every LDG of the kernel was preceded by two R2UR moves)
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int AD = k.app_dim;
-    const int in_dim = 5 * AD + 15;
     unsigned char* w1s = smem + L::W1;
     unsigned char* w2s = smem + L::W2;
     unsigned char* bbs = smem + L::BB;
@@ -217,7 +243,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     float4* l3s = reinterpret_cast<float4*>(smem + L::L3);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
     const uint32_t bar = smem_u32(smem + L::MBAR);
-    const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48;
+    const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48, img_full = bar + 56;
 
     // ---- one-time setup ----
     if (warp == 0) {
@@ -227,30 +253,21 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     if (tid == 32) {
         mbar_init(v_full0, 8); mbar_init(v_full0 + 8, 8);          // one arrive per gather warp
         mbar_init(v_empty0, 1); mbar_init(v_empty0 + 8, 1);        // tcgen05.commit
-        mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1);
+        mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(img_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < EGN_HID * TC_K1; i += FU_THREADS) {
-        const int n = i / TC_K1, kk = i % TC_K1;
-        const int src = tc_input_index(kk, AD);
-        store_elem_h(w1s, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
-    }
-    for (int i = tid; i < EGN_HID * EGN_HID; i += FU_THREADS) store_elem_h(w2s, i / EGN_HID, i % EGN_HID, w2[i]);
-    for (int i = tid; i < 64 * FU_VK; i += FU_THREADS) {            // rows 0..31: basis_mat_yin, 32..63: basis_mat_yang
-        const int n = i / FU_VK, kk = i % FU_VK, o = n & 31;
-        const float* B = (n >> 5) ? basis1 : basis0;
-        store_elem_h(bbs, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
+        // the operand image (W1, W2, basis, layer-3 table: FuLayout W1 .. IMAGE) in one bulk copy, completion on img_full
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(img_full), "r"((uint32_t)L::IMAGE) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(smem + L::W1)), "l"(image), "r"((uint32_t)L::IMAGE), "r"(img_full) : "memory");
     }
     for (int i = tid; i <= k.knots_last; i += FU_THREADS) s_knots[i] = k.r_knots[i];
-    // layer-3 operands next to the SM: this kernel's shared memory leaves no L1, a global load here is an L2 round trip
-    for (int i = tid; i < EGN_HID; i += FU_THREADS) l3s[i] = make_float4(b2[i], w3[i], w3[EGN_HID + i], w3[2 * EGN_HID + i]);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
-    bool ok = true;
+    bool ok = mbar_wait(img_full, 0);                           // operand image landed (async-proxy write -> visible after the wait)
     // CTA-local iteration -> tile.  Plain: tiles strided over the CTAs.  COMP: rays strided over the CTAs, the tpr tiles of a
     // ray consecutive (S = tpr * 128), so the transmittance can be carried from tile to tile.
     const int tpr = COMP ? k.S / TC_TM : 1;
@@ -573,21 +590,26 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 }
 
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
-                          float* fsig, float* feat_out, float* rgbs, const EgnOutputs* composite_out, cudaStream_t st) {
+                          float* fsig, float* feat_out, float* rgbs, const EgnOutputs* composite_out, void* image_buf,
+                          cudaStream_t st) {
     const long long M = n * k.S;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
+    unsigned char* img = reinterpret_cast<unsigned char*>(image_buf);
+    egn_fused_image_kernel<<<48, 256, 0, st>>>(k.app_dim, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1],
+                                               p->mlp_w[2], img);
     if (composite_out != nullptr) {           // compositing inside the kernel: CTAs walk whole rays
         const int blocks = (int)(n < 148 ? n : 148);
         cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
-        egn_fused_fine_kernel<true><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
-            k, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, z,
-            fsig, nullptr, rgbs, p->emission, *composite_out);
+        egn_fused_fine_kernel<true><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(k, img, p->mlp_b[2], rays, M, z, fsig, nullptr, rgbs,
+                                                                                 p->emission, *composite_out);
         return (int)cudaGetLastError();
     }
     const int blocks = (int)(tiles < 148 ? tiles : 148);
     cudaFuncSetAttribute(egn_fused_fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
-    egn_fused_fine_kernel<false><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(
-        k, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], p->mlp_b[2], rays, M, z,
-        fsig, feat_out, rgbs, nullptr, EgnOutputs{});
+    egn_fused_fine_kernel<false><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(k, img, p->mlp_b[2], rays, M, z, fsig, feat_out, rgbs,
+                                                                              nullptr, EgnOutputs{});
     return (int)cudaGetLastError();
 }
+
+// bytes of the operand image a caller of egn_launch_fused_fine must provide (16-byte aligned)
+long long egn_fused_image_bytes() { return FuLayout::IMAGE; }

@@ -28,7 +28,9 @@ int egn_launch_mlp_tc(const EgnKernelCfg& k, const EgnParams* p, const float* ra
                       float* rgbs, int split, cudaStream_t st);
 // fused fine pass (egn_fused.cu): gather + basis + MLP in one warp-specialised tcgen05 kernel (bf16 operands)
 int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
-                          float* fsig, float* feat_out, float* rgbs, const EgnOutputs* composite_out, cudaStream_t st);
+                          float* fsig, float* feat_out, float* rgbs, const EgnOutputs* composite_out, void* image_buf,
+                          cudaStream_t st);
+long long egn_fused_image_bytes();
 int egn_launch_adam_tables(const EgnConfig* cfg, const EgnGrads* params_out, const float* d_tables, float* m, float* v,
                            float* tables, void* tables_bf16, void* tables_h, float lr, float beta1, float beta2, float eps,
                            int step, cudaStream_t st);
