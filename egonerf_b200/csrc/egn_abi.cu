@@ -179,7 +179,7 @@ extern "C" int32_t egn_regularize_tables(const EgnConfig* c, const float* tables
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
 #define EGN_BWD_SUB_RAYS 4096
-struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, h1, h2, dz1, dz2, eval_total, total; };
+struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, gmax, h1, h2, dz1, dz2, eval_total, total; };
 // the fused fine pass keeps the r ladder in shared memory (EGN_FUSED_MAX_KNOTS entries); larger grids take the unfused kernels
 static bool is_fused(const EgnConfig* c) {
     return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_F16 && c->grid[0] + 3 <= EGN_FUSED_MAX_KNOTS;
@@ -201,6 +201,7 @@ static WsPlan plan_ws(const EgnConfig* c, long long n) {
     w.feat = take(M * EGN_FEAT_STRIDE);
     w.eval_total = is_fused(c) ? eval_fused : off;
     w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
+    w.gmax = take(1);                                                    // launch-wide max |d(sample colour)| (tcgen05 backward)
     const bool mlp = c->shading <= EGN_SHADE_MLP && !tc_backward(c);   // the tcgen05 backward needs no scratch
     const long long Ms = (n < EGN_BWD_SUB_RAYS ? n : EGN_BWD_SUB_RAYS) * S;
     w.h1 = take(mlp ? Ms * EGN_HID : 0); w.h2 = take(mlp ? Ms * EGN_HID : 0);
@@ -373,11 +374,12 @@ extern "C" int32_t egn_render_backward_sparse_env(const EgnConfig* c, const EgnP
     float* d_rgbs = (float*)(base + w.d_rgbs);
     float* d_fsig = (float*)(base + w.d_fsig);
     float* d_feat = (float*)(base + w.d_feat);
+    unsigned* gmax = (mlp && tc_backward(c)) ? (unsigned*)(base + w.gmax) : nullptr;
     int e;
     if ((e = egn_launch_composite_bwd(k, p, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs,
-                                      d_fsig, d_feat, g->emission, c->env_h > 0 ? d_env_rays : nullptr, st))) return cuda_fail("composite backward", e);
+                                      d_fsig, d_feat, g->emission, c->env_h > 0 ? d_env_rays : nullptr, gmax, st))) return cuda_fail("composite backward", e);
     if (mlp && tc_backward(c)) {
-        if ((e = egn_launch_mlp_bwd_tc(k, p, rays, n, feat, rgbs, d_rgbs, d_feat, g, st))) return cuda_fail("mlp backward (tcgen05)", e);
+        if ((e = egn_launch_mlp_bwd_tc(k, p, rays, n, feat, rgbs, d_rgbs, gmax, d_feat, g, st))) return cuda_fail("mlp backward (tcgen05)", e);
     } else if (mlp) {
         float* h1 = (float*)(base + w.h1); float* h2 = (float*)(base + w.h2);
         float* dz1 = (float*)(base + w.dz1); float* dz2 = (float*)(base + w.dz2);
@@ -389,7 +391,7 @@ extern "C" int32_t egn_render_backward_sparse_env(const EgnConfig* c, const EgnP
         }
     }
     if (tc_backward(c))
-        e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);
+        e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, gmax, d_tables, g, st);
     else
         e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);
     if (e) return cuda_fail("gather backward", e);

@@ -21,7 +21,7 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                          const float* __restrict__ rgbpre, const float* __restrict__ d_rgb, const float* __restrict__ d_bg,
                          const float* __restrict__ d_env, const float* __restrict__ d_alpha, float* __restrict__ d_rgbs,
                          float* __restrict__ d_fsig, float* __restrict__ d_feat, float* __restrict__ d_emission,
-                         float* __restrict__ d_env_rays) {
+                         float* __restrict__ d_env_rays, unsigned* __restrict__ gmax_bits) {
     const int lane = threadIdx.x & 31;
     const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (ray >= n) return;
@@ -100,7 +100,7 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         }
     }
     // forward walk: weights, d(colour), lane-local sum of dw * w
-    float sl = 0.f;
+    float sl = 0.f, gmx = 0.f;
 #pragma unroll
     for (int q = 0; q < K4_MAXE; ++q) {
         if (q < cnt) {
@@ -128,8 +128,17 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 d_feat[m * EGN_FEAT_STRIDE + 27] = 0.f;
             } else {
                 d_rgbs[m * 3] = w * g[0]; d_rgbs[m * 3 + 1] = w * g[1]; d_rgbs[m * 3 + 2] = w * g[2];
+                gmx = fmaxf(gmx, w);
             }
         }
+    }
+    // launch-wide max |d(sample colour)| for the fp16 gradient operands of the tcgen05 backward (tc_grad_scale, egn_tc.cuh);
+    // non-negative floats order like their bit patterns
+    if (gmax_bits != nullptr) {
+        gmx *= fmaxf(fabsf(g[0]), fmaxf(fabsf(g[1]), fabsf(g[2])));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) gmx = fmaxf(gmx, __shfl_xor_sync(FULL, gmx, d));
+        if (lane == 0 && gmx > 0.f) atomicMax(gmax_bits, __float_as_uint(gmx));
     }
     // exclusive suffix over lanes
     float suf = sl;
@@ -153,10 +162,15 @@ egn_composite_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,
                              const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
-                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, float* d_env_rays, cudaStream_t st) {
+                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, float* d_env_rays,
+                             unsigned* gmax_bits, cudaStream_t st) {
     long long threads = n * 32;
+    if (gmax_bits != nullptr) {
+        const int e = (int)cudaMemsetAsync(gmax_bits, 0, sizeof(unsigned), st);
+        if (e) return e;
+    }
     egn_composite_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        k, p->emission, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs, d_fsig, d_feat, d_emission, d_env_rays);
+        k, p->emission, rays, n, z, fsig, feat, rgbs, rgbpre, d_rgb, d_bg, d_env, d_alpha, d_rgbs, d_fsig, d_feat, d_emission, d_env_rays, gmax_bits);
     return (int)cudaGetLastError();
 }
 

@@ -60,20 +60,6 @@ struct FuLayout {
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
 
-// two floats -> packed fp16 pair (first value in the low half), round to nearest, saturating instead of overflowing to inf
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-}
-__device__ __forceinline__ void store_chunk_h(unsigned char* base, int chunk, int row, const float* v) {
-    uint4 h;
-    h.x = pack_h2(v[0], v[1]); h.y = pack_h2(v[2], v[3]); h.z = pack_h2(v[4], v[5]); h.w = pack_h2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(base + chunk * TC_CHUNK + row * 16) = h;
-}
-__device__ __forceinline__ void store_elem_h(unsigned char* base, int row, int kk, float x, int chunk_bytes = TC_CHUNK) {
-    *reinterpret_cast<__half*>(base + (kk >> 3) * chunk_bytes + row * 16 + (kk & 7) * 2) = __float2half_rn(x);
-}
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 

@@ -4,7 +4,7 @@
 //
 // Per 128-sample tile, one CTA per SM, 512 threads:
 //   Ph0  warp w: Yin-Yang coordinates + d(sigma feature) of rows 8w..8w+7 (kept in registers), hemisphere flags -> smem
-//   Ph1  thread (row, q): 8 values of d_feat -> bf16 tile dF2[128][64] (column block 32*hemisphere, other block zero)
+//   Ph1  thread (row, q): 8 values of d_feat -> fp16 tile S * dF2[128][64] (S: launch-wide power of two, tc_grad_scale()) (column block 32*hemisphere, other block zero)
 //        MMA1  dV[128 x 144] = dF2 . [B_yin ; B_yang]        (A K-major K = 64; B = MN-major view of the basis operand)
 //   Ph2  dV: TMEM -> fp32 smem tile (rows -> the gather lanes that need them)
 //   Ph3  warp w, half-warp per sample: re-gather the 18 taps (branch-free clamped loads), P, L, v = P*L;
@@ -20,8 +20,8 @@
 #define GT_BB_CHUNK 1024
 #define GT_DVS 148                         // dv smem row stride (floats)
 #define GT_VCHUNK (TC_CHUNK + 64)          // padded K-chunk stride of the V tile (bank-conflict-free row stores, see egn_fused.cu)
-#define IDESC_DV 0x08250490u               // M128 N144, A K-major, B MN-major
-#define IDESC_DB 0x08258490u               // M128 N144, A MN-major, B MN-major
+#define IDESC_DV TC_IDESC_F16(0x08250490u)               // M128 N144, A K-major, B MN-major
+#define IDESC_DB TC_IDESC_F16(0x08258490u)               // M128 N144, A MN-major, B MN-major
 #define GT_TM_DV 0
 #define GT_TM_DB 160
 
@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
                          const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
                          const float* __restrict__ zs, const float* __restrict__ d_fsig, const float* __restrict__ d_feat,
-                         float* __restrict__ d_tab, float* __restrict__ d_basis0, float* __restrict__ d_basis1) {
+                         const unsigned* __restrict__ gmax_bits, float* __restrict__ d_tab, float* __restrict__ d_basis0,
+                         float* __restrict__ d_basis1) {
     using L = GtLayout;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp-uniform
@@ -123,7 +124,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     for (int i = tid; i < 64 * GT_VK; i += GT_THREADS) {
         const int n = i / GT_VK, kk = i % GT_VK, o = n & 31;
         const float* B = (n >> 5) ? basis1 : basis0;
-        store_elem(bbs, nullptr, false, n, kk, o < AD ? B[o * GT_VK + kk] : 0.f, GT_BB_CHUNK);
+        store_elem_h(bbs, n, kk, o < AD ? B[o * GT_VK + kk] : 0.f, GT_BB_CHUNK);
     }
     for (int i = tid; i < 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i <= k.knots_last; i += GT_THREADS) s_knots[i] = k.r_knots[i];
@@ -135,6 +136,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bb_s = smem_u32(bbs), df_s = smem_u32(dfs), v_s = smem_u32(vs);
     const int sub = lane & 15;
+    float inv_scale;
+    const float scale = tc_grad_scale(gmax_bits, inv_scale);
 
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     uint32_t it = 0;
@@ -150,8 +153,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             if (gm < M) {
                 const float4* f4 = reinterpret_cast<const float4*>(d_feat + gm * EGN_FEAT_STRIDE) + 2 * q;
                 const float4 a = __ldg(f4);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                if (q < 3) { const float4 b = __ldg(f4 + 1); v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+                v[0] = a.x * scale; v[1] = a.y * scale; v[2] = a.z * scale; v[3] = a.w * scale;
+                if (q < 3) { const float4 b = __ldg(f4 + 1); v[4] = b.x * scale; v[5] = b.y * scale; v[6] = b.z * scale; v[7] = b.w * scale; }
             }
         }
         // ---- Ph0. coordinates + d(sigma feature) of the tile's 128 samples: one sample per lane of warps 0..3 -> smem ----
@@ -180,8 +183,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         {
             const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int yang = s_yang[row];
-            store_chunk<false>(dfs, nullptr, 4 * yang + q, row, v);
-            store_chunk<false>(dfs, nullptr, 4 * (1 - yang) + q, row, zero);
+            store_chunk_h(dfs, 4 * yang + q, row, v);
+            store_chunk_h(dfs, 4 * (1 - yang) + q, row, zero);
         }
         fence_async_smem();
         tc_fence_before();
@@ -203,8 +206,10 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             float4* dst = reinterpret_cast<float4*>(dvs + row * GT_DVS + 36 * q);
 #pragma unroll
             for (int g = 0; g < 8; ++g)
-                dst[g] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-            dst[8] = make_float4(__uint_as_float(r4[0]), __uint_as_float(r4[1]), __uint_as_float(r4[2]), __uint_as_float(r4[3]));
+                dst[g] = make_float4(__uint_as_float(r[4 * g]) * inv_scale, __uint_as_float(r[4 * g + 1]) * inv_scale,
+                                     __uint_as_float(r[4 * g + 2]) * inv_scale, __uint_as_float(r[4 * g + 3]) * inv_scale);
+            dst[8] = make_float4(__uint_as_float(r4[0]) * inv_scale, __uint_as_float(r4[1]) * inv_scale, __uint_as_float(r4[2]) * inv_scale,
+                                 __uint_as_float(r4[3]) * inv_scale);
         }
         tc_fence_before();
         __syncthreads();
@@ -288,7 +293,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                     const int kk = i * EGN_CA + (sub - EGN_CS / 4) * 4;
                     up = *reinterpret_cast<const float4*>(dvs + srow * GT_DVS + kk);
                     *reinterpret_cast<uint2*>(vs + (kk >> 3) * GT_VCHUNK + srow * 16 + (kk & 7) * 2) =
-                        make_uint2(pack_hi(prod.x, prod.y), pack_hi(prod.z, prod.w));
+                        make_uint2(pack_h2(prod.x, prod.y), pack_h2(prod.z, prod.w));
                 }
                 if (slive) {
                     const float4 dP = f4mul(up, Lv), dL = f4mul(up, P);
@@ -347,9 +352,9 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         float* dB = (row >> 5) ? d_basis1 : d_basis0;
         if (o < AD && dB != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dB + o * GT_VK + 36 * q + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(dB + o * GT_VK + 36 * q + j, __uint_as_float(r[j]) * inv_scale);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) atomicAdd(dB + o * GT_VK + 36 * q + 32 + j, __uint_as_float(r4[j]));
+            for (int j = 0; j < 4; ++j) atomicAdd(dB + o * GT_VK + 36 * q + 32 + j, __uint_as_float(r4[j]) * inv_scale);
         }
     }
     tc_fence_before();
@@ -358,7 +363,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 }
 
 int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
-                             const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st) {
+                             const float* d_fsig, const float* d_feat, const unsigned* gmax_bits, float* d_tables, const EgnGrads* g,
+                             cudaStream_t st) {
     const long long M = n * k.S;
     if (M <= 0) return 0;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
@@ -366,11 +372,11 @@ int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const fl
     if (k.tables_bf16 != nullptr) {
         cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
         egn_gather_bwd_tc_kernel<true><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
-                                                                                     d_feat, d_tables, g->basis[0], g->basis[1]);
+                                                                                     d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1]);
     } else {
         cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
         egn_gather_bwd_tc_kernel<false><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
-                                                                                      d_feat, d_tables, g->basis[0], g->basis[1]);
+                                                                                      d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1]);
     }
     return (int)cudaGetLastError();
 }

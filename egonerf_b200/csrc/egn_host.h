@@ -46,16 +46,20 @@ int egn_launch_erp_rays(int H, int W, int row0, int n_rows, const float* c2w_hos
 int egn_launch_composite_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* fsig, const float* feat, const float* rgbs, const float* rgbpre,
                              const float* d_rgb, const float* d_bg, const float* d_env, const float* d_alpha,
-                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, float* d_env_rays, cudaStream_t st);
+                             float* d_rgbs, float* d_fsig, float* d_feat, float* d_emission, float* d_env_rays,
+                             unsigned* gmax_bits, cudaStream_t st);
 // MLP backward of a sub-chunk of n rays: recomputes the hidden activations into scratch (h1, h2, dz1, dz2: n*S x 128 floats)
 int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                        const float* rgbs, const float* d_rgbs, float* d_feat, float* h1, float* h2, float* dz1,
                        float* dz2, const EgnGrads* g, cudaStream_t st);
-// tensor-core MLP backward of the whole chunk (throughput mode): no scratch, weight gradients accumulated in TMEM
+// tensor-core MLP backward of the whole chunk (throughput mode): no scratch, weight gradients accumulated in TMEM.
+// gmax_bits: largest |d(sample colour)| of the launch as float bits (egn_launch_composite_bwd) -> tc_grad_scale()
 int egn_launch_mlp_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
-                          const float* rgbs, const float* d_rgbs, float* d_feat, const EgnGrads* g, cudaStream_t st);
+                          const float* rgbs, const float* d_rgbs, const unsigned* gmax_bits, float* d_feat, const EgnGrads* g,
+                          cudaStream_t st);
 int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
-                             const float* d_fsig, const float* d_feat, float* d_tables, const EgnGrads* g, cudaStream_t st);
+                             const float* d_fsig, const float* d_feat, const unsigned* gmax_bits, float* d_tables, const EgnGrads* g,
+                             cudaStream_t st);
 int egn_launch_mlp_save(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                         float* h1, float* h2, cudaStream_t st);
 int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,

@@ -1,5 +1,9 @@
-// Backward of the colour-decode MLP on the tensor cores (tcgen05 + TMEM), bf16 operands / fp32 accumulation — the
+// Backward of the colour-decode MLP on the tensor cores (tcgen05 + TMEM), fp16 operands / fp32 accumulation — the
 // throughput-mode counterpart of egn_mlp_bwd.cu (which stays the exact-fp32 reference implementation).
+// Activations and weights are fp16 exactly as in the fused forward (same recomputed H1 / H2, same relu masks); the
+// gradient operands dO, dZ2, dZ1 are fp16 after multiplication by the launch-wide power of two S of tc_grad_scale()
+// (egn_tc.cuh), every fp32 result is multiplied by 1/S.  Against bf16 operands this cuts the rounding error of every
+// operand 8x (measured per-tensor error vs the reference's gradients: profiles/r02_parity.md).
 //
 // Per 128-sample tile (one CTA per SM, 512 threads = 4 threads per row, 32 / 40 columns each):
 //   recompute   X -> D1 = X W1^T -> H1 = relu -> D2 = H1 W2^T (+b2 through a constant-1 column) -> H2 = relu
@@ -17,12 +21,12 @@
 
 #define BT_THREADS 512
 #define BT_K2 144                        // hidden width + constant-1 column, padded to a multiple of 16
-#define IDESC_F      0x08200490u         // M128 N128, A K-major, B K-major
-#define IDESC_B3W    0x08048490u         // M128 N16,  A MN-major, B K-major
-#define IDESC_B2X    0x08210490u         // M128 N128, A K-major,  B MN-major
-#define IDESC_B2W    0x08258490u         // M128 N144, A MN-major, B MN-major
-#define IDESC_B1X    0x08290490u         // M128 N160, A K-major,  B MN-major
-#define IDESC_B1W    0x08298490u         // M128 N160, A MN-major, B MN-major
+#define IDESC_F      TC_IDESC_F16(0x08200490u)         // M128 N128, A K-major, B K-major
+#define IDESC_B3W    TC_IDESC_F16(0x08048490u)         // M128 N16,  A MN-major, B K-major
+#define IDESC_B2X    TC_IDESC_F16(0x08210490u)         // M128 N128, A K-major,  B MN-major
+#define IDESC_B2W    TC_IDESC_F16(0x08258490u)         // M128 N144, A MN-major, B MN-major
+#define IDESC_B1X    TC_IDESC_F16(0x08290490u)         // M128 N160, A K-major,  B MN-major
+#define IDESC_B1W    TC_IDESC_F16(0x08298490u)         // M128 N160, A MN-major, B MN-major
 
 struct BtLayout {
     static constexpr int W1 = 0;                                        // [128 n][160 k]  40 960
@@ -48,7 +52,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ w1, const float* __restrict__ b1,
                       const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                       const float* __restrict__ rays, long long M, const float* __restrict__ feat,
-                      const float* __restrict__ rgbs, const float* __restrict__ d_rgbs, float* __restrict__ d_feat,
+                      const float* __restrict__ rgbs, const float* __restrict__ d_rgbs, const unsigned* __restrict__ gmax_bits,
+                      float* __restrict__ d_feat,
                       float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2,
                       float* __restrict__ dW3, float* __restrict__ db3) {
     using L = BtLayout;
@@ -75,14 +80,14 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     for (int i = tid; i < EGN_HID * TC_K1; i += BT_THREADS) {
         const int n = i / TC_K1, kk = i % TC_K1;
         const int src = tc_input_index(kk, AD);
-        store_elem(w1s, nullptr, false, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
+        store_elem_h(w1s, n, kk, src >= 0 ? w1[n * in_dim + src] : (src == -2 ? b1[n] : 0.f));
     }
     for (int i = tid; i < EGN_HID * BT_K2; i += BT_THREADS) {
         const int n = i / BT_K2, kk = i % BT_K2;
-        store_elem(w2s, nullptr, false, n, kk, kk < EGN_HID ? w2[n * EGN_HID + kk] : (kk == EGN_HID ? b2[n] : 0.f));
+        store_elem_h(w2s, n, kk, kk < EGN_HID ? w2[n * EGN_HID + kk] : (kk == EGN_HID ? b2[n] : 0.f));
     }
     // constant-1 column of H1 (k = 128) and zero padding (k = 129..143); zero dO tile (channels 3..15 stay zero)
-    for (int i = tid; i < TC_TM * 16; i += BT_THREADS) store_elem(h1s, nullptr, false, i / 16, EGN_HID + i % 16, (i % 16) == 0 ? 1.f : 0.f);
+    for (int i = tid; i < TC_TM * 16; i += BT_THREADS) store_elem_h(h1s, i / 16, EGN_HID + i % 16, (i % 16) == 0 ? 1.f : 0.f);
     for (int i = tid; i < 16 * 256 / 4; i += BT_THREADS) reinterpret_cast<uint32_t*>(dos)[i] = 0u;
     fence_async_smem();
     tc_fence_before();
@@ -93,6 +98,8 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
     const uint32_t w1_s = smem_u32(w1s), w2_s = smem_u32(w2s), x_s = smem_u32(xs), h1_s = smem_u32(h1s), h2_s = smem_u32(h2s),
                    dz_s = smem_u32(dzs), do_s = smem_u32(dos);
     const float4* w3v = reinterpret_cast<const float4*>(w3);
+    float inv_scale;
+    const float scale = tc_grad_scale(gmax_bits, inv_scale);
 
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     uint32_t it = 0;
@@ -138,7 +145,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 v[5 * j + 3] = 2.f * s1 * c1; v[5 * j + 4] = 1.f - 2.f * s1 * s1;
             }
 #pragma unroll
-            for (int c = 0; c < 5; ++c) store_chunk<false>(xs, nullptr, 5 * q + c, row, v + 8 * c);
+            for (int c = 0; c < 5; ++c) store_chunk_h(xs, 5 * q + c, row, v + 8 * c);
         }
         fence_async_smem();
         tc_fence_before();
@@ -165,7 +172,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 v[j] = fmaxf(h, 0.f);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) store_chunk<false>(h1s, nullptr, 4 * q + c, row, v + 8 * c);
+            for (int c = 0; c < 4; ++c) store_chunk_h(h1s, 4 * q + c, row, v + 8 * c);
         }
         fence_async_smem();
         tc_fence_before();
@@ -193,9 +200,11 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     acc3[ch] += dq[ch];
-                    *reinterpret_cast<__nv_bfloat16*>(dos + (row >> 3) * 256 + ch * 16 + (row & 7) * 2) = __float2bfloat16_rn(dq[ch]);
+                    *reinterpret_cast<__half*>(dos + (row >> 3) * 256 + ch * 16 + (row & 7) * 2) = __float2half_rn(dq[ch] * scale);
                 }
             }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) dq[ch] *= scale;
             uint32_t r[32];
             tmem_ld32(tmem_lane + BT_WORK + 32 * q, r);
             float h2[32], dz[32];
@@ -213,8 +222,8 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                store_chunk<false>(h2s, nullptr, 4 * q + c, row, h2 + 8 * c);
-                store_chunk<false>(dzs, nullptr, 4 * q + c, row, dz + 8 * c);
+                store_chunk_h(h2s, 4 * q + c, row, h2 + 8 * c);
+                store_chunk_h(dzs, 4 * q + c, row, dz + 8 * c);
             }
         }
         fence_async_smem();
@@ -243,7 +252,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ((m1 >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) store_chunk<false>(dzs, nullptr, 4 * q + c, row, v + 8 * c);
+            for (int c = 0; c < 4; ++c) store_chunk_h(dzs, 4 * q + c, row, v + 8 * c);
         }
         fence_async_smem();
         tc_fence_before();
@@ -279,7 +288,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
                 float s1, c1;
                 __sincosf(el[j], &s1, &c1);
                 const float s2 = 2.f * s1 * c1, c2 = 1.f - 2.f * s1 * s1;
-                g[j] = dv[0] + (c1 * dv[1] - s1 * dv[2]) + 2.f * (c2 * dv[3] - s2 * dv[4]);
+                g[j] = (dv[0] + (c1 * dv[1] - s1 * dv[2]) + 2.f * (c2 * dv[3] - s2 * dv[4])) * inv_scale;
                 if (8 * q + j >= AD) g[j] = 0.f;
             }
             if (live) {
@@ -301,8 +310,8 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int n = 16 * c + j;
-            if (n < EGN_HID) atomicAdd(dW2 + row * EGN_HID + n, __uint_as_float(r[j]));
-            else if (n == EGN_HID) atomicAdd(db2 + row, __uint_as_float(r[j]));
+            if (n < EGN_HID) atomicAdd(dW2 + row * EGN_HID + n, __uint_as_float(r[j]) * inv_scale);
+            else if (n == EGN_HID) atomicAdd(db2 + row, __uint_as_float(r[j]) * inv_scale);
         }
     }
     for (int c = q; c < TC_K1 / 16; c += 4) {                     // dW1[k = row][our K order]; the constant-1 column is db1
@@ -311,15 +320,15 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int src = tc_input_index(16 * c + j, AD);
-            if (src >= 0) atomicAdd(dW1 + row * in_dim + src, __uint_as_float(r[j]));
-            else if (src == -2) atomicAdd(db1 + row, __uint_as_float(r[j]));
+            if (src >= 0) atomicAdd(dW1 + row * in_dim + src, __uint_as_float(r[j]) * inv_scale);
+            else if (src == -2) atomicAdd(db1 + row, __uint_as_float(r[j]) * inv_scale);
         }
     }
     if (q == 0) {                                                  // dW3[ch][n = row]
         uint32_t r[16];
         tmem_ld16(tmem_lane + BT_DW3, r);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) atomicAdd(dW3 + ch * EGN_HID + row, __uint_as_float(r[ch]));
+        for (int ch = 0; ch < 3; ++ch) atomicAdd(dW3 + ch * EGN_HID + row, __uint_as_float(r[ch]) * inv_scale);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             float s = acc3[ch];
@@ -334,14 +343,15 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
 }
 
 int egn_launch_mlp_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
-                          const float* rgbs, const float* d_rgbs, float* d_feat, const EgnGrads* g, cudaStream_t st) {
+                          const float* rgbs, const float* d_rgbs, const unsigned* gmax_bits, float* d_feat, const EgnGrads* g,
+                          cudaStream_t st) {
     const long long M = n * k.S;
     if (M <= 0) return 0;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     const int blocks = (int)(tiles < 148 ? tiles : 148);
     cudaFuncSetAttribute(egn_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BtLayout::TOTAL);
     egn_mlp_bwd_tc_kernel<<<blocks, BT_THREADS, BtLayout::TOTAL, st>>>(
-        k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], rays, M, feat, rgbs, d_rgbs, d_feat,
+        k, p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1], p->mlp_w[2], rays, M, feat, rgbs, d_rgbs, gmax_bits, d_feat,
         g->mlp_w[0], g->mlp_b[0], g->mlp_w[1], g->mlp_b[1], g->mlp_w[2], g->mlp_b[2]);
     return (int)cudaGetLastError();
 }

@@ -2,6 +2,7 @@
 // (egn_mlp_tc.cu, egn_fused.cu).  sm_100a only.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "egn_device.cuh"
 
 #define TC_THREADS 256
@@ -117,6 +118,38 @@ __device__ __forceinline__ void store_elem(unsigned char* hi_base, unsigned char
     const int off = (kk >> 3) * chunk_bytes + row * 16 + (kk & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
     if (split) *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+// ---- fp16 operand tiles (fused forward, tcgen05 backward) ------------------------------------------------------------
+// two floats -> packed fp16 pair (first value in the low half), round to nearest, saturating instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void store_chunk_h(unsigned char* base, int chunk, int row, const float* v) {
+    uint4 h;
+    h.x = pack_h2(v[0], v[1]); h.y = pack_h2(v[2], v[3]); h.z = pack_h2(v[4], v[5]); h.w = pack_h2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(base + chunk * TC_CHUNK + row * 16) = h;
+}
+__device__ __forceinline__ void store_elem_h(unsigned char* base, int row, int kk, float x, int chunk_bytes = TC_CHUNK) {
+    *reinterpret_cast<__half*>(base + (kk >> 3) * chunk_bytes + row * 16 + (kk & 7) * 2) = __float2half_rn(x);
+}
+
+// kind::f16 instruction descriptor with fp16 A / B instead of bf16 (format fields, bits 7-9 and 10-12, cleared)
+#define TC_IDESC_F16(idesc) ((idesc) & ~0x480u)
+
+// Power-of-two scale of the tcgen05 backward's GRADIENT operands (fp16 has 11 significand bits against bf16's 8, but only
+// 2^-14 .. 2^16 of normal range): S brings the largest |d(sample colour)| of the launch -- written by
+// egn_composite_bwd_kernel as the bit pattern of a non-negative float -- to (2^9, 2^10]; everything the kernels derive from
+// it is linear in it, the fp32 results are multiplied by 1/S.  Headroom above: 64x for the MLP's gain (conversions saturate
+// instead of overflowing); below: full precision down to 2^-24 of the launch maximum, gradual underflow down to 2^-34.
+__device__ __forceinline__ float tc_grad_scale(const unsigned* __restrict__ gmax_bits, float& inv) {
+    const float gmax = __uint_as_float(__ldg(gmax_bits));
+    float e = 0.f;
+    if (gmax > 0.f && gmax < 3.0e38f) e = fminf(fmaxf(10.f - ceilf(log2f(gmax)), -100.f), 100.f);
+    inv = exp2f(-e);
+    return exp2f(e);
 }
 
 // original input index (tensorBase.py:68-74 order) of our K position kk; -1 = padding; -2 = the constant-1 column that

@@ -137,18 +137,18 @@ def test_fused_kernel_with_and_without_the_compositing_epilogue_agree():
         assert (d[0] - e[0]).abs().max().item() <= TP_RGB_VS_FP32 and (d[4] - e[4]).abs().max().item() <= TP_ALPHA_VS_FP32
 
 
-# per-tensor bound of the tcgen05 backward (bf16 operands) against the REFERENCE's gradients of the training loss
-# (train.py:260, mean squared error): relative L2 error.  Measured on B200 (profiles/r02_parity.md): factor tensors 0.4-2.6e-2,
-# basis 1.1e-2, MLP weights up to 4.0e-2 (layer-1 weight, a sum over all samples of products of two bf16-rounded operands).
-# With bf16 re-gather tables the worst tensor reaches 6.1e-2.  The 2e-2 target of the round-1 review is met by the median and by
-# most tensors (printed per run), not by all: the bound below is 1.3x the worst measured, the median is held to 2e-2.
-TC_BWD_REL_L2 = 8e-2
-TC_BWD_REL_L2_MEDIAN = 2e-2
+# per-tensor bound of the tcgen05 backward against the REFERENCE's gradients of the training loss (train.py:260, mean squared
+# error): relative L2 error.  The kernels use fp16 operands with a launch-wide power-of-two scale on the gradient operands
+# (tc_grad_scale, egn_tc.cuh).  Measured on B200 (profiles/r02_parity.md): median 1.9e-3 (3.2e-3 with bf16 re-gather tables),
+# every tensor <= 1e-2 except one appearance plane of the envmap fixture at 2.1e-2 (bf16 operands, the first version of these
+# kernels: median 1e-2 / 3.7e-2, worst 4-6e-2).  Bounds = 2x the worst and 2.5x the median measured.
+TC_BWD_REL_L2 = 4e-2
+TC_BWD_REL_L2_MEDIAN = 8e-3
 
 
 @pytest.mark.parametrize("name", ["render_tiny_train_mse_grad", "render_tiny_env_train_mse_grad"])
 def test_tc_backward_matches_the_reference_gradients(name):
-    """egn_mlp_bwd_tc_kernel + egn_gather_bwd_tc_kernel (tcgen05, bf16 operands, fp32 accumulate; weight gradients accumulated
+    """egn_mlp_bwd_tc_kernel + egn_gather_bwd_tc_kernel (tcgen05, fp16 operands, fp32 accumulate; weight gradients accumulated
     in TMEM) against the `.grad` tensors of the UNMODIFIED reference for the loss it trains with (MSE on rgb, train.py:260),
     fixtures tests/golden/render_tiny*_mse_grad.npz.  Three configurations share the bound: throughput forward + tcgen05
     backward, the same with bf16 re-gather tables, and parity forward + tcgen05 backward."""
@@ -180,15 +180,15 @@ def test_tc_backward_matches_the_reference_gradients(name):
             rels.append(rel)
             if rel > worst[1]:
                 worst = (k, rel)
-            bound = 5e-4 if mode == "fp32" else TC_BWD_REL_L2
-            assert rel <= bound, (mode, tables, tcb, k, rel)
-        if mode != "fp32":
-            assert float(np.median(rels)) <= TC_BWD_REL_L2_MEDIAN, (mode, float(np.median(rels)))
         report[(mode, tables, tcb)] = (worst[0], worst[1], float(np.median(rels)), int(sum(r <= 2e-2 for r in rels)), len(rels))
     model.tc_backward, model.table_dtype = False, "f32"
     print(f"{name}: worst per-tensor relative L2 gradient error vs the reference: " +
           "; ".join(f"{m}/{t}{'+tcbwd' if b else ''}: worst {w[1]:.2e} ({w[0]}), median {w[2]:.2e}, {w[3]}/{w[4]} tensors <= 2e-2"
                     for (m, t, b), w in report.items()))
+    for (mode, tables, tcb), w in report.items():
+        assert w[1] <= (5e-4 if mode == "fp32" else TC_BWD_REL_L2), (mode, tables, tcb, w)
+        if mode != "fp32":
+            assert w[2] <= TC_BWD_REL_L2_MEDIAN, (mode, tables, tcb, w)
 
 
 def test_fused_kernels_are_deterministic_run_to_run():
