@@ -117,7 +117,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-CPU_SAMPLE_RAYS = 1024          # rays per CPU-baseline step: the in-line leg and `--impl reference` time the SAME sample
+CPU_SAMPLE_RAYS = 4096          # rays per CPU-baseline step: the in-line leg and `--impl reference` time the SAME sample
 
 
 def oracle_rays_per_s(scene, n_rays, repeats, warmup, seed=5, N_COARSE=128, N_FINE=128):
@@ -484,7 +484,7 @@ def main():
                             "tc_split": "fp32 tables; tcgen05 MLP and mma.sync basis with 3-term bf16 split (fp32-equivalent), fp32 accumulate",
                             "tc_f16": "density channels, alpha, transmittance and compositing in fp32; appearance tables, packed-half2 "
                                       "interpolation and tcgen05 MMA operands in fp16 with fp32 accumulate (rgb within 1e-4 of the "
-                                      "reference, tests/test_gpu_tc.py); backward: tcgen05 kernels with bf16 operands"}[args.mlp]
+                                      "reference, tests/test_gpu_tc.py); backward: tcgen05 kernels, fp16 operands with a launch-wide power-of-two gradient scale"}[args.mlp]
     launches = (model.launches_per_forward(S) * (-(-n_rays // chunk)) if not train else model.launches_per_train_step(n_rays)) * args.steps
     e2e = {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24 * world,
            "d2h_bytes_per_step": (n_rays * 16 if not train else 4) * world}

@@ -267,6 +267,7 @@ def test_checkpoint_round_trip(tmp_path):
     kw.update(device="cuda:0")
     clone = EgoNeRF(**kw)
     assert clone.load(ckpt) == 123
+    clone.mlp_mode = model.mlp_mode                  # the arithmetic mode is a run-time attribute, not part of the checkpoint
     with torch.no_grad():
         b = clone(rays, is_train=False, **RENDER_KW)
     for x, y in zip(a, b):
