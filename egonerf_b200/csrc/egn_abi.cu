@@ -266,6 +266,8 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
     mark(se, 1, st);
     const bool fused = is_fused(c);
     if (fused && !c->tables_h) return fail("EGN_MLP_TC_F16 needs EgnConfig.tables_h (egn_pack_tables_h)");
+    if (fused && (long long)n * k.S >= 0xffffff00ll)
+        return fail("fused fine pass: %lld samples in one call (32-bit sample indices inside the kernel): render in smaller chunks", (long long)n * k.S);
     if (fused) {
         // throughput mode: one warp-specialised kernel for gather + basis + MLP; the app feature is only written
         // when a backward pass will read it (full training workspace)

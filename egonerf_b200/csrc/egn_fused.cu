@@ -60,6 +60,14 @@ struct FuLayout {
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
 
+// exact n / d for the small divisors of this kernel (d <= 16, n < 2^27: n * (magic * d - 2^32) < 2^32), one IMAD.HI instead of
+// the ~100-instruction 64-bit division every thread used to run several times per tile
+struct FuDiv {
+    uint32_t magic, d;
+    __device__ __forceinline__ void init(uint32_t div) { d = div; magic = (uint32_t)((0x100000000ull + div - 1) / div); }
+    __device__ __forceinline__ uint32_t operator()(uint32_t n) const { return d == 1 ? n : __umulhi(n, magic); }
+};
+
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -252,16 +260,24 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const long long tiles = (M + TC_TM - 1) / TC_TM;
+    // sample indices are 32-bit inside the kernel (the launcher refuses M >= 2^32 - 256); S is a multiple of 32
+    const uint32_t M32 = (uint32_t)M, S32 = (uint32_t)k.S;
+    const uint32_t tiles = (M32 + TC_TM - 1) / TC_TM;
     bool ok = mbar_wait(img_full, 0);                           // operand image landed (async-proxy write -> visible after the wait)
     // CTA-local iteration -> tile.  Plain: tiles strided over the CTAs.  COMP: rays strided over the CTAs, the tpr tiles of a
     // ray consecutive (S = tpr * 128), so the transmittance can be carried from tile to tile.
-    const int tpr = COMP ? k.S / TC_TM : 1;
-    const long long n_local = COMP ? (((M / k.S) - blockIdx.x + gridDim.x - 1) / gridDim.x) * tpr
+    const uint32_t tpr = COMP ? S32 / TC_TM : 1;
+    const uint32_t n_local = COMP ? (((M32 / S32) - blockIdx.x + gridDim.x - 1) / gridDim.x) * tpr
                                    : (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    auto tile_of = [&](long long i) -> long long {
-        return COMP ? ((i / tpr) * gridDim.x + blockIdx.x) * tpr + i % tpr : blockIdx.x + i * (long long)gridDim.x;
+    FuDiv div_tpr, div_s;
+    div_tpr.init(tpr);
+    div_s.init(S32 >> 5);
+    auto tile_of = [&](uint32_t i) -> uint32_t {
+        if (!COMP) return blockIdx.x + i * gridDim.x;
+        const uint32_t q = div_tpr(i);
+        return (q * gridDim.x + blockIdx.x) * tpr + (i - q * tpr);
     };
+    auto ray_of = [&](uint32_t m) -> uint32_t { return div_s(m >> 5); };       // sample index -> ray
 
     if (warp >= 8) {
         // =========================== GATHER group ===========================
@@ -271,19 +287,19 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
         YYCoord held;                                                // coordinates computed one tile ahead (lanes 16..31)
         held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
-        for (uint32_t it = 0; it < (uint32_t)n_local; ++it) {
-            const long long tile = tile_of(it);
+        for (uint32_t it = 0; it < n_local; ++it) {
+            const uint32_t tile = tile_of(it);
             const uint32_t b = it & 1, u = it >> 1;
             // ---- phase 1a: coordinates.  Even iterations: lanes 0..15 take this tile's rows, lanes 16..31 the same rows of
             // the CTA's next tile (kept in `held`); odd iterations just fetch them ----
             YYCoord cc;
             if (b == 0) {
-                const long long m = (lane < 16 ? tile : tile_of(it + 1)) * TC_TM + row0 + (lane & 15);
+                const uint32_t m = (lane < 16 ? tile : tile_of(it + 1)) * TC_TM + row0 + (lane & 15);
                 cc.c[0] = cc.c[1] = cc.c[2] = -3.f;                  // out of range -> every tap gets weight zero
                 cc.yang = 0;
-                if (m < M && (lane < 16 || it + 1 < (uint32_t)n_local)) {
+                if (m < M32 && (lane < 16 || it + 1 < n_local)) {
                     const float z = zs[m];
-                    const float* ry = rays + (m / k.S) * 6;
+                    const float* ry = rays + (size_t)ray_of(m) * 6;
                     cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
                 }
                 held = cc;
@@ -317,8 +333,8 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                         f += fused_density_unit(rec, i, t[i]);
                         if (p == 0) fused_density_issue(dens, nxt, i, sub, t[i]);
                     }
-                    const long long m = tile * TC_TM + row0 + 8 * p + (lane >> 2);
-                    if (sub == 0 && m < M) fsig[m] = f;
+                    const uint32_t m = tile * TC_TM + row0 + 8 * p + (lane >> 2);
+                    if (sub == 0 && m < M32) fsig[m] = f;
                     rec = nxt;
                 }
             }
@@ -375,16 +391,16 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         float carryT = 1.f, sum_w = 0.f, sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_z = 0.f;     // sums live in thread 0
         float* red = reinterpret_cast<float*>(smem + L::RED);
         const int acols = k.S + (k.env_h > 0 ? 1 : 0);
-        auto layer3 = [&](long long gm3) {
+        auto layer3 = [&](uint32_t gm3) {
             // COMP: the upper-half threads (idle during the scan below) turn the row's sigma feature -- written by the gather
             // group, read back through L2 -- into alpha (tensorBase.py:22-27 with the distances of EgoNeRF.py:541-542,553:
             // z[j+1] - z[j], the last one repeated).  The loads are requested first and land behind the dot products.
             float fs = 0.f, zrow = 0.f, znext = 0.f;
-            long long ray3 = 0;
+            uint32_t ray3 = 0;
             int j3 = 0;
             if constexpr (COMP) {
-                ray3 = gm3 / k.S;
-                j3 = (int)(gm3 - ray3 * k.S);
+                ray3 = ray_of(gm3);
+                j3 = (int)(gm3 - ray3 * S32);
                 zrow = zs[gm3];
                 if (half == 1) {
                     fs = __ldcg(fsig + gm3);
@@ -410,17 +426,18 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 if constexpr (COMP) {
                     const float dist = ((j3 + 1 < k.S) ? (znext - zrow) : (zrow - znext)) * k.distance_scale;
                     a = 1.f - expf(-egn_density_act(fs, k.density_shift, k.fea2dense) * dist);
-                    out.alpha[ray3 * acols + j3] = a;
+                    out.alpha[(size_t)ray3 * acols + j3] = a;
                 }
                 *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, a);
             }
             named_bar_sync(1, FU_GROUP);
-            if (half == 0 && gm3 < M) {
+            if (half == 0 && gm3 < M32) {
                 const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
                 const float alpha = q.w;
                 const float c0 = egn_sigmoid(p0 + q.x + bias3[0]), c1 = egn_sigmoid(p1 + q.y + bias3[1]), c2 = egn_sigmoid(p2 + q.z + bias3[2]);
                 if constexpr (!COMP) {
-                    rgbs[gm3 * 3 + 0] = c0; rgbs[gm3 * 3 + 1] = c1; rgbs[gm3 * 3 + 2] = c2;
+                    float* o3 = rgbs + (size_t)gm3 * 3;
+                    o3[0] = c0; o3[1] = c1; o3[2] = c2;
                 } else {
                     // transmittance: T_j = prod_{i<j} (1 - alpha_i + 1e-10) (tensorBase.py:24-26); rows = consecutive samples
                     const int lane_ = tid & 31, w4 = tid >> 5;         // w4 in 0..3
@@ -448,7 +465,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                     }
                     named_bar_sync(2, TC_TM);
                     carryT *= ((q0 * q1) * q2) * q3;
-                    const long long ray = ray3;
+                    const size_t ray = ray3;
                     const bool last = j3 + TC_TM - row >= k.S;                     // this tile is the ray's last one
                     if (tid == 0) {
                         sum_w += (red[4] + red[9]) + (red[14] + red[19]);
@@ -481,11 +498,11 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         };
         if (tid == 0 && n_local > 0) issue_layer0(0);
         uint32_t it = 0;
-        long long gm_prev = M;
-        for (; it < (uint32_t)n_local; ++it) {
-            const long long tile = tile_of(it);
-            const long long gm = tile * TC_TM + row;
-            const bool live = gm < M;
+        uint32_t gm_prev = M32;
+        for (; it < n_local; ++it) {
+            const uint32_t tile = tile_of(it);
+            const uint32_t gm = tile * TC_TM + row;
+            const bool live = gm < M32;
             // ---- layer 0 of this tile was issued one iteration ago ----
             ok &= mbar_wait(feat_full, it & 1);
             tc_fence_after();
@@ -499,16 +516,20 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
 #pragma unroll
                 for (int j = 0; j < 16; ++j) el[j] = __uint_as_float(yang ? r1[j] : r0[j]);
                 if (feat_out != nullptr && live) {                     // saved for the backward pass (28 floats / sample)
-                    float4* dst = reinterpret_cast<float4*>(feat_out + gm * EGN_FEAT_STRIDE + 16 * half);
+                    float4* dst = reinterpret_cast<float4*>(feat_out + (size_t)gm * EGN_FEAT_STRIDE + 16 * half);
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (half == 0 || q < 3) dst[q] = make_float4(el[4 * q], el[4 * q + 1], el[4 * q + 2], el[4 * q + 3]);
                 }
-                const float* dir = rays + (live ? gm / k.S : 0) * 6 + 3;
+                const float* dir = rays + (size_t)(live ? ray_of(gm) : 0u) * 6 + 3;
+                if (AD == 27) {                                      // every shipped config: elements 27..29 = view direction, 30 = 1
+                    if (half) { el[11] = __ldg(dir); el[12] = __ldg(dir + 1); el[13] = __ldg(dir + 2); el[14] = 1.f; el[15] = 0.f; }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int e = 16 * half + j;
-                    if (e >= AD) el[j] = (e < AD + 3) ? __ldg(dir + (e - AD)) : (e == AD + 3 ? 1.f : 0.f);
+                    for (int j = 0; j < 16; ++j) {
+                        const int e = 16 * half + j;
+                        if (e >= AD) el[j] = (e < AD + 3) ? __ldg(dir + (e - AD)) : (e == AD + 3 ? 1.f : 0.f);
+                    }
                 }
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
@@ -561,7 +582,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 for (int ks = 0; ks < EGN_HID / 16; ++ks)
                     tc_mma(tmem + 128, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w2_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
                 tc_commit(d2_full);
-                if (it + 1 < (uint32_t)n_local) issue_layer0(it + 1);
+                if (it + 1 < n_local) issue_layer0(it + 1);
             }
             ok &= mbar_wait(d2_full, it & 1);
             tc_fence_after();
@@ -580,6 +601,7 @@ int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float
                           cudaStream_t st) {
     const long long M = n * k.S;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
+    if (M >= 0xffffff00ll) return (int)cudaErrorInvalidValue;      // 32-bit sample indices inside the kernel: render in smaller chunks
     unsigned char* img = reinterpret_cast<unsigned char*>(image_buf);
     egn_fused_image_kernel<<<48, 256, 0, st>>>(k.app_dim, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1],
                                                p->mlp_w[2], img);
