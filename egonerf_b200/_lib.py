@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libegn_b200.so")
+LIB_PATH = os.environ.get("EGN_B200_LIB") or os.path.join(_HERE, "libegn_b200.so")      # override: kernel experiments only
 ABI_VERSION = 7
 
 c_float_p = C.POINTER(C.c_float)

@@ -38,6 +38,17 @@
 #define FU_VBYTES (FU_VCHUNKS * FU_VCHUNK)   // 37 152
 #define FU_BB_CHUNK 1024                     // basis operand: 64 rows x 16 B per K chunk
 #define FU_REC_WORDS 36                      // address record of one sample: 3 x {4 plane texels, 2 line texels, 4 + 2 weights}
+#ifndef FU_APP_UNROLL
+#define FU_APP_UNROLL 1
+#endif
+#define FU_STR(x) #x
+#define FU_UNROLL(n) _Pragma(FU_STR(unroll n))
+#ifndef FU_PAIRED_W
+#define FU_PAIRED_W 0                        // measured: 5.50 ms with the paired conversions vs 5.41 ms (profiles/r02_fused.md)
+#endif
+#ifndef FU_MLP_BACKOFF
+#define FU_MLP_BACKOFF 0                     // ns between polls of the MLP group's wait for the next gathered tile (256 / 1024: no effect)
+#endif
 #define FU_IDESC_128x128 0x08200010u         // kind::f16: D fp32, A/B fp16, both K-major, N = 128, M = 128
 #define FU_IDESC_128x64  0x08100010u         // same, N = 64
 
@@ -168,8 +179,16 @@ __device__ __forceinline__ uint4 fused_app_unit(const uint4* __restrict__ rec, i
     const float f0 = __uint_as_float(b.z), f1 = __uint_as_float(b.w);
     const float f2 = __uint_as_float(c.x), f3 = __uint_as_float(c.y);
     const float g0 = __uint_as_float(c.z), g1 = __uint_as_float(c.w);
+#if FU_PAIRED_W
+    // three conversions make the six weights (two per register); the multiplies read one half of a register broadcast
+    // (SASS operand modifiers .H0_H0 / .H1_H1)
+    const __half2 w01 = as_h2(pack_h2(f0, f1)), w23 = as_h2(pack_h2(f2, f3)), u01 = as_h2(pack_h2(g0, g1));
+    const __half2 w0 = __low2half2(w01), w1 = __high2half2(w01), w2 = __low2half2(w23), w3 = __high2half2(w23);
+    const __half2 u0 = __low2half2(u01), u1 = __high2half2(u01);
+#else
     const __half2 w0 = as_h2(pack_h2(f0, f0)), w1 = as_h2(pack_h2(f1, f1)), w2 = as_h2(pack_h2(f2, f2)), w3 = as_h2(pack_h2(f3, f3));
     const __half2 u0 = as_h2(pack_h2(g0, g0)), u1 = as_h2(pack_h2(g1, g1));
+#endif
     uint4 o;
 #define FU_PL(m) { __half2 P = __hmul2(w0, as_h2(t[0].m)); P = __hfma2(w1, as_h2(t[1].m), P); P = __hfma2(w2, as_h2(t[2].m), P); \
                    P = __hfma2(w3, as_h2(t[3].m), P); const __half2 Lv = __hfma2(u1, as_h2(t[5].m), __hmul2(u0, as_h2(t[4].m))); \
@@ -349,7 +368,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
 #pragma unroll
                 for (int i = 0; i < 3; ++i) fused_app_issue(app, rec, i, q, t[i]);
                 ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);      // layer-0 MMAs of the tile that used this buffer are done
-#pragma unroll 1
+FU_UNROLL(FU_APP_UNROLL)
                 for (int p = 0; p < 4; ++p) {
                     const uint4* nxt = recs + fu_rec_slot(min(4 * (p + 1), 12) + (lane >> 3));
 #pragma unroll
@@ -504,7 +523,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
             const uint32_t gm = tile * TC_TM + row;
             const bool live = gm < M32;
             // ---- layer 0 of this tile was issued one iteration ago ----
-            ok &= mbar_wait(feat_full, it & 1);
+            ok &= mbar_wait<FU_MLP_BACKOFF>(feat_full, it & 1);
             tc_fence_after();
             // ---- A. this thread's 16 elements: features of its hemisphere (from TMEM), then view direction / 1 / padding ----
             {

@@ -38,6 +38,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // slots burnt, wake-up right after the arrive).  The bound is WALL-CLOCK (%globaltimer, 2 s), not a retry count: the parked
 // wait may return early any number of times (other barrier traffic of the CTA, instrumented runs under a profiler), and a
 // retry budget would then expire without a lost arrive.  On expiry the caller traps.
+// BACKOFF_NS > 0: for waits that are known to be long and not on the critical path (the MLP group of the fused kernel waiting
+// for the next gathered tile): the parked wait returns on every barrier event of the CTA (~50 times per tile there), and each
+// failed poll costs issue slots the gather warps of the same scheduler need -- sleep between polls instead.
+template <uint32_t BACKOFF_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1                                             // keep the wait sites small: their code sits inside the hot loops
@@ -45,6 +49,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
         if (done) return true;
+        if (BACKOFF_NS) __nanosleep(BACKOFF_NS);
     }
     uint32_t t0;                                             // low word of the ns timer: wraps at 4.29 s, the bound is 2 s
     asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t0));
