@@ -115,7 +115,10 @@ __device__ __forceinline__ float egn_aabb_entry(const EgnKernelCfg& k, float ox,
 #define K1_WARPS 8
 #define K1_MAXC 256
 
-__global__ void __launch_bounds__(K1_WARPS * 32, 2)
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(K1_WARPS * 32, K1_MIN_BLOCKS)
 egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ rays, long long n, int is_train,
                   const float* __restrict__ u_c, const float* __restrict__ u_f, unsigned long long seed,
                   long long ray0, float near_plane, float* __restrict__ z_out) {
@@ -381,7 +384,7 @@ int egn_launch_coarse(const EgnKernelCfg& k, const float* rays, long long n, int
                       const float* u_f, unsigned long long seed, long long ray0, float near_plane, float* z_out,
                       cudaStream_t st) {
     long long blocks = (n + K1_WARPS - 1) / K1_WARPS;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 4 * K1_MIN_BLOCKS) blocks = 148 * 4 * K1_MIN_BLOCKS;
     egn_coarse_kernel<<<(unsigned)blocks, K1_WARPS * 32, 0, st>>>(k, rays, n, is_train, u_c, u_f, seed, ray0, near_plane, z_out);
     return (int)cudaGetLastError();
 }

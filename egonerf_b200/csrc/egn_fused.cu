@@ -38,6 +38,9 @@
 #define FU_VBYTES (FU_VCHUNKS * FU_VCHUNK)   // 37 152
 #define FU_BB_CHUNK 1024                     // basis operand: 64 rows x 16 B per K chunk
 #define FU_REC_WORDS 36                      // address record of one sample: 3 x {4 plane texels, 2 line texels, 4 + 2 weights}
+#ifndef FU_VBUFS
+#define FU_VBUFS 2                           // V operand buffers: 2 = gather of tile i+1 overlaps layer 0 of tile i; 1 = -37 KB shared memory
+#endif
 #ifndef FU_APP_UNROLL
 #define FU_APP_UNROLL 1
 #endif
@@ -60,7 +63,7 @@ struct FuLayout {
     static constexpr int IMAGE = L3 + EGN_HID * 16;                   // W1 .. L3 = the operand image, one bulk copy (94 208 bytes)
     static constexpr int A = IMAGE;
     static constexpr int V = A + (TC_K1 / 8) * TC_CHUNK;              // + 40 960 ; two buffers
-    static constexpr int REC = V + 2 * FU_VBYTES;                     // address records: 128 samples x 144 B
+    static constexpr int REC = V + FU_VBUFS * FU_VBYTES;                     // address records: 128 samples x 144 B
     static constexpr int YANG = REC + 8 * (16 * (FU_REC_WORDS / 4) + 1) * 16;   // 8 warps x (16 records + 1 swizzle slot); then 4 x 128 bytes
     static constexpr int KNOTS = YANG + 4 * TC_TM;
     static constexpr int MBAR = KNOTS + ((EGN_FUSED_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
@@ -308,7 +311,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
         for (uint32_t it = 0; it < n_local; ++it) {
             const uint32_t tile = tile_of(it);
-            const uint32_t b = it & 1, u = it >> 1;
+            const uint32_t b = FU_VBUFS == 2 ? (it & 1) : 0, u = FU_VBUFS == 2 ? (it >> 1) : it;
             // ---- phase 1a: coordinates.  Even iterations: lanes 0..15 take this tile's rows, lanes 16..31 the same rows of
             // the CTA's next tile (kept in `held`); odd iterations just fetch them ----
             YYCoord cc;
@@ -395,8 +398,8 @@ FU_UNROLL(FU_APP_UNROLL)
         // tile t, and on layer 1 of tile t while the group runs layer 3 of tile t-1 out of TMEM: only the layer-2 wait is
         // exposed.  TMEM: D1 = columns 0..127, D2 = 128..255, feat2 = 256..319.
         auto issue_layer0 = [&](uint32_t i) {                   // thread 0: feat2 = V . [B_yin | B_yang]^T for CTA-local tile i
-            const uint32_t bb = i & 1;
-            ok &= mbar_wait(v_full0 + 8 * bb, (i >> 1) & 1);
+            const uint32_t bb = FU_VBUFS == 2 ? (i & 1) : 0;
+            ok &= mbar_wait(v_full0 + 8 * bb, (FU_VBUFS == 2 ? (i >> 1) : i) & 1);
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < FU_VK / 16; ++ks)
@@ -627,6 +630,9 @@ int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float
     if (composite_out != nullptr) {           // compositing inside the kernel: CTAs walk whole rays
         const int blocks = (int)(n < 148 ? n : 148);
         cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
+#ifdef FU_CARVEOUT
+        cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, FU_CARVEOUT);
+#endif
         egn_fused_fine_kernel<true><<<blocks, FU_THREADS, FuLayout::TOTAL, st>>>(k, img, p->mlp_b[2], rays, M, z, fsig, nullptr, rgbs,
                                                                                  p->emission, *composite_out);
         return (int)cudaGetLastError();
