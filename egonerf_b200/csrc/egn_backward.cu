@@ -238,7 +238,7 @@ egn_gather_bwd_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
         float dfs = 0.f;
         const bool live = (r < rounds) && (m < M);
         if (live) {
-            const long long ray = m / k.S;
+            const long long ray = egn_ray_of(m, k.S);
             const float z = zs[m];
             const float* ry = rays + ray * 6;
             cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, sm.knots);

@@ -153,6 +153,12 @@ __device__ __forceinline__ YYCoord egn_cart_to_yinyang(float px, float py, float
     return egn_cart_to_yinyang(px, py, pz, k, knots, k.knots_last, k.r_div);
 }
 
+// sample index -> ray index.  S is a multiple of 32 (validated: n_coarse, n_fine % 32 == 0), so m / S == (m >> 5) / (S >> 5): a
+// 32-bit division (~20 instructions) instead of the ~100-instruction 64-bit one; exact for m < 2^37
+__device__ __forceinline__ long long egn_ray_of(long long m, int S) {
+    return (long long)((unsigned)(m >> 5) / (unsigned)(S >> 5));
+}
+
 // F.grid_sample(align_corners=True) un-normalisation: ((x+1)/2)*(size-1)
 __device__ __forceinline__ float egn_unnorm(float x, int size) { return ((x + 1.f) / 2.f) * (float)(size - 1); }
 

@@ -453,7 +453,7 @@ egn_gather_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
                 cc.yang = (c7[6] != 0.f);           // EgoNeRF.py:292: last column == 0 selects Yin
                 cc.c[0] = c7[cc.yang * 3 + 0]; cc.c[1] = c7[cc.yang * 3 + 1]; cc.c[2] = c7[cc.yang * 3 + 2];
             } else {
-                const long long ray = m / k.S;
+                const long long ray = egn_ray_of(m, k.S);
                 const float z = zs[m];
                 const float* ry = rays + ray * 6;
                 cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, sm.knots);

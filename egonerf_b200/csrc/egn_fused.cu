@@ -23,6 +23,7 @@
 // Nothing of size (samples x features) touches HBM in between: per sample the kernel reads 24 B of ray, 4 B of depth and
 // its taps, and writes 4 B (sigma feature) + 12 B (colour) [+ 112 B app feature when the backward pass will need it].
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "egn_tc.cuh"
 #include "egn_host.h"
 #include "egn_shared.cuh"
@@ -54,6 +55,21 @@
 #endif
 #define FU_IDESC_128x128 0x08200010u         // kind::f16: D fp32, A/B fp16, both K-major, N = 128, M = 128
 #define FU_IDESC_128x64  0x08100010u         // same, N = 64
+
+// Layer-3 table {b2, W3[0], W3[1], W3[2]} per hidden unit, as constant-bank operands of the epilogue's FADD / FFMA (FU_L3_CONST):
+// the 64 broadcast LDS.128 per thread and tile it replaces were 1 053 of the 3 122 shared-memory wavefronts of a tile, i.e. 13 %
+// of the traffic on the L1 data pipe the kernel is bound by (profiles/r02_fused.md).  The symbol is refreshed by a device-to-
+// device copy from the operand image before every launch, on the launch's stream; launches on DIFFERENT streams are ordered
+// against each other by an event per device (a later copy waits for the earlier kernel), under a host mutex.
+#ifndef FU_L3_CONST
+#define FU_L3_CONST 0                        // measured: 5.54 ms with the constant-bank table vs 5.41 ms (LDCU.128 into uniform registers is slower than the LDS it saves)
+#endif
+#if FU_L3_CONST
+#include <mutex>
+__constant__ float4 c_fu_l3[EGN_HID];
+static std::mutex g_fu_l3_mutex;
+static cudaEvent_t g_fu_l3_event[64] = {};
+#endif
 
 struct FuLayout {
     static constexpr int W1 = 0;
@@ -256,7 +272,9 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     unsigned char* s_yang = smem + L::YANG;
     float* s_knots = reinterpret_cast<float*>(smem + L::KNOTS);
     float* part = reinterpret_cast<float*>(smem + L::PART);
+#if !FU_L3_CONST
     float4* l3s = reinterpret_cast<float4*>(smem + L::L3);
+#endif
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
     const uint32_t bar = smem_u32(smem + L::MBAR);
     const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48, img_full = bar + 56;
@@ -430,6 +448,24 @@ FU_UNROLL(FU_APP_UNROLL)
                 }
             }
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#if FU_L3_CONST
+            // the column half is warp-uniform: two copies of the loop with compile-time constant-bank offsets
+            auto dot64 = [&](auto HALF) {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    constexpr int col = 64 * decltype(HALF)::value + 0;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_lane + 128 + col + 32 * cc, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 w = c_fu_l3[col + 32 * cc + j];
+                        const float h = fmaxf(__uint_as_float(r[j]) + w.x, 0.f);
+                        p0 = fmaf(h, w.y, p0); p1 = fmaf(h, w.z, p1); p2 = fmaf(h, w.w, p2);
+                    }
+                }
+            };
+            if (half == 0) dot64(std::integral_constant<int, 0>{}); else dot64(std::integral_constant<int, 1>{});
+#else
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int col = 64 * half + 32 * cc;
@@ -442,6 +478,7 @@ FU_UNROLL(FU_APP_UNROLL)
                     p0 = fmaf(h, w.y, p0); p1 = fmaf(h, w.z, p1); p2 = fmaf(h, w.w, p2);
                 }
             }
+#endif
             tc_fence_before();
             if (half == 1) {
                 float a = 0.f;
@@ -627,6 +664,16 @@ int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float
     unsigned char* img = reinterpret_cast<unsigned char*>(image_buf);
     egn_fused_image_kernel<<<48, 256, 0, st>>>(k.app_dim, p->basis[0], p->basis[1], p->mlp_w[0], p->mlp_b[0], p->mlp_w[1], p->mlp_b[1],
                                                p->mlp_w[2], img);
+#if FU_L3_CONST
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::lock_guard<std::mutex> lock(g_fu_l3_mutex);
+    if (g_fu_l3_event[dev] == nullptr) cudaEventCreateWithFlags(&g_fu_l3_event[dev], cudaEventDisableTiming);
+    else cudaStreamWaitEvent(st, g_fu_l3_event[dev], 0);          // the previous launch (any stream) has finished reading the symbol
+    cudaMemcpyToSymbolAsync(c_fu_l3, img + FuLayout::L3, EGN_HID * sizeof(float4), 0, cudaMemcpyDeviceToDevice, st);
+    struct Mark { cudaEvent_t e; cudaStream_t s; ~Mark() { cudaEventRecord(e, s); } } mark{g_fu_l3_event[dev], st};   // after the launch below
+#endif
     if (composite_out != nullptr) {           // compositing inside the kernel: CTAs walk whole rays
         const int blocks = (int)(n < 148 ? n : 148);
         cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);

@@ -167,7 +167,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             float dsg = 0.f;
             const bool glive = mg < M;
             if (glive) {
-                const long long ray = mg / k.S;
+                const long long ray = egn_ray_of(mg, k.S);
                 const float z = zs[mg];
                 const float* ry = rays + ray * 6;
                 cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);

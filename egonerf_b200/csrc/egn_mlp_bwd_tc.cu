@@ -118,7 +118,7 @@ egn_mlp_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __res
             e8[0] = a.x; e8[1] = a.y; e8[2] = a.z; e8[3] = a.w;
             if (q < 3) { const float4 b = __ldg(f4 + 1); e8[4] = b.x; e8[5] = b.y; e8[6] = b.z; e8[7] = b.w; }
         }
-        const float* dir = rays + (lv ? g_m / k.S : 0) * 6 + 3;
+        const float* dir = rays + (lv ? egn_ray_of(g_m, k.S) : 0) * 6 + 3;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int e = 8 * q + j;

@@ -116,7 +116,7 @@ egn_mlp_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
                     el[4 * g] = v.x; el[4 * g + 1] = v.y; el[4 * g + 2] = v.z; el[4 * g + 3] = v.w;
                 }
             }
-            const float* dir = rays + (g_m / k.S) * 6 + 3;
+            const float* dir = rays + egn_ray_of(g_m, k.S) * 6 + 3;
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
                 const int e = EPT * q + j;
