@@ -1,19 +1,21 @@
 // Fused fine pass (throughput mode, EGN_MLP_TC_F16): Yin-Yang coordinates -> 18-tap factor gather -> VM products
 // -> basis contraction -> positional encoding -> 3-layer MLP -> sample colour, in ONE persistent warp-specialised kernel.
 // Replaces egn_gather_kernel + egn_mlp_*_kernel for one ray chunk (EgoNeRF.py:544-556: from_cartesian / normalize_coord,
-// compute_densityfeature, compute_appfeature, renderModule).  One CTA per SM, 512 threads:
+// compute_densityfeature, compute_appfeature, renderModule).  One CTA per SM, 768 threads at 80 registers (FU_GATHER_WARPS = 16;
+// the round-1 cut, 8 gather warps x 16 rows at 128 registers, is still selectable):
 //
-//   warps 8..15  GATHER group   per 128-sample tile, each warp owns 16 rows and runs three phases on them:
-//                  1. ADDRESS   one lane per sample: coordinates (every second tile for two tiles at once, all 32 lanes busy),
+//   warps 8..23  GATHER group   per 128-sample tile, each warp owns 8 rows and runs three phases on them:
+//                  1. ADDRESS   one lane per sample: coordinates (every fourth tile for four tiles at once, all 32 lanes busy),
 //                               then per-axis texel indices + tap weights -> the 18 global texel indices and 18 fp32 weights
 //                               of the sample go to a 144-byte record in shared memory.  Done ONCE per sample instead of
 //                               once per lane of the sample (the r01 kernel spent half its gather instructions here).
-//                  2. DENSITY   4 lanes per sample, 8 samples per pass: 16 fp32 channels per tap (exact: alpha stays inside the
-//                               parity bound), FFMA interpolation, relu-sum -> sigma feature.
-//                  3. APPEARANCE 8 lanes per sample (6 active), 4 samples per pass: 48 fp16 channels per tap = one aligned
+//                  2. DENSITY   4 lanes per sample, one pass of 8 samples: 16 fp32 channels per tap (exact: alpha stays inside
+//                               the parity bound), FFMA interpolation, relu-sum -> sigma feature.
+//                  3. APPEARANCE 8 lanes per sample (6 active), two passes of 4 samples: 48 fp16 channels per tap = one aligned
 //                               128-byte line, packed half2 interpolation (HFMA2: two channels per instruction, no unpacking),
 //                               the 144 products P*L go straight into shared memory as an fp16 row of the tcgen05 A operand V.
 //                               V is double buffered: tile i+1 is gathered while tile i runs through the MLP.
+//                 Two factor pairs of taps (12 loads per lane) are in flight per warp, 192 per SM.
 //   warps 0..7   MLP group      feat2 = V [B_yin | B_yang]^T (tcgen05, N = 64; the epilogue picks the sample's
 //                               hemisphere) -> PE -> X -> D1 -> relu -> H1 -> D2 -> relu . W3 -> sigmoid   (as egn_mlp_tc.cu)
 //   thread 0                    issues every tcgen05.mma; completions come back through tcgen05.commit -> mbarrier
@@ -28,7 +30,13 @@
 #include "egn_host.h"
 #include "egn_shared.cuh"
 
-#define FU_THREADS 512
+#ifndef FU_GATHER_WARPS
+#define FU_GATHER_WARPS 16                   // 8: 16 rows of every tile per gather warp (512 threads, 128 registers); 16: 8 rows (768 threads, 80 registers)
+#endif
+#ifndef FU_DEPTH
+#define FU_DEPTH 2                           // factor pairs of taps in flight per gather warp in the 16-warp variant (3 spills at 80 registers: 6.03 ms)
+#endif
+#define FU_THREADS (256 + 32 * FU_GATHER_WARPS)
 #define FU_GROUP 256
 #define FU_VK (3 * EGN_CA)                   // 144
 #define FU_VCHUNKS (FU_VK / 8)               // 18
@@ -61,6 +69,9 @@
 // of the traffic on the L1 data pipe the kernel is bound by (profiles/r02_fused.md).  The symbol is refreshed by a device-to-
 // device copy from the operand image before every launch, on the launch's stream; launches on DIFFERENT streams are ordered
 // against each other by an event per device (a later copy waits for the earlier kernel), under a host mutex.
+#ifndef FU_FFMA2
+#define FU_FFMA2 0                           // layer 3 with packed fp32 FFMA2 / FADD2 (two hidden units per instruction): 5.40 vs 5.37 ms with 16 gather warps
+#endif
 #ifndef FU_L3_CONST
 #define FU_L3_CONST 0                        // measured: 5.54 ms with the constant-bank table vs 5.41 ms (LDCU.128 into uniform registers is slower than the LDS it saves)
 #endif
@@ -97,6 +108,24 @@ struct FuDiv {
     __device__ __forceinline__ void init(uint32_t div) { d = div; magic = (uint32_t)((0x100000000ull + div - 1) / div); }
     __device__ __forceinline__ uint32_t operator()(uint32_t n) const { return d == 1 ? n : __umulhi(n, magic); }
 };
+
+// packed fp32 arithmetic of sm_100 (SASS FFMA2 / FADD2): two independent fp32 operations per instruction, each IEEE-rounded
+__device__ __forceinline__ float2 fu_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fu_fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fu_fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
 
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -242,8 +271,16 @@ egn_fused_image_kernel(int AD, const float* __restrict__ basis0, const float* __
         const float* B = (n >> 5) ? basis1 : basis0;
         store_elem_h(img + L::BB, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
     }
+#if FU_FFMA2 && !FU_L3_CONST
+    for (int i = t0; i < EGN_HID / 2; i += nthreads) {               // per PAIR of hidden units (2i, 2i+1): {b2, b2, W3[0], W3[0]} {W3[1], W3[1], W3[2], W3[2]}
+        reinterpret_cast<float4*>(img + L::L3)[2 * i] = make_float4(b2[2 * i], b2[2 * i + 1], w3[2 * i], w3[2 * i + 1]);
+        reinterpret_cast<float4*>(img + L::L3)[2 * i + 1] = make_float4(w3[EGN_HID + 2 * i], w3[EGN_HID + 2 * i + 1], w3[2 * EGN_HID + 2 * i],
+                                                                        w3[2 * EGN_HID + 2 * i + 1]);
+    }
+#else
     for (int i = t0; i < EGN_HID; i += nthreads)
         reinterpret_cast<float4*>(img + L::L3)[i] = make_float4(b2[i], w3[i], w3[EGN_HID + i], w3[2 * EGN_HID + i]);
+#endif
 }
 
 // COMP = true (forward-only calls with S a multiple of 128): compositing runs inside the kernel too (EgoNeRF.py:579-598,
@@ -285,7 +322,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        mbar_init(v_full0, 8); mbar_init(v_full0 + 8, 8);          // one arrive per gather warp
+        mbar_init(v_full0, FU_GATHER_WARPS); mbar_init(v_full0 + 8, FU_GATHER_WARPS);          // one arrive per gather warp
         mbar_init(v_empty0, 1); mbar_init(v_empty0 + 8, 1);        // tcgen05.commit
         mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(img_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -319,6 +356,86 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     };
     auto ray_of = [&](uint32_t m) -> uint32_t { return div_s(m >> 5); };       // sample index -> ray
 
+#if FU_GATHER_WARPS == 16
+    if (warp >= 8) {
+        // =========================== GATHER group, 16 warps x 8 rows ===========================
+        // Twice the warps over the same rows: the gather chain of a tile is split over 16 instruction streams (4 per scheduler
+        // next to 2 MLP warps) instead of 8.  Coordinates: every fourth iteration for four tiles at once (lanes 8g .. 8g+7 take
+        // the warp's rows of tile it + g).  Density: one pass of 8 samples; appearance: two passes of 4 samples.
+        const int gwarp = warp - 8, row0 = 8 * gwarp;
+        uint4* recs = reinterpret_cast<uint4*>(smem + L::REC) + gwarp * (8 * (FU_REC_WORDS / 4));
+        const uint4* app = reinterpret_cast<const uint4*>(k.tables_h);
+        const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
+        YYCoord held;
+        held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
+        for (uint32_t it = 0; it < n_local; ++it) {
+            const uint32_t tile = tile_of(it);
+            const uint32_t b = FU_VBUFS == 2 ? (it & 1) : 0, u = FU_VBUFS == 2 ? (it >> 1) : it;
+            if ((it & 3) == 0) {
+                const uint32_t g = lane >> 3;
+                const uint32_t m = tile_of(it + g) * TC_TM + row0 + (lane & 7);
+                held.c[0] = held.c[1] = held.c[2] = -3.f;            // out of range -> every tap gets weight zero
+                held.yang = 0;
+                if (m < M32 && it + g < n_local) {
+                    const float z = zs[m];
+                    const float* ry = rays + (size_t)ray_of(m) * 6;
+                    held = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+                }
+            }
+            YYCoord cc;
+            {
+                const int src = (lane & 7) + 8 * (it & 3);
+                cc.c[0] = __shfl_sync(FULL, held.c[0], src);
+                cc.c[1] = __shfl_sync(FULL, held.c[1], src);
+                cc.c[2] = __shfl_sync(FULL, held.c[2], src);
+                cc.yang = __shfl_sync(FULL, held.yang, src);
+            }
+            if (lane < 8) {
+                FuRecord R;
+                fused_address_record(k, cc, R);
+                fused_store_record(R, recs + lane * (FU_REC_WORDS / 4));
+                s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
+            }
+            __syncwarp();
+            // ---- density (fp32): 8 samples x 4 lanes, three factor pairs ----
+            {
+                const unsigned sub = lane & 3;
+                const uint4* rec = recs + (lane >> 2) * (FU_REC_WORDS / 4);
+                float4 t[FU_DEPTH][6];
+#pragma unroll
+                for (int i = 0; i < FU_DEPTH; ++i) fused_density_issue(dens, rec, i, sub, t[i]);
+                float f = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    f += fused_density_unit(rec, i, t[i % FU_DEPTH]);
+                    if (i + FU_DEPTH < 3) fused_density_issue(dens, rec, i + FU_DEPTH, sub, t[i % FU_DEPTH]);
+                }
+                const uint32_t m = tile * TC_TM + row0 + (lane >> 2);
+                if (sub == 0 && m < M32) fsig[m] = f;
+            }
+            // ---- appearance (fp16) into the V operand: 2 passes x 4 samples x 3 factor pairs = 6 units ----
+            {
+                const unsigned q = min(lane & 7, 5);
+                const bool owner = (lane & 7) < 6;
+                const uint4* recA = recs + (lane >> 3) * (FU_REC_WORDS / 4);
+                const uint4* recB = recA + 4 * (FU_REC_WORDS / 4);
+                unsigned char* vrow = vs + b * FU_VBYTES + (row0 + (lane >> 3)) * 16 + q * FU_VCHUNK;
+                uint4 t[FU_DEPTH][6];
+#pragma unroll
+                for (int un = 0; un < FU_DEPTH; ++un) fused_app_issue(app, un / 3 ? recB : recA, un % 3, q, t[un]);
+                ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);      // layer-0 MMAs of the tile that used this buffer are done
+#pragma unroll
+                for (int un = 0; un < 6; ++un) {
+                    const uint4 o = fused_app_unit(un / 3 ? recB : recA, un % 3, t[un % FU_DEPTH]);
+                    if (owner) *reinterpret_cast<uint4*>(vrow + (un / 3) * (4 * 16) + (un % 3) * (EGN_CA / 8) * FU_VCHUNK) = o;
+                    if (un + FU_DEPTH < 6) fused_app_issue(app, (un + FU_DEPTH) / 3 ? recB : recA, (un + FU_DEPTH) % 3, q, t[un % FU_DEPTH]);
+                }
+            }
+            fence_async_smem();                                      // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(v_full0 + 8 * b);
+        }
+#else
     if (warp >= 8) {
         // =========================== GATHER group ===========================
         const int gwarp = warp - 8, row0 = 16 * gwarp;
@@ -406,6 +523,7 @@ FU_UNROLL(FU_APP_UNROLL)
             __syncwarp();
             if (lane == 0) mbar_arrive(v_full0 + 8 * b);
         }
+#endif
     } else {
         // =========================== MLP group ===========================
         const int row = tid & 127, half = tid >> 7;
@@ -465,6 +583,26 @@ FU_UNROLL(FU_APP_UNROLL)
                 }
             };
             if (half == 0) dot64(std::integral_constant<int, 0>{}); else dot64(std::integral_constant<int, 1>{});
+#elif FU_FFMA2
+            {
+                float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;     // even / odd hidden units accumulate separately
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col = 64 * half + 32 * cc;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_lane + 128 + col, r);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 wa = l3s[col + 2 * j], wb = l3s[col + 2 * j + 1];          // two broadcast LDS.128 per unit pair
+                        float2 h = fu_fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), make_float2(wa.x, wa.y));
+                        h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
+                        q0 = fu_ffma2(h, make_float2(wa.z, wa.w), q0);
+                        q1 = fu_ffma2(h, make_float2(wb.x, wb.y), q1);
+                        q2 = fu_ffma2(h, make_float2(wb.z, wb.w), q2);
+                    }
+                }
+                p0 = q0.x + q0.y; p1 = q1.x + q1.y; p2 = q2.x + q2.y;
+            }
 #else
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {

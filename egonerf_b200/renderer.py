@@ -7,6 +7,7 @@ import torch
 
 
 MIN_EVAL_CHUNK = 65536
+HOST_SINK_CHUNK = 16384
 
 
 class _HostSink:
@@ -52,6 +53,10 @@ def volume_renderer(rays, model, chunk=4096, n_coarse=-1, n_fine=0, ndc_ray=Fals
     # depths of the FIRST ray of each chunk (EgoNeRF.py:515-516) and is therefore chunk-dependent in the reference itself.
     if not is_train and exp_sampling and chunk < MIN_EVAL_CHUNK:
         chunk = MIN_EVAL_CHUNK
+    # When every chunk leaves the device (`empty_gpu_cache=True`, 1 KB of alpha per ray), chunks of HOST_SINK_CHUNK rays let the
+    # device->host copy of chunk c run behind the kernels of chunk c+1 instead of after the only chunk of a 65 536-ray call.
+    if not is_train and exp_sampling and empty_gpu_cache:
+        chunk = min(chunk, HOST_SINK_CHUNK)
     start = time.time()
     has_env = False
     sink = None

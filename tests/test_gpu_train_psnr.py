@@ -86,3 +86,58 @@ def test_training_psnr_matches_reference_algorithm():
     assert abs(results[("tc_split", "f32")] - psnr_ref) <= 0.05
     assert abs(results[("tc_bf16", "f32")] - psnr_ref) <= 0.05
     assert abs(results[("tc_bf16", "bf16")] - psnr_ref) <= 0.05
+
+
+def test_long_run_psnr_of_the_default_mode(capsys):
+    """128^3 grid, 300 Adam steps of 4096 rays (the run of scripts/train_demo.py, promoted to a test): the default mode
+    (fused tcgen05 forward, tcgen05 backward, table-space Adam) against the fp32-equivalent mode (tc_split forward, exact
+    fp32 backward, torch Adam) from identical initialisation, batches and sampler seeds.  Every student is evaluated on 8192
+    held-out rays with the exact renderer AND with the default-mode renderer.  Training runs are not bit-reproducible (fp32
+    atomics in the gradient scatter), so the fp32-equivalent run is made twice and its own run-to-run spread is added to the
+    north_star bound of 0.05 dB."""
+    from egonerf_b200.optim import TableAdam
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    from egonerf_b200.synthetic import make_rays, make_scene
+    dev, steps, batch = "cuda:0", 300, 4096
+    teacher = model_from_scene(make_scene(n_voxels=128 ** 3, seed=7), dev)
+    teacher.mlp_mode = "tc_split"
+    student_scene = make_scene(n_voxels=128 ** 3, seed=11, sigma_std=0.4)
+    held = make_rays(8192, 'isotropic', seed=4242).to(dev)
+    rays_all = make_rays(batch * 64, 'isotropic', seed=99).to(dev)
+    with torch.no_grad():
+        gt = teacher(held, is_train=False, **RENDER_KW)[0]
+        tgt_all = torch.cat([teacher(rays_all[i:i + 65536], is_train=False, **RENDER_KW)[0] for i in range(0, rays_all.shape[0], 65536)])
+
+    def fit(mode, tables, table_adam):
+        model = model_from_scene(student_scene, dev)
+        model.mlp_mode, model.table_dtype = mode, tables
+        opt = TableAdam(model, 0.02, 0.001) if table_adam else \
+            torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
+        g = torch.Generator(device=dev).manual_seed(1)
+        for it in range(steps):
+            idx = torch.randint(0, rays_all.shape[0], (batch,), device=dev, generator=g)
+            opt.zero_grad()
+            rgb = model(rays_all[idx], is_train=True, seed=1000 + it, **RENDER_KW)[0]
+            ((rgb - tgt_all[idx]) ** 2).mean().backward()
+            opt.step()
+            model.update_coarse_sigma_grid()
+        out = {}
+        with torch.no_grad():
+            for ev_mode, ev_tables in (("tc_split", "f32"), ("tc_f16", "bf16")):
+                model.mlp_mode, model.table_dtype = ev_mode, ev_tables
+                out[ev_mode] = _psnr(model(held, is_train=False, **RENDER_KW)[0], gt)
+        return out
+
+    exact_a = fit("tc_split", "f32", False)
+    exact_b = fit("tc_split", "f32", False)
+    fast = fit("tc_f16", "bf16", True)
+    spread = abs(exact_a["tc_split"] - exact_b["tc_split"])
+    ref = 0.5 * (exact_a["tc_split"] + exact_b["tc_split"])
+    with capsys.disabled():
+        print(f"\n128^3 / 300 steps: fp32-equivalent runs {exact_a['tc_split']:.3f} / {exact_b['tc_split']:.3f} dB (spread {spread:.3f}); "
+              f"default mode {fast['tc_split']:.3f} dB with the exact renderer, {fast['tc_f16']:.3f} dB with its own renderer; "
+              f"exact student under the default renderer {exact_a['tc_f16']:.3f} dB")
+    assert ref > 25.0, "the run must actually learn something (starts at ~10.5 dB)"
+    assert abs(fast["tc_split"] - ref) <= 0.05 + spread
+    assert abs(fast["tc_f16"] - fast["tc_split"]) <= 0.01          # renderer-to-renderer difference on the same student
+    assert abs(exact_a["tc_f16"] - exact_a["tc_split"]) <= 0.01
