@@ -127,6 +127,37 @@ __device__ __forceinline__ float2 fu_fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2*>(&d);
 }
 
+// L2 residency: the factor tables (74 MB) fit the 126 MB L2, but every launch also streams z, sigma feature and alpha (3 x 67 MB at
+// cfg2) through it.  FU_L2_HINTS: table taps are loaded with an evict_last policy, the streams with evict_first.
+#ifndef FU_L2_HINTS
+#define FU_L2_HINTS 0                        // 1: streaming stores, 2: + evict_last table loads -- measured: no effect (5.38 / 5.38 / 5.39 ms)
+#endif
+__device__ __forceinline__ uint64_t fu_policy_keep() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 fu_ldg_keep(const uint4* ptr, uint64_t pol) {
+#if FU_L2_HINTS >= 2
+    uint4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
+    return v;
+#else
+    return __ldg(ptr);
+#endif
+}
+__device__ __forceinline__ float4 fu_ldg_keep(const float4* ptr, uint64_t pol) {
+    const uint4 v = fu_ldg_keep(reinterpret_cast<const uint4*>(ptr), pol);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ void fu_st_stream(float* ptr, float v) {
+#if FU_L2_HINTS >= 1
+    __stcs(ptr, v);
+#else
+    *ptr = v;
+#endif
+}
+
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -191,11 +222,11 @@ __device__ __forceinline__ void fused_store_record(const FuRecord& R, uint4* __r
 // density: 4 lanes x 4 fp32 channels per sample; lane group h = lane >> 2 takes row 8p + h in pass p (8 consecutive rows per
 // load instruction: identical texels of neighbouring samples are fetched once by the L1 tag stage)
 __device__ __forceinline__ void fused_density_issue(const float4* __restrict__ dens, const uint4* __restrict__ rec, int i, unsigned sub,
-                                                    float4 (&t)[6]) {
+                                                    float4 (&t)[6], uint64_t pol) {
     const uint4 a = rec[3 * i], b = rec[3 * i + 1];
-    t[0] = __ldg(dens + (a.x * 4u + sub)); t[1] = __ldg(dens + (a.y * 4u + sub));
-    t[2] = __ldg(dens + (a.z * 4u + sub)); t[3] = __ldg(dens + (a.w * 4u + sub));
-    t[4] = __ldg(dens + (b.x * 4u + sub)); t[5] = __ldg(dens + (b.y * 4u + sub));
+    t[0] = fu_ldg_keep(dens + (a.x * 4u + sub), pol); t[1] = fu_ldg_keep(dens + (a.y * 4u + sub), pol);
+    t[2] = fu_ldg_keep(dens + (a.z * 4u + sub), pol); t[3] = fu_ldg_keep(dens + (a.w * 4u + sub), pol);
+    t[4] = fu_ldg_keep(dens + (b.x * 4u + sub), pol); t[5] = fu_ldg_keep(dens + (b.y * 4u + sub), pol);
 }
 __device__ __forceinline__ float fused_density_unit(const uint4* __restrict__ rec, int i, const float4 (&t)[6]) {
     const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];
@@ -216,11 +247,11 @@ __device__ __forceinline__ float fused_density_unit(const uint4* __restrict__ re
 // 6, 7 shadow lane 5 -- same addresses, no extra wavefront, no divergent control flow -- and only skip the store); the four
 // quarters of pass p take the four consecutive rows 4p + g
 __device__ __forceinline__ void fused_app_issue(const uint4* __restrict__ app, const uint4* __restrict__ rec, int i, unsigned q,
-                                                uint4 (&t)[6]) {
+                                                uint4 (&t)[6], uint64_t pol) {
     const uint4 a = rec[3 * i], b = rec[3 * i + 1];
-    t[0] = __ldg(app + (a.x * 8u + q)); t[1] = __ldg(app + (a.y * 8u + q));
-    t[2] = __ldg(app + (a.z * 8u + q)); t[3] = __ldg(app + (a.w * 8u + q));
-    t[4] = __ldg(app + (b.x * 8u + q)); t[5] = __ldg(app + (b.y * 8u + q));
+    t[0] = fu_ldg_keep(app + (a.x * 8u + q), pol); t[1] = fu_ldg_keep(app + (a.y * 8u + q), pol);
+    t[2] = fu_ldg_keep(app + (a.z * 8u + q), pol); t[3] = fu_ldg_keep(app + (a.w * 8u + q), pol);
+    t[4] = fu_ldg_keep(app + (b.x * 8u + q), pol); t[5] = fu_ldg_keep(app + (b.y * 8u + q), pol);
 }
 __device__ __forceinline__ uint4 fused_app_unit(const uint4* __restrict__ rec, int i, const uint4 (&t)[6]) {
     const uint4 b = rec[3 * i + 1], c = rec[3 * i + 2];
@@ -366,6 +397,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         uint4* recs = reinterpret_cast<uint4*>(smem + L::REC) + gwarp * (8 * (FU_REC_WORDS / 4));
         const uint4* app = reinterpret_cast<const uint4*>(k.tables_h);
         const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
+        const uint64_t pol = fu_policy_keep();
         YYCoord held;
         held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
         for (uint32_t it = 0; it < n_local; ++it) {
@@ -403,15 +435,15 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 const uint4* rec = recs + (lane >> 2) * (FU_REC_WORDS / 4);
                 float4 t[FU_DEPTH][6];
 #pragma unroll
-                for (int i = 0; i < FU_DEPTH; ++i) fused_density_issue(dens, rec, i, sub, t[i]);
+                for (int i = 0; i < FU_DEPTH; ++i) fused_density_issue(dens, rec, i, sub, t[i], pol);
                 float f = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     f += fused_density_unit(rec, i, t[i % FU_DEPTH]);
-                    if (i + FU_DEPTH < 3) fused_density_issue(dens, rec, i + FU_DEPTH, sub, t[i % FU_DEPTH]);
+                    if (i + FU_DEPTH < 3) fused_density_issue(dens, rec, i + FU_DEPTH, sub, t[i % FU_DEPTH], pol);
                 }
                 const uint32_t m = tile * TC_TM + row0 + (lane >> 2);
-                if (sub == 0 && m < M32) fsig[m] = f;
+                if (sub == 0 && m < M32) fu_st_stream(fsig + m, f);
             }
             // ---- appearance (fp16) into the V operand: 2 passes x 4 samples x 3 factor pairs = 6 units ----
             {
@@ -422,13 +454,13 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 unsigned char* vrow = vs + b * FU_VBYTES + (row0 + (lane >> 3)) * 16 + q * FU_VCHUNK;
                 uint4 t[FU_DEPTH][6];
 #pragma unroll
-                for (int un = 0; un < FU_DEPTH; ++un) fused_app_issue(app, un / 3 ? recB : recA, un % 3, q, t[un]);
+                for (int un = 0; un < FU_DEPTH; ++un) fused_app_issue(app, un / 3 ? recB : recA, un % 3, q, t[un], pol);
                 ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);      // layer-0 MMAs of the tile that used this buffer are done
 #pragma unroll
                 for (int un = 0; un < 6; ++un) {
                     const uint4 o = fused_app_unit(un / 3 ? recB : recA, un % 3, t[un % FU_DEPTH]);
                     if (owner) *reinterpret_cast<uint4*>(vrow + (un / 3) * (4 * 16) + (un % 3) * (EGN_CA / 8) * FU_VCHUNK) = o;
-                    if (un + FU_DEPTH < 6) fused_app_issue(app, (un + FU_DEPTH) / 3 ? recB : recA, (un + FU_DEPTH) % 3, q, t[un % FU_DEPTH]);
+                    if (un + FU_DEPTH < 6) fused_app_issue(app, (un + FU_DEPTH) / 3 ? recB : recA, (un + FU_DEPTH) % 3, q, t[un % FU_DEPTH], pol);
                 }
             }
             fence_async_smem();                                      // generic-proxy stores -> visible to the tensor core
@@ -442,6 +474,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
         uint4* recs = reinterpret_cast<uint4*>(smem + L::REC) + gwarp * FU_REC_WARP_UINT4;
         const uint4* app = reinterpret_cast<const uint4*>(k.tables_h);
         const float4* dens = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(k.tables_h) + k.dens_byte_offset);
+        const uint64_t pol = fu_policy_keep();
         YYCoord held;                                                // coordinates computed one tile ahead (lanes 16..31)
         held.c[0] = held.c[1] = held.c[2] = -3.f; held.yang = 0;
         for (uint32_t it = 0; it < n_local; ++it) {
@@ -480,7 +513,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 const uint4* rec = recs + fu_rec_slot(lane >> 2);
                 float4 t[3][6];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) fused_density_issue(dens, rec, i, sub, t[i]);
+                for (int i = 0; i < 3; ++i) fused_density_issue(dens, rec, i, sub, t[i], pol);
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     const uint4* nxt = recs + fu_rec_slot(8 * (p + 1) + (lane >> 2));
@@ -488,10 +521,10 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         f += fused_density_unit(rec, i, t[i]);
-                        if (p == 0) fused_density_issue(dens, nxt, i, sub, t[i]);
+                        if (p == 0) fused_density_issue(dens, nxt, i, sub, t[i], pol);
                     }
                     const uint32_t m = tile * TC_TM + row0 + 8 * p + (lane >> 2);
-                    if (sub == 0 && m < M32) fsig[m] = f;
+                    if (sub == 0 && m < M32) fu_st_stream(fsig + m, f);
                     rec = nxt;
                 }
             }
@@ -504,7 +537,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 unsigned char* vrow = vs + b * FU_VBYTES + (row0 + (lane >> 3)) * 16 + q * FU_VCHUNK;
                 uint4 t[3][6];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) fused_app_issue(app, rec, i, q, t[i]);
+                for (int i = 0; i < 3; ++i) fused_app_issue(app, rec, i, q, t[i], pol);
                 ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);      // layer-0 MMAs of the tile that used this buffer are done
 FU_UNROLL(FU_APP_UNROLL)
                 for (int p = 0; p < 4; ++p) {
@@ -513,7 +546,7 @@ FU_UNROLL(FU_APP_UNROLL)
                     for (int i = 0; i < 3; ++i) {
                         const uint4 o = fused_app_unit(rec, i, t[i]);
                         if (owner) *reinterpret_cast<uint4*>(vrow + i * (EGN_CA / 8) * FU_VCHUNK) = o;   // K index i*48 + q*8 .. +7
-                        if (p < 3) fused_app_issue(app, nxt, i, q, t[i]);
+                        if (p < 3) fused_app_issue(app, nxt, i, q, t[i], pol);
                     }
                     rec = nxt;
                     vrow += 4 * 16;
@@ -623,7 +656,7 @@ FU_UNROLL(FU_APP_UNROLL)
                 if constexpr (COMP) {
                     const float dist = ((j3 + 1 < k.S) ? (znext - zrow) : (zrow - znext)) * k.distance_scale;
                     a = 1.f - expf(-egn_density_act(fs, k.density_shift, k.fea2dense) * dist);
-                    out.alpha[(size_t)ray3 * acols + j3] = a;
+                    fu_st_stream(out.alpha + (size_t)ray3 * acols + j3, a);
                 }
                 *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, a);
             }
@@ -813,7 +846,10 @@ int egn_launch_fused_fine(const EgnKernelCfg& k, const EgnParams* p, const float
     struct Mark { cudaEvent_t e; cudaStream_t s; ~Mark() { cudaEventRecord(e, s); } } mark{g_fu_l3_event[dev], st};   // after the launch below
 #endif
     if (composite_out != nullptr) {           // compositing inside the kernel: CTAs walk whole rays
-        const int blocks = (int)(n < 148 ? n : 148);
+#ifndef FU_MAX_BLOCKS
+#define FU_MAX_BLOCKS 148
+#endif
+        const int blocks = (int)(n < FU_MAX_BLOCKS ? n : FU_MAX_BLOCKS);
         cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuLayout::TOTAL);
 #ifdef FU_CARVEOUT
         cudaFuncSetAttribute(egn_fused_fine_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, FU_CARVEOUT);

@@ -44,14 +44,17 @@ __device__ __forceinline__ void gt_red4(float* addr, float4 v) { atomicAdd(reint
 __device__ __forceinline__ float4 gt_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
 
 // register cache of the angular-tap gradients of one half-warp (see Ph3)
+#ifndef GT_LINES_CACHED
+#define GT_LINES_CACHED 2            // 2: phi / theta lines; 3: the r line too (10 more registers)
+#endif
 struct GtCache {
-    unsigned po[4], lo[2][2];        // element offsets of the cached taps (0xffffffff = empty)
-    float4 pa[4], la[2][2];
+    unsigned po[4], lo[GT_LINES_CACHED][2];        // element offsets of the cached taps (0xffffffff = empty)
+    float4 pa[4], la[GT_LINES_CACHED][2];
     __device__ __forceinline__ void reset() {
 #pragma unroll
         for (int t = 0; t < 4; ++t) { po[t] = 0xffffffffu; pa[t] = f4zero(); }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { lo[i][0] = lo[i][1] = 0xffffffffu; la[i][0] = la[i][1] = f4zero(); }
+        for (int i = 0; i < GT_LINES_CACHED; ++i) { lo[i][0] = lo[i][1] = 0xffffffffu; la[i][0] = la[i][1] = f4zero(); }
     }
     __device__ __forceinline__ static bool nz(const float4& v) { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); }
     __device__ __forceinline__ void flush_plane(float* d_tab) {
@@ -222,7 +225,12 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         cache.reset();
 #pragma unroll 1
         for (int itr = 0; itr < 4; ++itr) {
-            const int src = 2 * itr + (lane >> 4);              // sample within the warp's 8
+#ifndef GT_CONSECUTIVE
+#define GT_CONSECUTIVE 1
+#endif
+            // each half-warp walks 4 CONSECUTIVE samples of the ray (0..3 / 4..7): neighbours share texels far more often than
+            // samples two apart, so the register cache below flushes less
+            const int src = GT_CONSECUTIVE ? 4 * (lane >> 4) + itr : 2 * itr + (lane >> 4);              // sample within the warp's 8
             const int srow = 8 * warp + src;
             const float4 sc = s_coord[srow];
             const float c[3] = {sc.x, sc.y, sc.z};
@@ -310,7 +318,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                         if (w2 != 0.f) gt_red4(d_tab + o2, gt_scale(w2, dP));
                         if (w3 != 0.f) gt_red4(d_tab + o3, gt_scale(w3, dP));
                     }
-                    if (i < 2) {                                    // phi / theta lines: cached
+                    if (i < GT_LINES_CACHED) {                      // phi / theta (/ r) lines: cached
                         if (cache.lo[i][0] != q0 || cache.lo[i][1] != q1) {
                             cache.flush_line(d_tab, i);
                             cache.lo[i][0] = q0; cache.lo[i][1] = q1;
@@ -325,8 +333,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             }
         }
         cache.flush_plane(d_tab);
-        cache.flush_line(d_tab, 0);
-        cache.flush_line(d_tab, 1);
+#pragma unroll
+        for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_tab, i);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();

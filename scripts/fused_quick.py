@@ -14,7 +14,7 @@ from egonerf_b200.synthetic import make_rays, make_scene               # noqa: E
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "run"
 dev = torch.device("cuda:0")
-scene = make_scene(n_voxels=27e6)
+scene = make_scene(n_voxels=float(os.environ.get("EGN_QUICK_VOXELS", 27e6)))
 model = model_from_scene(scene, dev)
 rays = make_rays(65536, 'isotropic', seed=1000).to(dev)
 out = {"tag": tag}
