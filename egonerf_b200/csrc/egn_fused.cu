@@ -63,12 +63,17 @@
 #endif
 #define FU_IDESC_128x128 0x08200010u         // kind::f16: D fp32, A/B fp16, both K-major, N = 128, M = 128
 #define FU_IDESC_128x64  0x08100010u         // same, N = 64
+#define FU_IDESC_128x16  0x08040010u         // same, N = 16
+#define FU_W3_CHUNK 128                      // layer-3 operand: 8 rows (3 used) x 16 B per K chunk; the N = 16 tile reads them twice (SBO = 0)
 
 // Layer-3 table {b2, W3[0], W3[1], W3[2]} per hidden unit, as constant-bank operands of the epilogue's FADD / FFMA (FU_L3_CONST):
 // the 64 broadcast LDS.128 per thread and tile it replaces were 1 053 of the 3 122 shared-memory wavefronts of a tile, i.e. 13 %
 // of the traffic on the L1 data pipe the kernel is bound by (profiles/r02_fused.md).  The symbol is refreshed by a device-to-
 // device copy from the operand image before every launch, on the launch's stream; launches on DIFFERENT streams are ordered
 // against each other by an event per device (a later copy waits for the earlier kernel), under a host mutex.
+#ifndef FU_L3_MMA
+#define FU_L3_MMA 1                          // layer 3 as a fourth MMA: H2 = relu(D2 + b2) goes back to shared memory as an fp16 operand, D3 = H2 . W3^T (N = 16)
+#endif
 #ifndef FU_FFMA2
 #define FU_FFMA2 0                           // layer 3 with packed fp32 FFMA2 / FADD2 (two hidden units per instruction): 5.40 vs 5.37 ms with 16 gather warps
 #endif
@@ -87,16 +92,18 @@ struct FuLayout {
     static constexpr int W2 = W1 + (TC_K1 / 8) * TC_CHUNK;            // 40 960
     static constexpr int BB = W2 + (EGN_HID / 8) * TC_CHUNK;          // + 32 768
     static constexpr int L3 = BB + FU_VCHUNKS * FU_BB_CHUNK;          // + 18 432; layer 3: per hidden unit {b2, W3[0], W3[1], W3[2]}: 128 x float4
-    static constexpr int IMAGE = L3 + EGN_HID * 16;                   // W1 .. L3 = the operand image, one bulk copy (94 208 bytes)
+                                                                      // (FU_L3_MMA: W3 as an fp16 K-major operand, 16 chunks x 128 B)
+    static constexpr int B2 = L3 + EGN_HID * 16;                      // FU_L3_MMA: b2, 128 floats
+    static constexpr int IMAGE = B2 + (FU_L3_MMA ? EGN_HID * 4 : 0);  // W1 .. = the operand image, one bulk copy (94 208 / 94 720 bytes)
     static constexpr int A = IMAGE;
     static constexpr int V = A + (TC_K1 / 8) * TC_CHUNK;              // + 40 960 ; two buffers
     static constexpr int REC = V + FU_VBUFS * FU_VBYTES;                     // address records: 128 samples x 144 B
-    static constexpr int YANG = REC + 8 * (16 * (FU_REC_WORDS / 4) + 1) * 16;   // 8 warps x (16 records + 1 swizzle slot); then 4 x 128 bytes
+    static constexpr int YANG = REC + (FU_GATHER_WARPS == 16 ? TC_TM * (FU_REC_WORDS / 4) : 8 * (16 * (FU_REC_WORDS / 4) + 1)) * 16;   // records (8-warp cut: + 1 swizzle slot per warp); then 4 x 128 bytes
     static constexpr int KNOTS = YANG + 4 * TC_TM;
     static constexpr int MBAR = KNOTS + ((EGN_FUSED_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
-    static constexpr int TMEM = MBAR + 8 * 8;
-    static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4
-    static constexpr int RED = PART + TC_TM * 16;                     // fused compositing: 4 warp products + 4 x 5 warp sums
+    static constexpr int TMEM = MBAR + 10 * 8;
+    static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4 (FU_L3_MMA: alpha only)
+    static constexpr int RED = PART + TC_TM * (FU_L3_MMA ? 4 : 16);   // fused compositing: 4 warp products + 4 x 5 warp sums
     static constexpr int TOTAL = RED + 4 * 8 * 4;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
@@ -302,7 +309,13 @@ egn_fused_image_kernel(int AD, const float* __restrict__ basis0, const float* __
         const float* B = (n >> 5) ? basis1 : basis0;
         store_elem_h(img + L::BB, n, kk, o < AD ? B[o * FU_VK + kk] : 0.f, FU_BB_CHUNK);
     }
-#if FU_FFMA2 && !FU_L3_CONST
+#if FU_L3_MMA
+    for (int i = t0; i < 8 * EGN_HID; i += nthreads) {                // rows 0..2 = W3, rows 3..7 zero
+        const int n = i / EGN_HID, kk = i % EGN_HID;
+        store_elem_h(img + L::L3, n, kk, n < 3 ? w3[n * EGN_HID + kk] : 0.f, FU_W3_CHUNK);
+    }
+    for (int i = t0; i < EGN_HID; i += nthreads) reinterpret_cast<float*>(img + L::B2)[i] = b2[i];
+#elif FU_FFMA2 && !FU_L3_CONST
     for (int i = t0; i < EGN_HID / 2; i += nthreads) {               // per PAIR of hidden units (2i, 2i+1): {b2, b2, W3[0], W3[0]} {W3[1], W3[1], W3[2], W3[2]}
         reinterpret_cast<float4*>(img + L::L3)[2 * i] = make_float4(b2[2 * i], b2[2 * i + 1], w3[2 * i], w3[2 * i + 1]);
         reinterpret_cast<float4*>(img + L::L3)[2 * i + 1] = make_float4(w3[EGN_HID + 2 * i], w3[EGN_HID + 2 * i + 1], w3[2 * EGN_HID + 2 * i],
@@ -340,12 +353,12 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     unsigned char* s_yang = smem + L::YANG;
     float* s_knots = reinterpret_cast<float*>(smem + L::KNOTS);
     float* part = reinterpret_cast<float*>(smem + L::PART);
-#if !FU_L3_CONST
+#if !FU_L3_CONST && !FU_L3_MMA
     float4* l3s = reinterpret_cast<float4*>(smem + L::L3);
 #endif
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
     const uint32_t bar = smem_u32(smem + L::MBAR);
-    const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48, img_full = bar + 56;
+    const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48, img_full = bar + 56, d3_full = bar + 64;
 
     // ---- one-time setup ----
     if (warp == 0) {
@@ -355,7 +368,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     if (tid == 32) {
         mbar_init(v_full0, FU_GATHER_WARPS); mbar_init(v_full0 + 8, FU_GATHER_WARPS);          // one arrive per gather warp
         mbar_init(v_empty0, 1); mbar_init(v_empty0 + 8, 1);        // tcgen05.commit
-        mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(img_full, 1);
+        mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(img_full, 1); mbar_init(d3_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the operand image (W1, W2, basis, layer-3 table: FuLayout W1 .. IMAGE) in one bulk copy, completion on img_full
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(img_full), "r"((uint32_t)L::IMAGE) : "memory");
@@ -599,6 +612,13 @@ FU_UNROLL(FU_APP_UNROLL)
                 }
             }
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#if FU_L3_MMA
+            if (half == 0) {                                         // D3 = H2 . W3^T of this tile sits in TMEM columns 384..386
+                uint32_t r4[4];
+                tmem_ld4(tmem_lane + 384, r4);
+                p0 = __uint_as_float(r4[0]); p1 = __uint_as_float(r4[1]); p2 = __uint_as_float(r4[2]);
+            }
+#else
 #if FU_L3_CONST
             // the column half is warp-uniform: two copies of the loop with compile-time constant-bank offsets
             auto dot64 = [&](auto HALF) {
@@ -650,6 +670,7 @@ FU_UNROLL(FU_APP_UNROLL)
                 }
             }
 #endif
+#endif
             tc_fence_before();
             if (half == 1) {
                 float a = 0.f;
@@ -658,11 +679,19 @@ FU_UNROLL(FU_APP_UNROLL)
                     a = 1.f - expf(-egn_density_act(fs, k.density_shift, k.fea2dense) * dist);
                     fu_st_stream(out.alpha + (size_t)ray3 * acols + j3, a);
                 }
+#if FU_L3_MMA
+                part[row] = a;
+#else
                 *reinterpret_cast<float4*>(part + row * 4) = make_float4(p0, p1, p2, a);
+#endif
             }
             named_bar_sync(1, FU_GROUP);
             if (half == 0 && gm3 < M32) {
+#if FU_L3_MMA
+                const float4 q = make_float4(0.f, 0.f, 0.f, part[row]);
+#else
                 const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
+#endif
                 const float alpha = q.w;
                 const float c0 = egn_sigmoid(p0 + q.x + bias3[0]), c1 = egn_sigmoid(p1 + q.y + bias3[1]), c2 = egn_sigmoid(p2 + q.z + bias3[2]);
                 if constexpr (!COMP) {
@@ -735,6 +764,9 @@ FU_UNROLL(FU_APP_UNROLL)
             const bool live = gm < M32;
             // ---- layer 0 of this tile was issued one iteration ago ----
             ok &= mbar_wait<FU_MLP_BACKOFF>(feat_full, it & 1);
+#if FU_L3_MMA
+            if (it > 0) ok &= mbar_wait(d3_full, (it - 1) & 1);      // layer 3 of the previous tile has finished reading the operand buffer
+#endif
             tc_fence_after();
             // ---- A. this thread's 16 elements: features of its hemisphere (from TMEM), then view direction / 1 / padding ----
             {
@@ -816,8 +848,43 @@ FU_UNROLL(FU_APP_UNROLL)
             }
             ok &= mbar_wait(d2_full, it & 1);
             tc_fence_after();
+#if FU_L3_MMA
+            // ---- E. H2 = relu(D2 + b2) -> operand of layer 3 (same buffer), D3 = H2 . W3^T ----
+            {
+                const float4* b2s = reinterpret_cast<const float4*>(smem + L::B2);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col = 64 * half + 32 * cc;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_lane + 128 + col, r);
+                    float v[32];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 bq = b2s[(col >> 2) + g];
+                        v[4 * g] = fmaxf(__uint_as_float(r[4 * g]) + bq.x, 0.f); v[4 * g + 1] = fmaxf(__uint_as_float(r[4 * g + 1]) + bq.y, 0.f);
+                        v[4 * g + 2] = fmaxf(__uint_as_float(r[4 * g + 2]) + bq.z, 0.f); v[4 * g + 3] = fmaxf(__uint_as_float(r[4 * g + 3]) + bq.w, 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) store_chunk_h(as, (col >> 3) + c, row, v + 8 * c);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                named_bar_sync(1, FU_GROUP);
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t w3_s = smem_u32(smem + L::L3);
+#pragma unroll
+                    for (int ks = 0; ks < EGN_HID / 16; ++ks)
+                        tc_mma(tmem + 384, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc_sbo(w3_s + ks * 2 * FU_W3_CHUNK, FU_W3_CHUNK, 0), FU_IDESC_128x16, ks > 0);
+                    tc_commit(d3_full);
+                }
+            }
+#endif
             gm_prev = gm;
         }
+#if FU_L3_MMA
+        if (it > 0) { ok &= mbar_wait(d3_full, (it - 1) & 1); tc_fence_after(); }
+#endif
         if (it > 0) layer3(gm_prev);                            // layer 3 of the last tile
     }
     if (!ok) __trap();                                          // a lost mbarrier arrive: fail loudly, never hang
