@@ -30,13 +30,19 @@
 #include "egn_host.h"
 #include "egn_shared.cuh"
 
+#ifndef FU_L3_MMA
+#define FU_L3_MMA 1                          // layer 3 as a fourth MMA: H2 = relu(D2 + b2) goes back to shared memory as an fp16 operand, D3 = H2 . W3^T (N = 16)
+#endif
 #ifndef FU_GATHER_WARPS
 #define FU_GATHER_WARPS 16                   // 8: 16 rows of every tile per gather warp (512 threads, 128 registers); 16: 8 rows (768 threads, 80 registers)
 #endif
 #ifndef FU_DEPTH
 #define FU_DEPTH 2                           // factor pairs of taps in flight per gather warp in the 16-warp variant (3 spills at 80 registers: 6.03 ms)
 #endif
-#define FU_THREADS (256 + 32 * FU_GATHER_WARPS)
+#ifndef FU_MMA_WARP
+#define FU_MMA_WARP (FU_GATHER_WARPS == 16 && FU_L3_MMA)     // a 25th warp issues every tcgen05.mma (800 threads x 80 registers)
+#endif
+#define FU_THREADS (256 + 32 * FU_GATHER_WARPS + 32 * FU_MMA_WARP)
 #define FU_GROUP 256
 #define FU_VK (3 * EGN_CA)                   // 144
 #define FU_VCHUNKS (FU_VK / 8)               // 18
@@ -71,9 +77,6 @@
 // of the traffic on the L1 data pipe the kernel is bound by (profiles/r02_fused.md).  The symbol is refreshed by a device-to-
 // device copy from the operand image before every launch, on the launch's stream; launches on DIFFERENT streams are ordered
 // against each other by an event per device (a later copy waits for the earlier kernel), under a host mutex.
-#ifndef FU_L3_MMA
-#define FU_L3_MMA 1                          // layer 3 as a fourth MMA: H2 = relu(D2 + b2) goes back to shared memory as an fp16 operand, D3 = H2 . W3^T (N = 16)
-#endif
 #ifndef FU_FFMA2
 #define FU_FFMA2 0                           // layer 3 with packed fp32 FFMA2 / FADD2 (two hidden units per instruction): 5.40 vs 5.37 ms with 16 gather warps
 #endif
@@ -358,7 +361,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
 #endif
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::TMEM);
     const uint32_t bar = smem_u32(smem + L::MBAR);
-    const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48, img_full = bar + 56, d3_full = bar + 64;
+    const uint32_t v_full0 = bar, v_empty0 = bar + 16, feat_full = bar + 32, d1_full = bar + 40, d2_full = bar + 48, img_full = bar + 56, d3_full = bar + 64, a_ready = bar + 72;
 
     // ---- one-time setup ----
     if (warp == 0) {
@@ -368,7 +371,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     if (tid == 32) {
         mbar_init(v_full0, FU_GATHER_WARPS); mbar_init(v_full0 + 8, FU_GATHER_WARPS);          // one arrive per gather warp
         mbar_init(v_empty0, 1); mbar_init(v_empty0 + 8, 1);        // tcgen05.commit
-        mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(img_full, 1); mbar_init(d3_full, 1);
+        mbar_init(feat_full, 1); mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(img_full, 1); mbar_init(d3_full, 1); mbar_init(a_ready, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the operand image (W1, W2, basis, layer-3 table: FuLayout W1 .. IMAGE) in one bulk copy, completion on img_full
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(img_full), "r"((uint32_t)L::IMAGE) : "memory");
@@ -401,7 +404,7 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     auto ray_of = [&](uint32_t m) -> uint32_t { return div_s(m >> 5); };       // sample index -> ray
 
 #if FU_GATHER_WARPS == 16
-    if (warp >= 8) {
+    if (warp >= 8 && warp < 8 + FU_GATHER_WARPS) {
         // =========================== GATHER group, 16 warps x 8 rows ===========================
         // Twice the warps over the same rows: the gather chain of a tile is split over 16 instruction streams (4 per scheduler
         // next to 2 MLP warps) instead of 8.  Coordinates: every fourth iteration for four tiles at once (lanes 8g .. 8g+7 take
@@ -570,6 +573,54 @@ FU_UNROLL(FU_APP_UNROLL)
             if (lane == 0) mbar_arrive(v_full0 + 8 * b);
         }
 #endif
+#if FU_MMA_WARP
+    } else if (warp == 8 + FU_GATHER_WARPS) {
+        // =========================== MMA warp ===========================
+        // One elected thread issues every tcgen05.mma of the CTA in the order the tensor pipe should run them: layer 1 and 2 of
+        // tile t, layer 0 of tile t+1, layer 3 of tile t.  The MLP warps announce each finished operand (X, H1, H2 -- the same
+        // buffer, three phases per tile) on the `a_ready` mbarrier and run on; they meet the results on d1 / d2 / d3 / feat_full.
+        // (With the issue inside MLP warp 0 that warp executed ~450 instructions per tile more than the other seven, and every
+        // group barrier waited for it: 27 % of the group's stall samples.)
+        if (lane == 0) {
+            const uint32_t a_s = smem_u32(as), w1_s = smem_u32(w1s), w2_s = smem_u32(w2s), bb_s = smem_u32(bbs), v_s = smem_u32(vs);
+            const uint32_t w3_s = smem_u32(smem + L::L3);
+            auto issue_layer0 = [&](uint32_t i) {                   // thread 0: feat2 = V . [B_yin | B_yang]^T for CTA-local tile i
+                const uint32_t bb = FU_VBUFS == 2 ? (i & 1) : 0;
+                ok &= mbar_wait(v_full0 + 8 * bb, (FU_VBUFS == 2 ? (i >> 1) : i) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < FU_VK / 16; ++ks)
+                    tc_mma(tmem + 256, tc_desc(v_s + bb * FU_VBYTES + ks * 2 * FU_VCHUNK, FU_VCHUNK),
+                           tc_desc(bb_s + ks * 2 * FU_BB_CHUNK, FU_BB_CHUNK), FU_IDESC_128x64, ks > 0);
+                tc_commit(v_empty0 + 8 * bb);
+                tc_commit(feat_full);
+            };
+            uint32_t ph = 0;
+            if (n_local > 0) issue_layer0(0);
+            for (uint32_t it = 0; it < n_local; ++it) {
+                ok &= mbar_wait(a_ready, ph++ & 1);              // X of tile it
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < TC_K1 / 16; ++ks)
+                    tc_mma(tmem, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w1_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
+                tc_commit(d1_full);
+                ok &= mbar_wait(a_ready, ph++ & 1);              // H1
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < EGN_HID / 16; ++ks)
+                    tc_mma(tmem + 128, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w2_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
+                tc_commit(d2_full);
+                if (it + 1 < n_local) issue_layer0(it + 1);
+                ok &= mbar_wait(a_ready, ph++ & 1);              // H2
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < EGN_HID / 16; ++ks)
+                    tc_mma(tmem + 384, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc_sbo(w3_s + ks * 2 * FU_W3_CHUNK, FU_W3_CHUNK, 0), FU_IDESC_128x16, ks > 0);
+                tc_commit(d3_full);
+            }
+        }
+        __syncwarp();
+#endif
     } else {
         // =========================== MLP group ===========================
         const int row = tid & 127, half = tid >> 7;
@@ -579,6 +630,7 @@ FU_UNROLL(FU_APP_UNROLL)
         // Software pipeline over tiles.  The tensor pipe works on layer 0 of tile t+1 while this group waits for layer 2 of
         // tile t, and on layer 1 of tile t while the group runs layer 3 of tile t-1 out of TMEM: only the layer-2 wait is
         // exposed.  TMEM: D1 = columns 0..127, D2 = 128..255, feat2 = 256..319.
+#if !FU_MMA_WARP
         auto issue_layer0 = [&](uint32_t i) {                   // thread 0: feat2 = V . [B_yin | B_yang]^T for CTA-local tile i
             const uint32_t bb = FU_VBUFS == 2 ? (i & 1) : 0;
             ok &= mbar_wait(v_full0 + 8 * bb, (FU_VBUFS == 2 ? (i >> 1) : i) & 1);
@@ -590,6 +642,7 @@ FU_UNROLL(FU_APP_UNROLL)
             tc_commit(v_empty0 + 8 * bb);
             tc_commit(feat_full);
         };
+#endif
         // layer 3 + sigmoid of the tile whose D2 sits in TMEM (its layer-2 completion has been waited for); COMP: then the
         // compositing of the tile's 128 samples (they belong to one ray), carried over the tiles of the ray
         float carryT = 1.f, sum_w = 0.f, sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_z = 0.f;     // sums live in thread 0
@@ -755,7 +808,9 @@ FU_UNROLL(FU_APP_UNROLL)
                 }
             }
         };
+#if !FU_MMA_WARP
         if (tid == 0 && n_local > 0) issue_layer0(0);
+#endif
         uint32_t it = 0;
         uint32_t gm_prev = M32;
         for (; it < n_local; ++it) {
@@ -810,6 +865,10 @@ FU_UNROLL(FU_APP_UNROLL)
             }
             fence_async_smem();
             tc_fence_before();
+#if FU_MMA_WARP
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);                     // X ready: the MMA warp issues layer 1
+#else
             named_bar_sync(1, FU_GROUP);
             // ---- B. layer 1 (runs on the tensor pipe during layer 3 of the previous tile) ----
             if (tid == 0) {
@@ -819,6 +878,7 @@ FU_UNROLL(FU_APP_UNROLL)
                     tc_mma(tmem, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc(w1_s + ks * 2 * TC_CHUNK), FU_IDESC_128x128, ks > 0);
                 tc_commit(d1_full);
             }
+#endif
             if (it > 0) layer3(gm_prev);
             ok &= mbar_wait(d1_full, it & 1);
             tc_fence_after();
@@ -836,6 +896,10 @@ FU_UNROLL(FU_APP_UNROLL)
             }
             fence_async_smem();
             tc_fence_before();
+#if FU_MMA_WARP
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);                     // H1 ready: layer 2, then layer 0 of the next tile
+#else
             named_bar_sync(1, FU_GROUP);
             // ---- D. layer 2, then layer 0 of the next tile ----
             if (tid == 0) {
@@ -846,6 +910,7 @@ FU_UNROLL(FU_APP_UNROLL)
                 tc_commit(d2_full);
                 if (it + 1 < n_local) issue_layer0(it + 1);
             }
+#endif
             ok &= mbar_wait(d2_full, it & 1);
             tc_fence_after();
 #if FU_L3_MMA
@@ -869,6 +934,10 @@ FU_UNROLL(FU_APP_UNROLL)
                 }
                 fence_async_smem();
                 tc_fence_before();
+#if FU_MMA_WARP
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);                 // H2 ready: layer 3
+#else
                 named_bar_sync(1, FU_GROUP);
                 if (tid == 0) {
                     tc_fence_after();
@@ -878,6 +947,7 @@ FU_UNROLL(FU_APP_UNROLL)
                         tc_mma(tmem + 384, tc_desc(a_s + ks * 2 * TC_CHUNK), tc_desc_sbo(w3_s + ks * 2 * FU_W3_CHUNK, FU_W3_CHUNK, 0), FU_IDESC_128x16, ks > 0);
                     tc_commit(d3_full);
                 }
+#endif
             }
 #endif
             gm_prev = gm;
