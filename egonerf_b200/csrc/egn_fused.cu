@@ -42,6 +42,9 @@
 #ifndef FU_MMA_WARP
 #define FU_MMA_WARP (FU_GATHER_WARPS == 16 && FU_L3_MMA)     // a 25th warp issues every tcgen05.mma (800 threads x 80 registers)
 #endif
+#ifndef FU_ALPHA_IN_GATHER
+#define FU_ALPHA_IN_GATHER 0                 // 1: the density lanes of the gather group turn the sigma feature into alpha (needs FU_MMA_WARP); measured 4.88 vs 4.82 ms: off
+#endif
 #define FU_THREADS (256 + 32 * FU_GATHER_WARPS + 32 * FU_MMA_WARP)
 #define FU_GROUP 256
 #define FU_VK (3 * EGN_CA)                   // 144
@@ -102,11 +105,11 @@ struct FuLayout {
     static constexpr int V = A + (TC_K1 / 8) * TC_CHUNK;              // + 40 960 ; two buffers
     static constexpr int REC = V + FU_VBUFS * FU_VBYTES;                     // address records: 128 samples x 144 B
     static constexpr int YANG = REC + (FU_GATHER_WARPS == 16 ? TC_TM * (FU_REC_WORDS / 4) : 8 * (16 * (FU_REC_WORDS / 4) + 1)) * 16;   // records (8-warp cut: + 1 swizzle slot per warp); then 4 x 128 bytes
-    static constexpr int KNOTS = YANG + 4 * TC_TM;
+    static constexpr int KNOTS = YANG + 4 * TC_TM * (FU_ALPHA_IN_GATHER ? 4 : 1);   // FU_ALPHA_IN_GATHER: 4 x 128 floats {alpha | hemisphere in the sign bit}
     static constexpr int MBAR = KNOTS + ((EGN_FUSED_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
     static constexpr int TMEM = MBAR + 10 * 8;
     static constexpr int PART = TMEM + 16;                            // layer-3 partial sums of the upper column half: 128 x float4 (FU_L3_MMA: alpha only)
-    static constexpr int RED = PART + TC_TM * (FU_L3_MMA ? 4 : 16);   // fused compositing: 4 warp products + 4 x 5 warp sums
+    static constexpr int RED = PART + (FU_ALPHA_IN_GATHER ? 0 : TC_TM * (FU_L3_MMA ? 4 : 16));   // fused compositing: 4 warp products + 4 x 5 warp sums
     static constexpr int TOTAL = RED + 4 * 8 * 4;
 };
 static_assert(FuLayout::TOTAL <= 227 * 1024, "fused kernel exceeds the shared memory of one SM");
@@ -353,9 +356,15 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
     unsigned char* bbs = smem + L::BB;
     unsigned char* as = smem + L::A;
     unsigned char* vs = smem + L::V;
+#if FU_ALPHA_IN_GATHER
+    float* s_ay = reinterpret_cast<float*>(smem + L::YANG);      // ring of 4 tiles x 128 {alpha, sign bit = hemisphere}
+#else
     unsigned char* s_yang = smem + L::YANG;
+#endif
     float* s_knots = reinterpret_cast<float*>(smem + L::KNOTS);
+#if !FU_ALPHA_IN_GATHER
     float* part = reinterpret_cast<float*>(smem + L::PART);
+#endif
 #if !FU_L3_CONST && !FU_L3_MMA
     float4* l3s = reinterpret_cast<float4*>(smem + L::L3);
 #endif
@@ -442,24 +451,56 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 FuRecord R;
                 fused_address_record(k, cc, R);
                 fused_store_record(R, recs + lane * (FU_REC_WORDS / 4));
+#if !FU_ALPHA_IN_GATHER
                 s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
+#endif
             }
             __syncwarp();
             // ---- density (fp32): 8 samples x 4 lanes, three factor pairs ----
+#if FU_ALPHA_IN_GATHER
+            float ay = 0.f;                                          // {alpha, sign bit = hemisphere} of row lane >> 2
+#endif
             {
                 const unsigned sub = lane & 3;
                 const uint4* rec = recs + (lane >> 2) * (FU_REC_WORDS / 4);
                 float4 t[FU_DEPTH][6];
 #pragma unroll
                 for (int i = 0; i < FU_DEPTH; ++i) fused_density_issue(dens, rec, i, sub, t[i], pol);
+#if FU_ALPHA_IN_GATHER
+                // the row's depth step, requested behind the taps (tensorBase.py:22-27 with the distances of EgoNeRF.py:541-542,553:
+                // z[j+1] - z[j], the last one of a ray repeated)
+                const uint32_t m = tile * TC_TM + row0 + (lane >> 2);
+                const int yang_row = __shfl_sync(FULL, cc.yang, lane >> 2);
+                float dist = 0.f;
+                uint32_t ray_a = 0, j_a = 0;
+                if (COMP && m < M32) {
+                    ray_a = ray_of(m);
+                    j_a = m - ray_a * S32;
+                    const float z0 = zs[m];
+                    dist = (j_a + 1 < S32 ? zs[m + 1] - z0 : z0 - zs[m - 1]) * k.distance_scale;
+                }
+#endif
                 float f = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     f += fused_density_unit(rec, i, t[i % FU_DEPTH]);
                     if (i + FU_DEPTH < 3) fused_density_issue(dens, rec, i + FU_DEPTH, sub, t[i % FU_DEPTH], pol);
                 }
+#if FU_ALPHA_IN_GATHER
+                float a = 0.f;
+                if (sub == 0 && m < M32) {
+                    if constexpr (COMP) {
+                        a = 1.f - expf(-egn_density_act(f, k.density_shift, k.fea2dense) * dist);
+                        fu_st_stream(out.alpha + (size_t)ray_a * (S32 + (k.env_h > 0 ? 1 : 0)) + j_a, a);
+                    } else {
+                        fu_st_stream(fsig + m, f);
+                    }
+                }
+                ay = __uint_as_float(__float_as_uint(a) | ((unsigned)yang_row << 31));
+#else
                 const uint32_t m = tile * TC_TM + row0 + (lane >> 2);
                 if (sub == 0 && m < M32) fu_st_stream(fsig + m, f);
+#endif
             }
             // ---- appearance (fp16) into the V operand: 2 passes x 4 samples x 3 factor pairs = 6 units ----
             {
@@ -472,6 +513,10 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
 #pragma unroll
                 for (int un = 0; un < FU_DEPTH; ++un) fused_app_issue(app, un / 3 ? recB : recA, un % 3, q, t[un], pol);
                 ok &= mbar_wait(v_empty0 + 8 * b, (u & 1) ^ 1);      // layer-0 MMAs of the tile that used this buffer are done
+#if FU_ALPHA_IN_GATHER
+                // ring slot it & 3: layer 0 of tile it - 2 is complete, so every MLP warp has finished the epilogue of tile it - 4
+                if ((lane & 3) == 0) s_ay[(it & 3) * TC_TM + row0 + (lane >> 2)] = ay;
+#endif
 #pragma unroll
                 for (int un = 0; un < 6; ++un) {
                     const uint4 o = fused_app_unit(un / 3 ? recB : recA, un % 3, t[un % FU_DEPTH]);
@@ -648,7 +693,7 @@ FU_UNROLL(FU_APP_UNROLL)
         float carryT = 1.f, sum_w = 0.f, sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_z = 0.f;     // sums live in thread 0
         float* red = reinterpret_cast<float*>(smem + L::RED);
         const int acols = k.S + (k.env_h > 0 ? 1 : 0);
-        auto layer3 = [&](uint32_t gm3) {
+        auto layer3 = [&](uint32_t gm3, uint32_t it3) {
             // COMP: the upper-half threads (idle during the scan below) turn the row's sigma feature -- written by the gather
             // group, read back through L2 -- into alpha (tensorBase.py:22-27 with the distances of EgoNeRF.py:541-542,553:
             // z[j+1] - z[j], the last one repeated).  The loads are requested first and land behind the dot products.
@@ -658,11 +703,15 @@ FU_UNROLL(FU_APP_UNROLL)
             if constexpr (COMP) {
                 ray3 = ray_of(gm3);
                 j3 = (int)(gm3 - ray3 * S32);
+#if FU_ALPHA_IN_GATHER
+                if (half == 0) zrow = zs[gm3];
+#else
                 zrow = zs[gm3];
                 if (half == 1) {
                     fs = __ldcg(fsig + gm3);
                     znext = (j3 + 1 < k.S) ? zs[gm3 + 1] : zs[gm3 - 1];
                 }
+#endif
             }
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #if FU_L3_MMA
@@ -725,6 +774,11 @@ FU_UNROLL(FU_APP_UNROLL)
 #endif
 #endif
             tc_fence_before();
+#if FU_ALPHA_IN_GATHER
+            (void)fs; (void)znext;
+            if (half == 0 && gm3 < M32) {
+                const float4 q = make_float4(0.f, 0.f, 0.f, fabsf(s_ay[(it3 & 3) * TC_TM + row]));
+#else
             if (half == 1) {
                 float a = 0.f;
                 if constexpr (COMP) {
@@ -744,6 +798,7 @@ FU_UNROLL(FU_APP_UNROLL)
                 const float4 q = make_float4(0.f, 0.f, 0.f, part[row]);
 #else
                 const float4 q = *reinterpret_cast<const float4*>(part + row * 4);
+#endif
 #endif
                 const float alpha = q.w;
                 const float c0 = egn_sigmoid(p0 + q.x + bias3[0]), c1 = egn_sigmoid(p1 + q.y + bias3[1]), c2 = egn_sigmoid(p2 + q.z + bias3[2]);
@@ -825,7 +880,11 @@ FU_UNROLL(FU_APP_UNROLL)
             tc_fence_after();
             // ---- A. this thread's 16 elements: features of its hemisphere (from TMEM), then view direction / 1 / padding ----
             {
+#if FU_ALPHA_IN_GATHER
+                const int yang = (int)(__float_as_uint(s_ay[(it & 3) * TC_TM + row]) >> 31);
+#else
                 const int yang = s_yang[(it & 3) * TC_TM + row];
+#endif
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tmem_lane + 256 + 16 * half, r0);            // yin block
                 tmem_ld16(tmem_lane + 256 + 32 + 16 * half, r1);       // yang block
@@ -879,7 +938,7 @@ FU_UNROLL(FU_APP_UNROLL)
                 tc_commit(d1_full);
             }
 #endif
-            if (it > 0) layer3(gm_prev);
+            if (it > 0) layer3(gm_prev, it - 1);
             ok &= mbar_wait(d1_full, it & 1);
             tc_fence_after();
             // ---- C. H1 = relu(D1) -> operand of layer 2 ----
@@ -955,7 +1014,7 @@ FU_UNROLL(FU_APP_UNROLL)
 #if FU_L3_MMA
         if (it > 0) { ok &= mbar_wait(d3_full, (it - 1) & 1); tc_fence_after(); }
 #endif
-        if (it > 0) layer3(gm_prev);                            // layer 3 of the last tile
+        if (it > 0) layer3(gm_prev, it - 1);                    // layer 3 of the last tile
     }
     if (!ok) __trap();                                          // a lost mbarrier arrive: fail loudly, never hang
     tc_fence_before();
