@@ -80,6 +80,9 @@
 // of the traffic on the L1 data pipe the kernel is bound by (profiles/r02_fused.md).  The symbol is refreshed by a device-to-
 // device copy from the operand image before every launch, on the launch's stream; launches on DIFFERENT streams are ordered
 // against each other by an event per device (a later copy waits for the earlier kernel), under a host mutex.
+#ifndef FU_RELU_CVT
+#define FU_RELU_CVT 1                        // relu of H1 / H2 folded into the fp16 conversion (cvt.rn.relu.f16x2.f32), b2 added with packed FADD2
+#endif
 #ifndef FU_FFMA2
 #define FU_FFMA2 0                           // layer 3 with packed fp32 FFMA2 / FADD2 (two hidden units per instruction): 5.40 vs 5.37 ms with 16 gather warps
 #endif
@@ -948,10 +951,17 @@ FU_UNROLL(FU_APP_UNROLL)
                 uint32_t r[32];
                 tmem_ld32(tmem_lane + col, r);
                 float v[32];
+#if FU_RELU_CVT
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_chunk_h_relu(as, (col >> 3) + c, row, v + 8 * c);
+#else
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]), 0.f);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_chunk_h(as, (col >> 3) + c, row, v + 8 * c);
+#endif
             }
             fence_async_smem();
             tc_fence_before();
@@ -982,6 +992,17 @@ FU_UNROLL(FU_APP_UNROLL)
                     uint32_t r[32];
                     tmem_ld32(tmem_lane + 128 + col, r);
                     float v[32];
+#if FU_RELU_CVT
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 bq = b2s[(col >> 2) + g];
+                        const float2 s0 = fu_fadd2(make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])), make_float2(bq.x, bq.y));
+                        const float2 s1 = fu_fadd2(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), make_float2(bq.z, bq.w));
+                        v[4 * g] = s0.x; v[4 * g + 1] = s0.y; v[4 * g + 2] = s1.x; v[4 * g + 3] = s1.y;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) store_chunk_h_relu(as, (col >> 3) + c, row, v + 8 * c);
+#else
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const float4 bq = b2s[(col >> 2) + g];
@@ -990,6 +1011,7 @@ FU_UNROLL(FU_APP_UNROLL)
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) store_chunk_h(as, (col >> 3) + c, row, v + 8 * c);
+#endif
                 }
                 fence_async_smem();
                 tc_fence_before();

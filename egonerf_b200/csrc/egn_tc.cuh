@@ -136,6 +136,17 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+// the same with max(x, 0) folded into the conversion (F2FP.RELU): relu(round(x)) == round(relu(x))
+__device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void store_chunk_h_relu(unsigned char* base, int chunk, int row, const float* v) {
+    uint4 h;
+    h.x = pack_h2_relu(v[0], v[1]); h.y = pack_h2_relu(v[2], v[3]); h.z = pack_h2_relu(v[4], v[5]); h.w = pack_h2_relu(v[6], v[7]);
+    *reinterpret_cast<uint4*>(base + chunk * TC_CHUNK + row * 16) = h;
+}
 __device__ __forceinline__ void store_chunk_h(unsigned char* base, int chunk, int row, const float* v) {
     uint4 h;
     h.x = pack_h2(v[0], v[1]); h.y = pack_h2(v[2], v[3]); h.z = pack_h2(v[4], v[5]); h.w = pack_h2(v[6], v[7]);
