@@ -80,6 +80,12 @@
 // of the traffic on the L1 data pipe the kernel is bound by (profiles/r02_fused.md).  The symbol is refreshed by a device-to-
 // device copy from the operand image before every launch, on the launch's stream; launches on DIFFERENT streams are ordered
 // against each other by an event per device (a later copy waits for the earlier kernel), under a host mutex.
+#ifndef FU_FAST_SIGMOID
+#define FU_FAST_SIGMOID 1                    // sample colour with ex2.approx / rcp.approx instead of expf and an IEEE division
+#endif
+#ifndef FU_PREFETCH
+#define FU_PREFETCH 1                        // epilogue inputs of the previous tile requested at the top of the iteration
+#endif
 #ifndef FU_RELU_CVT
 #define FU_RELU_CVT 1                        // relu of H1 / H2 folded into the fp16 conversion (cvt.rn.relu.f16x2.f32), b2 added with packed FADD2
 #endif
@@ -696,25 +702,34 @@ FU_UNROLL(FU_APP_UNROLL)
         float carryT = 1.f, sum_w = 0.f, sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_z = 0.f;     // sums live in thread 0
         float* red = reinterpret_cast<float*>(smem + L::RED);
         const int acols = k.S + (k.env_h > 0 ? 1 : 0);
-        auto layer3 = [&](uint32_t gm3, uint32_t it3) {
-            // COMP: the upper-half threads (idle during the scan below) turn the row's sigma feature -- written by the gather
-            // group, read back through L2 -- into alpha (tensorBase.py:22-27 with the distances of EgoNeRF.py:541-542,553:
-            // z[j+1] - z[j], the last one repeated).  The loads are requested first and land behind the dot products.
-            float fs = 0.f, zrow = 0.f, znext = 0.f;
+        // COMP: the upper-half threads turn the row's sigma feature -- written by the gather group, read back through L2 -- into
+        // alpha (tensorBase.py:22-27 with the distances of EgoNeRF.py:541-542,553: z[j+1] - z[j], the last one repeated).  Its
+        // inputs {sigma feature, z, next z} are requested a whole operand phase before they are used (FU_PREFETCH).
+        auto prefetch = [&](uint32_t gm3) -> float3 {
+            float3 pre = make_float3(0.f, 0.f, 0.f);
+            if constexpr (COMP) {
+                if (gm3 < M32) {
+#if FU_ALPHA_IN_GATHER
+                    if (half == 0) pre.y = zs[gm3];
+#else
+                    pre.y = zs[gm3];
+                    if (half == 1) {
+                        const uint32_t ray = ray_of(gm3);
+                        pre.x = __ldcg(fsig + gm3);
+                        pre.z = (gm3 - ray * S32 + 1 < S32) ? zs[gm3 + 1] : zs[gm3 - 1];
+                    }
+#endif
+                }
+            }
+            return pre;
+        };
+        auto layer3 = [&](uint32_t gm3, uint32_t it3, float3 pre) {
+            const float fs = pre.x, zrow = pre.y, znext = pre.z;
             uint32_t ray3 = 0;
             int j3 = 0;
             if constexpr (COMP) {
                 ray3 = ray_of(gm3);
                 j3 = (int)(gm3 - ray3 * S32);
-#if FU_ALPHA_IN_GATHER
-                if (half == 0) zrow = zs[gm3];
-#else
-                zrow = zs[gm3];
-                if (half == 1) {
-                    fs = __ldcg(fsig + gm3);
-                    znext = (j3 + 1 < k.S) ? zs[gm3 + 1] : zs[gm3 - 1];
-                }
-#endif
             }
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #if FU_L3_MMA
@@ -804,7 +819,12 @@ FU_UNROLL(FU_APP_UNROLL)
 #endif
 #endif
                 const float alpha = q.w;
+#if FU_FAST_SIGMOID
+                const float c0 = __fdividef(1.f, 1.f + __expf(-(p0 + q.x + bias3[0]))), c1 = __fdividef(1.f, 1.f + __expf(-(p1 + q.y + bias3[1]))),
+                            c2 = __fdividef(1.f, 1.f + __expf(-(p2 + q.z + bias3[2])));
+#else
                 const float c0 = egn_sigmoid(p0 + q.x + bias3[0]), c1 = egn_sigmoid(p1 + q.y + bias3[1]), c2 = egn_sigmoid(p2 + q.z + bias3[2]);
+#endif
                 if constexpr (!COMP) {
                     float* o3 = rgbs + (size_t)gm3 * 3;
                     o3[0] = c0; o3[1] = c1; o3[2] = c2;
@@ -875,6 +895,8 @@ FU_UNROLL(FU_APP_UNROLL)
             const uint32_t tile = tile_of(it);
             const uint32_t gm = tile * TC_TM + row;
             const bool live = gm < M32;
+            float3 pre = make_float3(0.f, 0.f, 0.f);
+            if (FU_PREFETCH && it > 0) pre = prefetch(gm_prev);
             // ---- layer 0 of this tile was issued one iteration ago ----
             ok &= mbar_wait<FU_MLP_BACKOFF>(feat_full, it & 1);
 #if FU_L3_MMA
@@ -941,7 +963,7 @@ FU_UNROLL(FU_APP_UNROLL)
                 tc_commit(d1_full);
             }
 #endif
-            if (it > 0) layer3(gm_prev, it - 1);
+            if (it > 0) layer3(gm_prev, it - 1, FU_PREFETCH ? pre : prefetch(gm_prev));
             ok &= mbar_wait(d1_full, it & 1);
             tc_fence_after();
             // ---- C. H1 = relu(D1) -> operand of layer 2 ----
@@ -1036,7 +1058,7 @@ FU_UNROLL(FU_APP_UNROLL)
 #if FU_L3_MMA
         if (it > 0) { ok &= mbar_wait(d3_full, (it - 1) & 1); tc_fence_after(); }
 #endif
-        if (it > 0) layer3(gm_prev, it - 1);                    // layer 3 of the last tile
+        if (it > 0) layer3(gm_prev, it - 1, prefetch(gm_prev));   // layer 3 of the last tile
     }
     if (!ok) __trap();                                          // a lost mbarrier arrive: fail loudly, never hang
     tc_fence_before();
