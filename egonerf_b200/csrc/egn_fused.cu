@@ -1,8 +1,8 @@
 // Fused fine pass (throughput mode, EGN_MLP_TC_F16): Yin-Yang coordinates -> 18-tap factor gather -> VM products
 // -> basis contraction -> positional encoding -> 3-layer MLP -> sample colour, in ONE persistent warp-specialised kernel.
 // Replaces egn_gather_kernel + egn_mlp_*_kernel for one ray chunk (EgoNeRF.py:544-556: from_cartesian / normalize_coord,
-// compute_densityfeature, compute_appfeature, renderModule).  One CTA per SM, 768 threads at 80 registers (FU_GATHER_WARPS = 16;
-// the round-1 cut, 8 gather warps x 16 rows at 128 registers, is still selectable):
+// compute_densityfeature, compute_appfeature, renderModule).  One CTA per SM, 800 threads at 72 registers (FU_GATHER_WARPS = 16;
+// the round-1 cut, 8 gather warps x 16 rows at 128 registers with the MMA issue inside MLP warp 0, is still selectable):
 //
 //   warps 8..23  GATHER group   per 128-sample tile, each warp owns 8 rows and runs three phases on them:
 //                  1. ADDRESS   one lane per sample: coordinates (every fourth tile for four tiles at once, all 32 lanes busy),
@@ -16,9 +16,12 @@
 //                               the 144 products P*L go straight into shared memory as an fp16 row of the tcgen05 A operand V.
 //                               V is double buffered: tile i+1 is gathered while tile i runs through the MLP.
 //                 Two factor pairs of taps (12 loads per lane) are in flight per warp, 192 per SM.
-//   warps 0..7   MLP group      feat2 = V [B_yin | B_yang]^T (tcgen05, N = 64; the epilogue picks the sample's
-//                               hemisphere) -> PE -> X -> D1 -> relu -> H1 -> D2 -> relu . W3 -> sigmoid   (as egn_mlp_tc.cu)
-//   thread 0                    issues every tcgen05.mma; completions come back through tcgen05.commit -> mbarrier
+//   warps 0..7   MLP group      feat2 = V [B_yin | B_yang]^T (N = 64; the epilogue picks the sample's hemisphere) -> PE -> X -> D1 ->
+//                               relu (folded into the fp16 conversion) -> H1 -> D2 -> + b2, relu -> H2 -> D3 = H2 W3^T (N = 16) ->
+//                               sigmoid [-> compositing].  X, H1 and H2 share one operand buffer; the warps announce each finished
+//                               operand on an mbarrier and run on (no group barrier in front of an MMA)
+//   warp 24      MMA warp       one elected thread issues every tcgen05.mma in the order layer 1, layer 2, layer 0 of the next
+//                               tile, layer 3; completions come back through tcgen05.commit -> mbarrier
 //
 // All MMA operands are FP16 (fp32 accumulate in TMEM): against bf16 the rounding error of every operand is 8x smaller, which
 // brings rgb to ~1e-5 of the exact render (scripts/error_budget.py) at the same bytes and tensor throughput.
