@@ -48,9 +48,10 @@ def test_tc_split_matches_fp32_and_reference(name):
     assert e <= 1e-4 or "white" in name
 
 
-# measured on B200 (profiles/r02_parity.md): throughput mode vs the exact fp32 kernels rgb 0.9-1.0e-5, alpha 3.6-5.4e-7,
-# 107-111 dB between the renders; vs the reference fixtures 1.0-1.2e-5 (reference depths).  Gates = ~2x measured.
-TP_RGB_VS_FP32, TP_ALPHA_VS_FP32, TP_PSNR_BETWEEN = 2.5e-5, 2e-6, 100.0
+# measured on B200 (profiles/r02_parity.md, end-of-round build with layer 3 on the tensor core): throughput mode vs the exact
+# fp32 kernels rgb 1.0-1.8e-5, alpha 3.6-5.4e-7, 103-108 dB between the renders; vs the reference fixtures 0.95-1.8e-5 (3.0e-5 on
+# the uniform-march train case; reference depths).  Gates = ~2x measured.
+TP_RGB_VS_FP32, TP_ALPHA_VS_FP32, TP_PSNR_BETWEEN = 3.5e-5, 2e-6, 98.0
 
 
 @pytest.mark.parametrize("name", MLP_FEA_CASES)
