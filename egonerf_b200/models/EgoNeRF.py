@@ -340,24 +340,40 @@ class EgoNeRF(torch.nn.Module):
             self.envmap = EnvironmentMap(h=ckpt['envmap_res_H'], init_strategy='zero', device=self.device)
             self.envmap.load_envmap(emission=ckpt['envmap.emission'], device=self.device)
         self.load_state_dict(ckpt['state_dict'])
+        self._fp_cache = self._pl_cache = self._ps_cache = None
         self.update_coarse_sigma_grid()
         return ckpt['global_step']
 
     # ---- render tables ------------------------------------------------------------------------------
     def _factor_params(self):
+        """The 24 factor tensors [h][kind][i].  Walking eight ParameterLists costs ~90 us per call and a forward needs the list
+        three times, so it is cached; the cache is dropped wherever Parameters are replaced by new objects
+        (`upsample_volume_grid`, `load`) and re-validated against the first and the last entry on every use."""
+        c = getattr(self, "_fp_cache", None)
+        if c is not None and c[0] is self.density_plane_yin[0] and c[-1] is self.app_line_yang[2]:
+            return c
         out = []
         for h in ('yin', 'yang'):
             for kind in ('density_plane', 'density_line', 'app_plane', 'app_line'):
                 out += list(getattr(self, f'{kind}_{h}'))
-        return out                                   # 24 tensors: [h][kind][i]
+        self._fp_cache = out
+        self._pl_cache = None
+        return out
 
     def _param_list(self):
-        ps = self._factor_params() + [self.basis_mat_yin.weight, self.basis_mat_yang.weight]
+        fp = self._factor_params()
+        c = getattr(self, "_pl_cache", None)
+        n_expected = 26 + (6 if isinstance(self.renderModule, torch.nn.Module) else 0) + (self.envmap is not None)
+        if c is not None and len(c) == n_expected and (self.envmap is None or c[-1] is self.envmap.emission) \
+                and c[24] is self.basis_mat_yin.weight:
+            return c
+        ps = list(fp) + [self.basis_mat_yin.weight, self.basis_mat_yang.weight]
         if isinstance(self.renderModule, torch.nn.Module):
             ps += [self.renderModule.mlp[0].weight, self.renderModule.mlp[0].bias, self.renderModule.mlp[2].weight,
                    self.renderModule.mlp[2].bias, self.renderModule.mlp[4].weight, self.renderModule.mlp[4].bias]
         if self.envmap is not None:
             ps += [self.envmap.emission]
+        self._pl_cache = ps
         return ps
 
     def _fill_struct(self, S, tensors):
@@ -378,7 +394,14 @@ class EgoNeRF(torch.nn.Module):
         return S
 
     def _params_struct(self):
-        return self._fill_struct(_lib.EgnParams(), [p.detach() for p in self._param_list()])
+        """EgnParams with the raw pointers of the current parameters; rebuilt only when a pointer changed."""
+        plist = self._param_list()
+        key = tuple(map(torch.Tensor.data_ptr, plist))
+        c = getattr(self, "_ps_cache", None)
+        if c is None or c[0] != key:
+            c = (key, self._fill_struct(_lib.EgnParams(), [p.detach() for p in plist]))
+            self._ps_cache = c
+        return c[1]
 
     def _grads_struct(self, grads):
         return self._fill_struct(_lib.EgnGrads(), grads)
@@ -449,6 +472,28 @@ class EgoNeRF(torch.nn.Module):
         return self._cfg_static
 
     def _config(self, opts):
+        """EgnConfig for `opts`, cached: filling ~45 ctypes fields costs ~50 us per forward otherwise.  The key holds everything
+        the struct is built from that can change after construction."""
+        co = self.coordinates
+        t16, th = self._tables_bf16, getattr(self, "_tables_h", None)
+        key = (None if opts is None else (opts["n_coarse"], opts["n_fine"], opts["use_coarse_sample"], opts["resampling"],
+                                          opts.get("exp_sampling", True)),
+               self.mlp_mode, self.table_dtype, bool(self.tc_backward), None if t16 is None else t16.data_ptr(),
+               None if th is None else th.data_ptr(), None if self.envmap is None else self.envmap.emission.shape[2],
+               co.N_r, co.r0, co.interval_th, self.shadingMode, self.app_dim, self.view_pe, self.fea_pe, self.featureC,
+               self.fea2denseAct, self.density_shift, self.distance_scale, self.near_far[0], self.near_far[1],
+               self._cfg_static is None)
+        cache = self.__dict__.setdefault("_cfg_cache", {})
+        cfg = cache.get(key)
+        if cfg is None:
+            if len(cache) > 64:
+                cache.clear()
+            cfg = self._build_config(opts)
+            key = key[:-1] + (self._cfg_static is None,)          # _build_config fills the static part
+            cache[key] = cfg
+        return cfg
+
+    def _build_config(self, opts):
         co = self.coordinates
         if self._sched.get('ladder') != (co.N_r, co.r0):          # set_resolution changes N_r and resets r0
             self._sched = {'ladder': (co.N_r, co.r0)}
@@ -607,6 +652,8 @@ class EgoNeRF(torch.nn.Module):
         self.update_stepSize(res_target)
         # everything derived from the old resolution: render tables, ladders, cached scalars, table-space optimiser state
         self._tables = self._tables_key = self._tables_bf16 = self._tables_h = self._cfg_static = None
+        self._fp_cache = self._pl_cache = self._ps_cache = None
+        self._cfg_cache = {}
         self._sched = {}
         self._table_opt = None
         self._bucket = None
