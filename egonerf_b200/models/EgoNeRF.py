@@ -706,12 +706,13 @@ class EgoNeRF(torch.nn.Module):
 
     def launches_per_forward(self, S=256, keep_for_backward=False):
         """Kernels of libegn_b200 launched by one `forward`: sampler, gather, [MLP], composite -- or, in the throughput mode,
-        sampler + fused fine pass (+ composite only when the backward pass needs the per-sample state or S % 128 != 0)."""
+        sampler + operand-image kernel + fused fine pass (+ composite only when the backward pass needs the per-sample state
+        or S % 128 != 0)."""
         if not isinstance(self.renderModule, torch.nn.Module):
             return 3
         fused = self._fused_mode() and self.shadingMode == 'MLP_Fea' and self.view_pe == 2 and self.fea_pe == 2
-        if fused:
-            return 2 if (not keep_for_backward and S % 128 == 0) else 3
+        if fused:        # sampler + operand-image kernel (6 us) + fused fine pass (+ composite)
+            return 3 if (not keep_for_backward and S % 128 == 0) else 4
         return 4
 
     def launches_per_train_step(self, n_rays):
