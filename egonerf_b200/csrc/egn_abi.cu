@@ -179,7 +179,7 @@ extern "C" int32_t egn_regularize_tables(const EgnConfig* c, const float* tables
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
 #define EGN_BWD_SUB_RAYS 4096
-struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, d_rgbs, d_fsig, d_feat, gmax, h1, h2, dz1, dz2, eval_total, total; };
+struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, coord, d_rgbs, d_fsig, d_feat, gmax, h1, h2, dz1, dz2, eval_total, total; };
 // the fused fine pass keeps the r ladder in shared memory (EGN_FUSED_MAX_KNOTS entries); larger grids take the unfused kernels
 static bool is_fused(const EgnConfig* c) {
     return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_F16 && c->grid[0] + 3 <= EGN_FUSED_MAX_KNOTS;
@@ -200,6 +200,7 @@ static WsPlan plan_ws(const EgnConfig* c, long long n) {
     const long long eval_fused = off;
     w.feat = take(M * EGN_FEAT_STRIDE);
     w.eval_total = is_fused(c) ? eval_fused : off;
+    w.coord = take(is_fused(c) && tc_backward(c) ? M * 4 : 0);          // sample coordinates handed from the fused forward to the backward
     w.d_rgbs = take(M * 3); w.d_fsig = take(M); w.d_feat = take(M * EGN_FEAT_STRIDE);
     w.gmax = take(1);                                                    // launch-wide max |d(sample colour)| (tcgen05 backward)
     const bool mlp = c->shading <= EGN_SHADE_MLP && !tc_backward(c);   // the tcgen05 backward needs no scratch
@@ -273,6 +274,7 @@ static int render_samples_impl(const EgnConfig* c, const EgnParams* p, const flo
         // when a backward pass will read it (full training workspace)
         // forward-only calls with whole 128-sample tiles per ray composite inside the kernel (no egn_composite_kernel launch)
         const bool comp = !save_feat && k.S % 128 == 0;
+        if (save_feat && tc_backward(c)) k.coords = (float*)(base + w.coord);
         if ((e = egn_launch_fused_fine(k, p, rays, n, z, fsig, save_feat ? feat : nullptr, rgbs, comp ? out : nullptr, base + w.image, st)))
             return cuda_fail("fused fine pass", e);
         mark(se, 2, st);
@@ -392,8 +394,10 @@ extern "C" int32_t egn_render_backward_sparse_env(const EgnConfig* c, const EgnP
                                         d_feat + m0 * EGN_FEAT_STRIDE, h1, h2, dz1, dz2, g, st))) return cuda_fail("mlp backward", e);
         }
     }
-    if (tc_backward(c))
+    if (tc_backward(c)) {
+        if (is_fused(c)) k.coords = (float*)(base + w.coord);          // written by the forward of this very workspace
         e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, gmax, d_tables, g, st);
+    }
     else
         e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);
     if (e) return cuda_fail("gather backward", e);

@@ -99,6 +99,9 @@ struct EgnKernelCfg {
     const void* tables_h;     // half tables of the fused fine pass (EgnLayoutH), or NULL
     int texp[2][3], texl[2][3];   // EgnLayoutH section starts (global texel indices)
     long long dens_byte_offset;
+    float* coords;            // optional [samples][4]: {r, polar, azimuth (index space), hemisphere} written by the fused training
+                              // forward and read back by the tcgen05 gather backward instead of recomputing acosf / atan2f / the
+                              // knot search per sample (bit-identical: same function, same inputs); NULL = recompute
 };
 
 #ifdef __CUDACC__

@@ -463,6 +463,10 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 FuRecord R;
                 fused_address_record(k, cc, R);
                 fused_store_record(R, recs + lane * (FU_REC_WORDS / 4));
+                if (!COMP && k.coords != nullptr) {                  // training forward: the backward reads the coordinates back
+                    const uint32_t mrow = tile * TC_TM + row0 + lane;
+                    if (mrow < M32) reinterpret_cast<float4*>(k.coords)[mrow] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang));
+                }
 #if !FU_ALPHA_IN_GATHER
                 s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
 #endif
@@ -577,6 +581,10 @@ egn_fused_fine_kernel(const __grid_constant__ EgnKernelCfg k, const unsigned cha
                 FuRecord R;
                 fused_address_record(k, cc, R);
                 fused_store_record(R, recs + fu_rec_slot(lane));
+                if (!COMP && k.coords != nullptr) {                  // training forward: the backward reads the coordinates back
+                    const uint32_t mrow = tile * TC_TM + row0 + lane;
+                    if (mrow < M32) reinterpret_cast<float4*>(k.coords)[mrow] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang));
+                }
                 s_yang[(it & 3) * TC_TM + row0 + lane] = (unsigned char)cc.yang;
             }
             __syncwarp();

@@ -170,10 +170,15 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             float dsg = 0.f;
             const bool glive = mg < M;
             if (glive) {
-                const long long ray = egn_ray_of(mg, k.S);
-                const float z = zs[mg];
-                const float* ry = rays + ray * 6;
-                cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+                if (k.coords != nullptr) {                           // saved by the fused forward (egn_fused.cu, phase 1b)
+                    const float4 sv = __ldg(reinterpret_cast<const float4*>(k.coords) + mg);
+                    cc.c[0] = sv.x; cc.c[1] = sv.y; cc.c[2] = sv.z; cc.yang = __float_as_int(sv.w);
+                } else {
+                    const long long ray = egn_ray_of(mg, k.S);
+                    const float z = zs[mg];
+                    const float* ry = rays + ray * 6;
+                    cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+                }
                 dsg = d_fsig[mg];
             }
             s_coord[r] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang | (glive ? 2 : 0)));
