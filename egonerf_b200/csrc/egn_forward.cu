@@ -118,7 +118,12 @@ __device__ __forceinline__ float egn_aabb_entry(const EgnKernelCfg& k, float ox,
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(K1_WARPS * 32, K1_MIN_BLOCKS)
+// MAXQ = per-lane slots of the scans / sorts: 4 for n_coarse, n_fine <= 128 (every shipped config), 8 up to 256
+// Resident CTAs per SM: 4 (64 registers) for MAXQ = 4 -- measured 0.752 ms per 65 536 rays against 0.770 at 2 CTAs / 128 registers
+// and 0.802 at 3 (the kernel is bound by ALU latency at few warps; 80 B of spills cost less than the extra warps bring)
+#define K1_BLOCKS(MAXQ) ((MAXQ) == 4 ? 2 * K1_MIN_BLOCKS : K1_MIN_BLOCKS)
+template <int MAXQ>
+__global__ void __launch_bounds__(K1_WARPS * 32, K1_BLOCKS(MAXQ))
 egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ rays, long long n, int is_train,
                   const float* __restrict__ u_c, const float* __restrict__ u_f, unsigned long long seed,
                   long long ray0, float near_plane, float* __restrict__ z_out) {
@@ -226,10 +231,10 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         }
         __syncwarp();
         // ---- 3. raw2alpha (tensorBase.py:22-27): lane owns `cnt` consecutive samples, warp product scan ----
-        float a_loc[K1_MAXC / 32], m_loc[K1_MAXC / 32];
+        float a_loc[MAXQ], m_loc[MAXQ];
         float prodl = 1.f;
 #pragma unroll
-        for (int q = 0; q < K1_MAXC / 32; ++q) {
+        for (int q = 0; q < MAXQ; ++q) {
             if (q < cnt) {
                 const int j = lane * cnt + q;
                 const float dist = ((j + 1 < nc) ? (zc[j + 1] - zc[j]) : (zc[nc - 1] - zc[nc - 2])) * k.distance_scale;
@@ -249,7 +254,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         if (lane == 0) T = 1.f;
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < K1_MAXC / 32; ++q) {
+        for (int q = 0; q < MAXQ; ++q) {
             if (q < cnt) {
                 sw[lane * cnt + q] = a_loc[q] * T;     // weights
                 T *= m_loc[q];
@@ -258,10 +263,10 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         __syncwarp();
         // ---- 4. pdf / cdf over weights[1:-1] + 1e-5 (ray_utils.py:159-162) ----
         const int nb = nc - 2;                      // number of pdf entries; cdf has nb + 1 = nc - 1 knots
-        float wp[K1_MAXC / 32];
+        float wp[MAXQ];
         float suml = 0.f;
 #pragma unroll
-        for (int q = 0; q < K1_MAXC / 32; ++q) {
+        for (int q = 0; q < MAXQ; ++q) {
             if (q < cnt) {
                 const int kk = lane * cnt + q;
                 wp[q] = (kk < nb) ? (sw[kk + 1] + 1e-5f) : 0.f;
@@ -273,7 +278,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
         float pl = 0.f;
 #pragma unroll
-        for (int q = 0; q < K1_MAXC / 32; ++q)
+        for (int q = 0; q < MAXQ; ++q)
             if (q < cnt) { wp[q] = wp[q] / tot; pl += wp[q]; }
         float inc2 = pl;
 #pragma unroll
@@ -285,7 +290,7 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         __syncwarp();
         if (lane == 0) sw[0] = 0.f;                 // cdf[0]
 #pragma unroll
-        for (int q = 0; q < K1_MAXC / 32; ++q) {
+        for (int q = 0; q < MAXQ; ++q) {
             if (q < cnt) {
                 const int kk = lane * cnt + q;
                 run += wp[q];
@@ -321,49 +326,49 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
         const int na = k.use_coarse_sample ? nc : 0;
         const int S = na + nf;
         const int EF = nf >> 5;
-        float vf[K1_MAXC / 32];
-        int rf[K1_MAXC / 32];
+        float vf[MAXQ];
+        int rf[MAXQ];
         if (EF == 4 || EF == 8) {
             // power-of-two draw counts (128: every shipped config; 256: the ERP-frame config): already-sorted fast path
             // (eval: u is a linspace and the inverse CDF is monotone), else a bitonic network in registers / shuffles
 #pragma unroll
-            for (int e = 0; e < K1_MAXC / 32; ++e) vf[e] = (e < EF) ? zn[lane * EF + e] : 0.f;
+            for (int e = 0; e < MAXQ; ++e) vf[e] = (e < EF) ? zn[lane * EF + e] : 0.f;
             bool sorted_ok = true;
 #pragma unroll
-            for (int e = 0; e < K1_MAXC / 32; ++e)
+            for (int e = 0; e < MAXQ; ++e)
                 if (e < EF) { const int idx = lane * EF + e; sorted_ok &= (idx + 1 >= nf) || (vf[e] <= zn[idx + 1]); }
             if (!__all_sync(FULL, sorted_ok)) {
                 if (EF == 4) {
                     float w4[4] = {vf[0], vf[1], vf[2], vf[3]};
                     egn_bitonic_sort<4>(w4, lane);
                     vf[0] = w4[0]; vf[1] = w4[1]; vf[2] = w4[2]; vf[3] = w4[3];
-                } else {
+                } else if constexpr (MAXQ == 8) {
                     egn_bitonic_sort<8>(vf, lane);
                 }
             }
 #pragma unroll
-            for (int e = 0; e < K1_MAXC / 32; ++e) rf[e] = lane * EF + e;
+            for (int e = 0; e < MAXQ; ++e) rf[e] = lane * EF + e;
         } else {
 #pragma unroll
-            for (int e = 0; e < K1_MAXC / 32; ++e) {
+            for (int e = 0; e < MAXQ; ++e) {
                 rf[e] = 0;
                 vf[e] = (e < EF) ? zn[e * 32 + lane] : 0.f;
             }
             for (int b = 0; b < nf; ++b) {
                 const float vb = zn[b];
 #pragma unroll
-                for (int e = 0; e < K1_MAXC / 32; ++e)
+                for (int e = 0; e < MAXQ; ++e)
                     if (e < EF) rf[e] += (vb < vf[e]) || (vb == vf[e] && b < e * 32 + lane);
             }
         }
         __syncwarp();
 #pragma unroll
-        for (int e = 0; e < K1_MAXC / 32; ++e)
+        for (int e = 0; e < MAXQ; ++e)
             if (e < EF) sw[rf[e]] = vf[e];          // sw (the cdf) is dead: it now holds the fine draws in increasing order
         __syncwarp();
         float* zo = z_out + ray * S;
 #pragma unroll
-        for (int e = 0; e < K1_MAXC / 32; ++e) {
+        for (int e = 0; e < MAXQ; ++e) {
             if (e < EF) {                            // fine element: coarse depths <= it come first
                 int lo = 0, hi = na;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= vf[e]) lo = mid + 1; else hi = mid; }
@@ -384,8 +389,13 @@ int egn_launch_coarse(const EgnKernelCfg& k, const float* rays, long long n, int
                       const float* u_f, unsigned long long seed, long long ray0, float near_plane, float* z_out,
                       cudaStream_t st) {
     long long blocks = (n + K1_WARPS - 1) / K1_WARPS;
-    if (blocks > 148 * 4 * K1_MIN_BLOCKS) blocks = 148 * 4 * K1_MIN_BLOCKS;
-    egn_coarse_kernel<<<(unsigned)blocks, K1_WARPS * 32, 0, st>>>(k, rays, n, is_train, u_c, u_f, seed, ray0, near_plane, z_out);
+    const bool small = k.n_coarse <= 128 && k.n_fine <= 128;
+    const long long cap = 148ll * 4 * (small ? K1_BLOCKS(4) : K1_BLOCKS(8));
+    if (blocks > cap) blocks = cap;
+    if (small)
+        egn_coarse_kernel<4><<<(unsigned)blocks, K1_WARPS * 32, 0, st>>>(k, rays, n, is_train, u_c, u_f, seed, ray0, near_plane, z_out);
+    else
+        egn_coarse_kernel<8><<<(unsigned)blocks, K1_WARPS * 32, 0, st>>>(k, rays, n, is_train, u_c, u_f, seed, ray0, near_plane, z_out);
     return (int)cudaGetLastError();
 }
 
