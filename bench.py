@@ -146,14 +146,17 @@ def cpu_baseline_record(rps, repeats):
                       f"({os.cpu_count()} threads); identical leg in-line and under --impl reference"}
 
 
+FACT_SOURCES = ("egn_fused.cu", "egn_tc.cuh", "egn_shared.cuh", "egn_device.cuh", "egn_host.h")
+
+
 def source_sha():
-    """Hash of the kernel sources: profile-derived numbers (ncu dram traffic, issue utilisation) are reported only when they
-    were captured from THIS build (profiles/kernel_facts.json records the hash they belong to)."""
-    import glob
+    """Hash of the sources the dominant kernel (egn_fused_fine_kernel) is compiled from: profile-derived numbers (ncu dram
+    traffic, issue utilisation) are reported only when they were captured from THIS build of that kernel
+    (profiles/kernel_facts.json records the hash they belong to)."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "egonerf_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "egonerf_b200", "csrc", "*.cuh"))):
-        h.update(open(f, "rb").read())
+    for f in FACT_SOURCES:
+        h.update(open(os.path.join(ROOT, "egonerf_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -178,6 +181,8 @@ def main():
                     help="arithmetic: exact fp32 FFMA, tcgen05 3-term bf16 split (fp32-equivalent), tc_f16 = throughput mode "
                          "(fused kernel, fp16 operands + fp32 density; tc_bf16 is its old name)")
     ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"], help="dtype of the factor-gradient all-reduce")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1 training: gradient exchange by one kernel over NVLink peer memory (egn_peer_allreduce) or by ncclAllReduce")
     args = ap.parse_args()
     if args.mlp == "tc_bf16":
         args.mlp = "tc_f16"
@@ -288,10 +293,19 @@ def main():
             if table_adam:
                 self.opt = TableAdam(model_, 0.02, 0.001, 0.1)
                 self.opt.grad_allreduce_dtype = torch.bfloat16 if args.grad_dtype == "bf16" else None
+                # gradient exchange: one kernel over NVLink peer memory (egn_peer_allreduce) unless --exchange nccl
+                self.peer = (world > 1 and args.exchange == "peer" and args.grad_dtype == "f32"
+                             and self.opt.enable_peer_exchange())
             else:
                 self.opt = torch.optim.Adam(model_.get_optparam_groups(0.02, 0.001, merged=True), betas=(0.9, 0.99), fused=True)
             self.table_adam = table_adam
             self.ar_events = []
+            if not table_adam:
+                self.peer = False
+
+        def close(self):
+            if self.table_adam:
+                self.opt.disable_peer_exchange()
 
         def __call__(self, e2e=False, time_allreduce=False):
             m = self.model
@@ -342,9 +356,14 @@ def main():
                "allreduce": {"bytes_dense": int(numel * (2 if args.grad_dtype == "bf16" else 4)), "dtype": args.grad_dtype,
                              "envmap_gradient": ("sparse: all-gather of 24 B/ray + local scatter (egn_envmap_backward)"
                                                  if model_.envmap is not None else None),
-                             "what": "NCCL all-reduce of the table-layout factor gradient + one flat bucket of basis / MLP gradients"
-                                     if world > 1 else "single GPU: no collective (local envmap scatter only)"},
+                             "what": ("one kernel over NVLink peer memory (egn_peer_allreduce): table-layout factor gradient + the "
+                                      "basis / MLP bucket in its tail, reduce-scatter by peer loads, all-gather by peer stores"
+                                      if st.peer else
+                                      "NCCL all-reduce of the table-layout factor gradient + one flat bucket of basis / MLP gradients")
+                                     if world > 1 else "single GPU: no collective (local envmap scatter only)",
+                             "path": ("peer" if st.peer else "nccl") if world > 1 else None},
                "optimizer": "TableAdam (egn_adam_tables)", "gpu_launches_per_step": model_.launches_per_train_step(n)}
+        st.close()
         del st, model_, scene_
         torch.cuda.empty_cache()
         return rec

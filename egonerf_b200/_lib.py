@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EGN_B200_LIB") or os.path.join(_HERE, "libegn_b200.so")      # override: kernel experiments only
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -102,6 +102,14 @@ PROTOTYPES = {
     "egn_host_r_knots": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p]),
     "egn_host_plain_sample_schedule": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p, c_float_p, c_float_p]),
     "egn_host_plain_r_knots": (C.c_int32, [C.c_float, C.c_float, C.c_int32, c_float_p]),
+    "egn_peer_flag_bytes": (C.c_int64, []),
+    "egn_peer_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "egn_peer_free": (C.c_int32, [C.c_void_p]),
+    "egn_peer_export": (C.c_int32, [C.c_void_p, C.c_char_p]),
+    "egn_peer_open": (C.c_int32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "egn_peer_close": (C.c_int32, [C.c_void_p]),
+    "egn_peer_allreduce": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_float,
+                                       C.c_uint32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

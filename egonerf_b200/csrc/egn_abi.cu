@@ -14,6 +14,14 @@ static int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
+// for the other translation units of the library (egn_peer.cu)
+int egn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
 static int cuda_fail(const char* what, int e) {
     return fail("%s: %s", what, cudaGetErrorString((cudaError_t)e));
 }

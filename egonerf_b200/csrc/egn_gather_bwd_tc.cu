@@ -36,9 +36,25 @@ struct GtLayout {
     static constexpr int DSG = COORD + TC_TM * 16;                         // [128] d(sigma feature)
     static constexpr int MBAR = DSG + TC_TM * 4;
     static constexpr int TMEM = MBAR + 16;
-    static constexpr int TOTAL = TMEM + 16;
+    // GT_PREFETCH: inputs of the NEXT tile, fetched by cp.async while this tile is being scattered
+    static constexpr int NXT_DF = TMEM + 16;                               // [128 m][28] d_feat rows   14 336
+    static constexpr int NXT_CO = NXT_DF + TC_TM * EGN_FEAT_STRIDE * 4;     // [128] saved coordinates     2 048
+    static constexpr int NXT_DS = NXT_CO + TC_TM * 16;                      // [128] d(sigma feature)        512
+    static constexpr int TOTAL = NXT_DS + TC_TM * 4;
 };
 static_assert(GtLayout::TOTAL <= 227 * 1024, "gather backward kernel exceeds the shared memory of one SM");
+
+#ifndef GT_PREFETCH
+#define GT_PREFETCH 1                // 1: d_feat / saved coordinates / d(sigma feature) of tile t+1 land in shared memory (cp.async) during Ph3 of tile t
+#endif
+__device__ __forceinline__ void gt_cp16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void gt_cp4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void gt_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gt_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void gt_red4(float* addr, float4 v) { atomicAdd(reinterpret_cast<float4*>(addr), v); }
 __device__ __forceinline__ float4 gt_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
@@ -145,12 +161,44 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     uint32_t it = 0;
     bool ok = true;
+#if GT_PREFETCH
+    float4* nx_df = reinterpret_cast<float4*>(smem + L::NXT_DF);
+    float4* nx_co = reinterpret_cast<float4*>(smem + L::NXT_CO);
+    float* nx_ds = reinterpret_cast<float*>(smem + L::NXT_DS);
+    // the tile's inputs are contiguous in global memory: 128 rows x 7 float4 of d_feat, 128 float4 of coordinates, 128 floats
+    auto prefetch = [&](long long t) {
+        if (t < tiles) {
+            const long long m0 = t * TC_TM;
+            const long long live = (M - m0 < TC_TM) ? (M - m0) : TC_TM;
+            const float4* src = reinterpret_cast<const float4*>(d_feat + m0 * EGN_FEAT_STRIDE);
+            for (int i = tid; i < live * (EGN_FEAT_STRIDE / 4); i += GT_THREADS) gt_cp16(nx_df + i, src + i);
+            if (tid < live) {
+                if (k.coords != nullptr) gt_cp16(nx_co + tid, reinterpret_cast<const float4*>(k.coords) + m0 + tid);
+                gt_cp4(nx_ds + tid, d_fsig + m0 + tid);
+            }
+        }
+        gt_cp_commit();
+    };
+    prefetch(blockIdx.x);
+    gt_cp_wait();                                                // each thread's own copies have landed ...
+    __syncthreads();                                             // ... and so have everybody else's
+#endif
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const uint32_t par = it & 1;
-        // ---- Ph1a. this thread's 8 values of d_feat: requested now, in flight during Ph0 ----
+        // ---- Ph1a. this thread's 8 values of d_feat ----
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#if GT_PREFETCH
+        {                                                        // staged by cp.async during the previous tile's Ph3
+            const long long gm = tile * TC_TM + row;
+            if (gm < M) {
+                const float4 a = nx_df[row * (EGN_FEAT_STRIDE / 4) + 2 * q];
+                v[0] = a.x * scale; v[1] = a.y * scale; v[2] = a.z * scale; v[3] = a.w * scale;
+                if (q < 3) { const float4 b = nx_df[row * (EGN_FEAT_STRIDE / 4) + 2 * q + 1]; v[4] = b.x * scale; v[5] = b.y * scale; v[6] = b.z * scale; v[7] = b.w * scale; }
+            }
+        }
+#else
         {
             const long long gm = tile * TC_TM + row;
             if (gm < M) {
@@ -160,6 +208,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 if (q < 3) { const float4 b = __ldg(f4 + 1); v[4] = b.x * scale; v[5] = b.y * scale; v[6] = b.z * scale; v[7] = b.w * scale; }
             }
         }
+#endif
         // ---- Ph0. coordinates + d(sigma feature) of the tile's 128 samples: one sample per lane of warps 0..3 -> smem ----
         if (warp < 4) {
             const int r = 32 * warp + lane;
@@ -171,7 +220,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             const bool glive = mg < M;
             if (glive) {
                 if (k.coords != nullptr) {                           // saved by the fused forward (egn_fused.cu, phase 1b)
+#if GT_PREFETCH
+                    const float4 sv = nx_co[r];
+#else
                     const float4 sv = __ldg(reinterpret_cast<const float4*>(k.coords) + mg);
+#endif
                     cc.c[0] = sv.x; cc.c[1] = sv.y; cc.c[2] = sv.z; cc.yang = __float_as_int(sv.w);
                 } else {
                     const long long ray = egn_ray_of(mg, k.S);
@@ -179,7 +232,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                     const float* ry = rays + ray * 6;
                     cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
                 }
+#if GT_PREFETCH
+                dsg = nx_ds[r];
+#else
                 dsg = d_fsig[mg];
+#endif
             }
             s_coord[r] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang | (glive ? 2 : 0)));
             s_dsg[r] = dsg;
@@ -197,6 +254,9 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+#if GT_PREFETCH
+        prefetch(tile + gridDim.x);                             // staging consumed by everybody (Ph0, Ph1a): refill it behind Ph2 / Ph3
+#endif
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
@@ -340,6 +400,9 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         cache.flush_plane(d_tab);
 #pragma unroll
         for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_tab, i);
+#if GT_PREFETCH
+        gt_cp_wait();                                            // next tile's inputs: own copies landed; the barrier below covers the rest
+#endif
         fence_async_smem();
         tc_fence_before();
         __syncthreads();

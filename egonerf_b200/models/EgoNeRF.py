@@ -127,9 +127,10 @@ class _VolumeRender(torch.autograd.Function):
         c = lambda t: None if t is None else t.contiguous().float()
         d_rgb, d_bg, d_env, d_alpha = c(d_rgb), c(d_bg), c(d_env), c(d_alpha)
         cfg = model._config(opts)
-        d_tables = torch.zeros_like(tables)
         plist = model._param_list()
         table_opt = getattr(model, "_table_opt", None)
+        # with a table-space optimiser the gradient may live in NVLink peer memory (TableAdam.enable_peer_exchange)
+        d_tables = table_opt.grad_target(tables) if table_opt is not None else torch.zeros_like(tables)
         # one allocation for every gradient: the 24 factor gradients are overwritten by egn_unpack_table_grads, the rest
         # (basis, MLP, envmap) is accumulated into and must start at zero — a single fill instead of one per tensor.
         # With a table-space optimiser attached (egonerf_b200/optim.py) the factor gradients stay in table layout.
@@ -726,16 +727,25 @@ class EgoNeRF(torch.nn.Module):
         persistent flat bucket (egonerf_b200/sharding.py)."""
         from ..sharding import GradientBucket, gather_env_gradient
         ps = self._param_list()
-        if getattr(self, "_table_opt", None) is not None:        # factor gradients live in table layout: one buffer already
-            self._table_opt.allreduce(group, average)
+        table_opt = getattr(self, "_table_opt", None)
+        if table_opt is not None:                                # factor gradients live in table layout: one buffer already
             ps = ps[24:]
         if self.envmap is not None and self.sparse_env_grad:     # 24 B / ray all-gather + local scatter instead of 88 MB
             gather_env_gradient(self, group, average)
             ps = ps[:-1]
-        if getattr(self, "_bucket", None) is None or [id(p) for p in self._bucket.params] != [id(p) for p in ps]:
-            self._bucket = GradientBucket(ps)
+        # peer-memory exchange (TableAdam.enable_peer_exchange): the bucket lives in the tail of the peer buffer and is
+        # summed by the same kernel as the factor gradient
+        peer_tail = getattr(table_opt, "peer_tail", None) if (table_opt is not None and table_opt.peer is not None) else None
+        if peer_tail is not None and sum(p.numel() for p in ps) > peer_tail.numel():
+            peer_tail = None
+        if (getattr(self, "_bucket", None) is None or [id(p) for p in self._bucket.params] != [id(p) for p in ps]
+                or (peer_tail is not None) != self._bucket.external):
+            self._bucket = GradientBucket(ps, storage=peer_tail)
         self._bucket.gather_from_params()
-        self._bucket.allreduce(group, average)
+        if table_opt is not None:
+            table_opt.allreduce(group, average)
+        if not self._bucket.external:
+            self._bucket.allreduce(group, average)
 
     def stage_times(self, rays_chunk, repeats=3, n_coarse=128, n_fine=128, resampling=True, use_coarse_sample=True, **_):
         """Mean device time (ms) of each stage of the eval forward, from CUDA events recorded between the launches

@@ -45,19 +45,67 @@ class TableAdam:
         # None: all-reduce the table gradient in fp32 (exact: the sum of the shards' gradients); torch.bfloat16: half the bytes
         # over NVLink at 2^-9 relative rounding per element (a measured option of bench.py --grad-dtype, not the default)
         self.grad_allreduce_dtype = None
+        # ray-sharded training over NVLink peer memory (enable_peer_exchange): the gradient buffer then IS peer memory
+        self.peer = None
+        self._n_tables = tables.numel()
         model._table_opt = self
+
+    def enable_peer_exchange(self, group=None, tail_floats=None, blocks=148):
+        """Collective over `group`: from now on the table-layout gradient is accumulated in a buffer every rank can reach over
+        NVLink (cudaIpc peer memory, `sharding.PeerExchange`) and `allreduce()` is ONE kernel over peer memory
+        (`egn_peer_allreduce`) instead of `ncclAllReduce`; the buffer's tail carries the flat bucket of the basis / MLP
+        gradients (`EgoNeRF.allreduce_gradients`), so the step needs no other gradient collective.  Returns False (and keeps
+        the NCCL path on every rank) when peer memory cannot be mapped."""
+        import torch.distributed as dist
+        from .sharding import PeerExchange
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return False
+        if tail_floats is None:                      # everything but the factor tensors and the envmap emission
+            fac = {id(p) for p in self.model._factor_params()}
+            em = id(self.model.envmap.emission) if self.model.envmap is not None else None
+            tail_floats = sum(p.numel() for p in self.model._param_list() if id(p) not in fac and id(p) != em)
+        self._n_head = (self._n_tables + 3) // 4 * 4
+        try:
+            self.peer = PeerExchange(self._n_head + int(tail_floats), self._device(), group, blocks)
+        except RuntimeError as e:
+            import warnings
+            warnings.warn(f"egonerf_b200: {e}; gradient exchange stays on NCCL")
+            self.peer = None
+            return False
+        self.peer_head = self.peer.tensor[:self._n_tables]
+        self.peer_tail = self.peer.tensor[self._n_head:]
+        self.d_tables = None
+        return True
+
+    def disable_peer_exchange(self):
+        """Collective: back to the NCCL path; unmaps and frees the peer buffers."""
+        if self.peer is not None:
+            self.d_tables = None
+            self.peer_head = self.peer_tail = None
+            self.peer.close()
+            self.peer = None
+            self.model._bucket = None
+
+    def grad_target(self, like):
+        """Zeroed table-layout buffer for one backward pass: the peer buffer itself for the first backward of a step."""
+        if self.peer is not None and self.d_tables is None:
+            return self.peer_head.view_as(like).zero_()
+        return torch.zeros_like(like)
 
     def _device(self):
         return self.exp_avg.device
 
     def _grad_buffer(self):
         if self.d_tables is None:
-            self.d_tables = torch.zeros_like(self.exp_avg)
+            self.d_tables = self.grad_target(self.exp_avg)
         return self.d_tables
 
     # called by the render autograd node instead of egn_unpack_table_grads
     def accumulate(self, d_tables):
-        self.d_tables = d_tables if self.d_tables is None else self.d_tables.add_(d_tables)
+        if self.d_tables is None or self.d_tables is d_tables:
+            self.d_tables = d_tables
+        else:
+            self.d_tables.add_(d_tables)
 
     def zero_grad(self, set_to_none=True):
         self.d_tables = None
@@ -103,6 +151,13 @@ class TableAdam:
             return
         self._fold_param_grads()
         buf = self._grad_buffer()
+        if self.peer is not None:
+            if buf.data_ptr() != self.peer_head.data_ptr():      # gradient was produced outside the peer buffer
+                self.peer_head.view_as(buf).copy_(buf)
+                buf = self.d_tables = self.peer_head.view_as(buf)
+            # head (factor gradient) and tail (basis / MLP bucket) in one kernel; the mean over ranks is folded in
+            self.peer.allreduce(1.0 / dist.get_world_size(group) if average else 1.0)
+            return
         if self.grad_allreduce_dtype is not None:
             low = buf.to(self.grad_allreduce_dtype)
             dist.all_reduce(low, op=dist.ReduceOp.SUM, group=group)

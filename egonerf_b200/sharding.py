@@ -23,11 +23,13 @@ class GradientBucket:
     """One flat buffer holding every gradient, so that a step needs ONE all-reduce launch (latency-bound over NVSwitch:
     bucket for launch count, not link count).  `p.grad` of every parameter becomes a view into the buffer."""
 
-    def __init__(self, params):
+    def __init__(self, params, storage=None):
         self.params = [p for p in params]
         total = sum(p.numel() for p in self.params)
         p0 = self.params[0]
-        self.flat = torch.zeros(total, dtype=p0.dtype, device=p0.device)
+        # `storage`: a flat fp32 tensor someone else reduces (the tail of the peer-memory buffer, PeerExchange)
+        self.external = storage is not None
+        self.flat = storage[:total].zero_() if self.external else torch.zeros(total, dtype=p0.dtype, device=p0.device)
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
@@ -98,3 +100,106 @@ def gather_env_gradient(model, group=None, average=False, equal_counts=True):
     if average:
         d_em.div_(world)
     em.grad = d_em
+
+
+def slice_bounds(n_floats: int, rank: int, world: int):
+    """[start, stop) in floats of the slice rank `rank` sums in `egn_peer_allreduce` (egn_peer.cu: float4 units, ceil split)."""
+    n4 = int(n_floats) // 4
+    per = -(-n4 // int(world))
+    lo = min(per * rank, n4)
+    return 4 * lo, 4 * min(lo + per, n4)
+
+
+class _DevicePointer:
+    """`__cuda_array_interface__` view of device memory this library allocated, so torch can wrap it without owning it."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Gradient buffer in NVLink peer memory + the one-kernel all-reduce over it (`egn_peer_allreduce`, csrc/egn_peer.cu).
+
+    Every rank allocates `numel` floats (+ a flag block) with `egn_peer_alloc`, the ranks exchange cudaIpc handles through the
+    process group and map each other's allocations.  `tensor` is the local buffer as a torch tensor: the backward kernels
+    scatter into it, `allreduce()` replaces it by the sum over ranks (bit-identical on every rank) and `egn_adam_tables`
+    reads it -- no copy in between.  Construction is collective; if any rank cannot map its peers, all ranks raise and the
+    caller keeps the NCCL path."""
+
+    def __init__(self, numel, device, group=None, blocks=148):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        self.numel = (int(numel) + 3) // 4 * 4
+        self.blocks, self.epoch = int(blocks), 0
+        self._opened, self._own = [], []
+        ok, err = True, ""
+        with torch.cuda.device(self.device):
+            try:
+                buf, flg = C.c_void_p(), C.c_void_p()
+                _lib.check(self.lib.egn_peer_alloc(self.numel * 4, C.byref(buf)))
+                self._own.append(buf.value)
+                _lib.check(self.lib.egn_peer_alloc(self.lib.egn_peer_flag_bytes(), C.byref(flg)))
+                self._own.append(flg.value)
+                hb, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+                _lib.check(self.lib.egn_peer_export(buf, hb))
+                _lib.check(self.lib.egn_peer_export(flg, hf))
+                mine = (self.rank, bytes(hb.raw), bytes(hf.raw))
+            except RuntimeError as e:                    # still take part in the collectives below
+                ok, err, mine = False, str(e), (self.rank, b"", b"")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            bufs, flags = [None] * self.world, [None] * self.world
+            if ok:
+                bufs[self.rank], flags[self.rank] = buf.value, flg.value
+                try:
+                    for r, b, f in handles:
+                        if r == self.rank:
+                            continue
+                        if not b:
+                            raise RuntimeError(f"rank {r} could not export its buffer")
+                        pb, pf = C.c_void_p(), C.c_void_p()
+                        _lib.check(self.lib.egn_peer_open(b, C.byref(pb)))
+                        self._opened.append(pb.value)
+                        _lib.check(self.lib.egn_peer_open(f, C.byref(pf)))
+                        self._opened.append(pf.value)
+                        bufs[r], flags[r] = pb.value, pf.value
+                except RuntimeError as e:
+                    ok, err = False, str(e)
+            agree = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)
+            if int(agree.item()) == 0:
+                self.close()
+                raise RuntimeError("peer-memory exchange unavailable: " + (err or "a peer rank failed to map the buffers"))
+            self._bufs = (C.c_void_p * self.world)(*bufs)
+            self._flags = (C.c_void_p * self.world)(*flags)
+            self._holder = _DevicePointer(buf.value, self.numel)
+            self.tensor = torch.as_tensor(self._holder, device=self.device)
+            # nobody may start the first exchange before every rank has mapped everything
+            dist.barrier(group=group)
+
+    def allreduce(self, scale=1.0, stream=None):
+        """tensor <- scale * sum over ranks of tensor, on `stream` (default: torch's current stream)."""
+        from . import _lib
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.egn_peer_allreduce(self._bufs, self._flags, self.rank, self.world, self.numel, float(scale),
+                                                   self.epoch, self.blocks, st))
+
+    def close(self):
+        """Collective: every rank unmaps its peers' allocations before anybody frees its own."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._opened:
+                self.lib.egn_peer_close(p)
+            self._opened = []
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for p in self._own:
+                self.lib.egn_peer_free(p)
+            self._own = []
+        self.tensor = None

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EGN_ABI_VERSION 7
+#define EGN_ABI_VERSION 8
 
 /* renderModule kinds, TensorBase.init_render_func (models/tensorBase.py:187-203) */
 enum { EGN_SHADE_MLP_FEA = 0, EGN_SHADE_MLP = 1, EGN_SHADE_RGB = 2, EGN_SHADE_SH = 3 };
@@ -271,6 +271,28 @@ int32_t egn_host_r_knots(float far_r, float r0, int32_t n_r, float* knots_out /*
 int32_t egn_host_plain_sample_schedule(float near_plane, float far_plane, int32_t n, float* z_out, float* ratio_out /*nullable*/,
                                        float* r0_out /*nullable*/);
 int32_t egn_host_plain_r_knots(float far_r, float r0, int32_t n_r, float* knots_out /*n_r+3*/);
+
+/* ---- gradient exchange of ray-sharded training over NVLink peer memory --------------------------------
+ * The reference is single-process (train.py:20, no process group at train.py:409-422); the multi-GPU launcher sums the
+ * gradients of the ray shards once per step.  These entry points replace the `ncclAllReduce` of the table-layout factor
+ * gradient by ONE kernel over peer memory: rank r sums slice r of every rank's buffer (peer loads) and stores the sum into
+ * slice r of every rank's buffer (peer stores); block b of every rank handshakes with block b of every peer before the first
+ * load and after the last store (flags in peer memory, release / acquire at system scope; a missing peer traps after 4 s).
+ *   egn_peer_alloc / _free      cudaMalloc'ed, zero-filled device memory (cudaIpc handles address whole allocations)
+ *   egn_peer_export / _open / _close   cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) / cudaIpcCloseMemHandle
+ *   egn_peer_flag_bytes         size of the flag block every rank allocates with egn_peer_alloc and exports next to its buffer
+ *   egn_peer_allreduce          bufs[world], flags[world]: HOST arrays of device pointers in rank order (own entries = the local
+ *                               allocations); n_floats % 4 == 0; every rank passes the same n_floats, scale, epoch (1, 2, 3, ...
+ *                               per call) and blocks (<= 256); result: buf_p[i] = scale * sum_q buf_q[i] on every rank p,
+ *                               bit-identical across ranks. */
+int64_t egn_peer_flag_bytes(void);
+int32_t egn_peer_alloc(int64_t bytes, void** ptr_out);
+int32_t egn_peer_free(void* ptr);
+int32_t egn_peer_export(const void* ptr, unsigned char handle_out[64]);
+int32_t egn_peer_open(const unsigned char handle[64], void** ptr_out);
+int32_t egn_peer_close(void* ptr);
+int32_t egn_peer_allreduce(void* const* bufs, void* const* flags, int32_t rank, int32_t world, int64_t n_floats, float scale,
+                           uint32_t epoch, int32_t blocks, void* stream);
 
 #ifdef __cplusplus
 }

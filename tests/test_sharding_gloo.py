@@ -65,3 +65,26 @@ def test_gradient_bucket_allreduce_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert len(out) == world and all(e < 1e-5 for e in out.values()), dict(out)
+
+
+def test_peer_slices_partition_the_buffer():
+    """Slice split of egn_peer_allreduce (float4 units, ceil split): slices are disjoint, ordered and cover the buffer."""
+    from egonerf_b200.sharding import slice_bounds
+    for n in (4, 8, 12, 4000, 24721124 + 56320, 104):
+        for world in (1, 2, 3, 4, 8, 16):
+            prev = 0
+            for r in range(world):
+                lo, hi = slice_bounds(n, r, world)
+                assert lo == prev and lo % 4 == 0 and hi % 4 == 0 and hi >= lo
+                prev = hi
+            assert prev == n
+
+
+def test_peer_exchange_is_not_used_without_a_process_group():
+    """enable_peer_exchange is a no-op (False) outside a multi-rank process group: single-GPU training is untouched."""
+    import types
+    from egonerf_b200.optim import TableAdam
+    opt = TableAdam.__new__(TableAdam)
+    opt.peer = None
+    opt.model = types.SimpleNamespace()
+    assert TableAdam.enable_peer_exchange(opt) is False and opt.peer is None
