@@ -410,6 +410,7 @@ def main():
     train = args.mode == "train"
     if train:
         tstep = TrainStep(model, rays_dev, n_rays, table_adam=not args.torch_adam, host_rays=rays_host)
+        config["exchange"] = ("peer-memory kernel (egn_peer_allreduce)" if tstep.peer else "nccl") if world > 1 else None
         config["optimizer"] = ("torch.optim.Adam(fused=True) + egn_unpack_table_grads + egn_pack_tables" if args.torch_adam
                                else "TableAdam (egn_adam_tables: Adam + table refresh in one pass)")
 

@@ -100,8 +100,20 @@ __device__ __forceinline__ float4 gt_tap(const EgnKernelCfg& k, unsigned off) {
         return ldg4(k.tables + off);
     }
 }
+#ifndef GT_L2_KEEP
+#define GT_L2_KEEP 0                 // 1: table taps loaded with an L2 evict_last policy (the 50 MB bf16 table competes with the 99 MB gradient table for L2)
+#endif
 __device__ __forceinline__ uint2 gt_raw(const EgnKernelCfg& k, unsigned off) {
+#if GT_L2_KEEP
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    uint2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y)
+                 : "l"(reinterpret_cast<const __nv_bfloat16*>(k.tables_bf16) + off), "l"(pol));
+    return v;
+#else
     return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(k.tables_bf16) + off));
+#endif
 }
 __device__ __forceinline__ float4 gt_widen(const uint2& q) {
     return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),

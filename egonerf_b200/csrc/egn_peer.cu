@@ -26,7 +26,12 @@
 #define PEER_MAX_WORLD 16
 #define PEER_MAX_BLOCKS 256
 #define PEER_THREADS 512
+#ifndef PEER_UNROLL
 #define PEER_UNROLL 2
+#endif
+#ifndef PEER_ACCESS
+#define PEER_ACCESS 0                // 0: ld / st .relaxed.sys (SASS .STRONG.SYS); 1: ld.global.cg / st.global.cg (L2-only, weak) -- ordered by the handshakes
+#endif
 #ifndef EGN_PEER_TIMEOUT_NS
 #define EGN_PEER_TIMEOUT_NS 4000000000ull
 #endif
@@ -53,12 +58,20 @@ __device__ __forceinline__ unsigned long long peer_now() {
 }
 // peer data changes between launches and is written by other GPUs: read it past L1, at system scope
 __device__ __forceinline__ float4 peer_ld4(const float4* p) {
+#if PEER_ACCESS == 1
+    return __ldcg(p);
+#else
     float4 v;
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
+#endif
 }
 __device__ __forceinline__ void peer_st4(float4* p, float4 v) {
+#if PEER_ACCESS == 1
+    __stcg(p, v);
+#else
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
 }
 
 // flags of one rank: [phase 2][source rank PEER_MAX_WORLD][block PEER_MAX_BLOCKS]

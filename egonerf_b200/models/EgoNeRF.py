@@ -134,13 +134,23 @@ class _VolumeRender(torch.autograd.Function):
         # one allocation for every gradient: the 24 factor gradients are overwritten by egn_unpack_table_grads, the rest
         # (basis, MLP, envmap) is accumulated into and must start at zero — a single fill instead of one per tensor.
         # With a table-space optimiser attached (egonerf_b200/optim.py) the factor gradients stay in table layout.
-        sizes = [0 if (table_opt is not None and i < 24) else p.numel() for i, p in enumerate(plist)]
+        # Non-factor gradients (basis, MLP, envmap) are ACCUMULATED by the kernels.  If such a parameter already carries a
+        # contiguous fp32 .grad (e.g. the views of the exchange bucket that TableAdam.zero_grad() re-attaches and zeroes every
+        # step), the kernels add straight into it and autograd gets None for it: no per-parameter copies, and several backward
+        # passes per step sum as autograd would.
+        def in_place(i, p):
+            g = p.grad
+            return (i >= 24 and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == tables.device
+                    and g.shape == p.shape)
+        inplace = [in_place(i, p) for i, p in enumerate(plist)]
+        sizes = [0 if ((table_opt is not None and i < 24) or inplace[i]) else p.numel() for i, p in enumerate(plist)]
         flat = torch.empty(sum(sizes), device=tables.device, dtype=torch.float32)
         n_fac = sum(sizes[:24])
-        flat[n_fac:].zero_()
+        if flat.numel() > n_fac:
+            flat[n_fac:].zero_()
         grads, off = [], 0
-        for p, sz in zip(plist, sizes):
-            grads.append(flat[off:off + sz].view_as(p) if sz else None)
+        for i, (p, sz) in enumerate(zip(plist, sizes)):
+            grads.append(p.grad if inplace[i] else (flat[off:off + sz].view_as(p) if sz else None))
             off += sz
         G = model._grads_struct(grads)
         # ray-sharded training exchanges the envmap gradient in sparse form (24 B per ray instead of the dense (3, 2h, h)
@@ -154,6 +164,7 @@ class _VolumeRender(torch.autograd.Function):
                                                       _lib.ptr(d_alpha), d_tables.data_ptr(), G, _lib.ptr(env_rays), _stream()))
         if env_rays is not None:
             grads[-1] = None                      # the dense emission gradient is produced by allreduce_gradients
+        grads = [None if inplace[i] else g for i, g in enumerate(grads)]
         if table_opt is not None:
             table_opt.accumulate(d_tables)
         else:

@@ -113,6 +113,9 @@ class TableAdam:
             p.grad = None
         if self.other:
             self.other.zero_grad(set_to_none=set_to_none)
+        bucket = getattr(self.model, "_bucket", None)
+        if bucket is not None:                       # ray-sharded training: gradients accumulate in place in the exchange bucket
+            bucket.zero()
 
     @torch.no_grad()
     def regularize(self, tv_density=0.0, tv_app=0.0, l1_density=0.0):

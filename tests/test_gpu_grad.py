@@ -370,3 +370,38 @@ def test_sparse_envmap_gradient_equals_the_dense_one():
     ref = grads[False]
     assert float(ref.abs().max()) > 0
     assert float((grads[True] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_second_backward_accumulates_in_place_like_autograd():
+    """A parameter that already carries a contiguous fp32 .grad (the exchange bucket's views, or simply a step without
+    zero_grad) gets the new gradient ADDED in place by the kernels and None from the autograd node (models/EgoNeRF.py
+    `_backward`): same result as autograd's own accumulation, no per-parameter copies.  Checked on every non-factor tensor
+    (basis, MLP, envmap) -- the factor tensors go through egn_unpack_table_grads as before."""
+    from egonerf_b200.scene_io import model_from_scene, RENDER_KW
+    name = "render_tiny_env_train_grad"
+    skw, okw = RENDER_CASES[name]
+    g = load_golden(name)
+    dev = "cuda:0"
+    model = model_from_scene(scene_for(skw), dev, interval_th=okw.get("interval_th", True))
+    kw = dict(RENDER_KW)
+    kw.update(okw)
+
+    def backward():
+        out = model(T(g["rays"]).to(dev), is_train=True, u_coarse=T(g["u_coarse"]).to(dev), u_fine=T(g["u_fine"]).to(dev),
+                    z_vals=T(g["z_vals"]).to(dev), **kw)
+        _loss(out, g, dev).backward()
+
+    backward()
+    named = dict(model.named_parameters())
+    named["envmap.emission"] = model.envmap.emission
+    first = {k: p.grad.clone() for k, p in named.items()}
+    ptrs = {k: p.grad.data_ptr() for k, p in named.items()}
+    backward()
+    torch.cuda.synchronize()
+    factor = {id(p) for p in model._factor_params()}
+    for k, p in named.items():
+        ref = 2 * first[k]
+        rel = float((p.grad - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+        assert rel <= 1e-4, (k, rel)
+        if id(p) not in factor:
+            assert p.grad.data_ptr() == ptrs[k], f"{k}: .grad was replaced instead of accumulated into"
