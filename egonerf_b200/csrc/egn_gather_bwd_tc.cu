@@ -22,19 +22,23 @@
 #define GT_VCHUNK (TC_CHUNK + 64)          // padded K-chunk stride of the V tile (bank-conflict-free row stores, see egn_fused.cu)
 #define IDESC_DV TC_IDESC_F16(0x08250490u)               // M128 N144, A K-major, B MN-major
 #define IDESC_DB TC_IDESC_F16(0x08258490u)               // M128 N144, A MN-major, B MN-major
-#define GT_TM_DV 0
-#define GT_TM_DB 160
+#ifndef GT_PIPE
+#define GT_PIPE 0                    // 1: dF2 / MMA1 of tile t+1 are staged BEFORE the scatter phase of tile t (two dF2 tiles, two dV accumulators in TMEM):
+#endif                               //    no MMA wait is exposed and a tile takes three CTA barriers instead of four (needs GT_PREFETCH)
+#define GT_TM_DV 0                   // dV accumulator(s): columns 0..143 (and 160..303 with GT_PIPE)
+#define GT_TM_DB (GT_PIPE ? 320 : 160)
+#define GT_NBUF (GT_PIPE ? 2 : 1)
 
 struct GtLayout {
     static constexpr int BB = 0;                                          // [64 n][144 k]      18 432
     static constexpr int DF = BB + (GT_VK / 8) * GT_BB_CHUNK;             // [128 m][128]       32 768 (cols 64.. zero)
-    static constexpr int V = DF + 16 * TC_CHUNK;                          // [128 m][144] bf16  36 864
+    static constexpr int V = DF + GT_NBUF * 16 * TC_CHUNK;                // [128 m][144] bf16  36 864
     static constexpr int DV = V + (GT_VK / 8) * GT_VCHUNK;                 // [128 m][148] fp32  75 776
     static constexpr int KNOTS = DV + TC_TM * GT_DVS * 4;
     static constexpr int YANG = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
-    static constexpr int COORD = YANG + TC_TM;                             // [128] float4: normalised r, polar, azimuth, flags
-    static constexpr int DSG = COORD + TC_TM * 16;                         // [128] d(sigma feature)
-    static constexpr int MBAR = DSG + TC_TM * 4;
+    static constexpr int COORD = YANG + GT_NBUF * TC_TM;                   // [128] float4: normalised r, polar, azimuth, flags
+    static constexpr int DSG = COORD + GT_NBUF * TC_TM * 16;               // [128] d(sigma feature)
+    static constexpr int MBAR = DSG + GT_NBUF * TC_TM * 4;
     static constexpr int TMEM = MBAR + 16;
     // GT_PREFETCH: inputs of the NEXT tile, fetched by cp.async while this tile is being scattered
     static constexpr int NXT_DF = TMEM + 16;                               // [128 m][28] d_feat rows   14 336
@@ -157,7 +161,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         const float* B = (n >> 5) ? basis1 : basis0;
         store_elem_h(bbs, n, kk, o < AD ? B[o * GT_VK + kk] : 0.f, GT_BB_CHUNK);
     }
-    for (int i = tid; i < 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < GT_NBUF * 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i <= k.knots_last; i += GT_THREADS) s_knots[i] = k.r_knots[i];
     fence_async_smem();
     tc_fence_before();
@@ -195,8 +199,112 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     gt_cp_wait();                                                // each thread's own copies have landed ...
     __syncthreads();                                             // ... and so have everybody else's
 #endif
+#if GT_PIPE
+    static_assert(GT_PREFETCH, "GT_PIPE stages the next tile from the cp.async staging buffers");
+    // Stage A of a tile (runs one tile AHEAD of its scatter phase): coordinates / d(sigma) / hemisphere into the tile's meta
+    // buffer mb, the fp16 dF2 operand into dF2 buffer mb (both from the cp.async staging area), then -- after the CTA barrier
+    // that the caller places -- MMA1 into the dV accumulator mb.
+    auto stage_a = [&](long long t, uint32_t mb) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        const long long gm = t * TC_TM + row;
+        if (gm < M) {
+            const float4 a = nx_df[row * (EGN_FEAT_STRIDE / 4) + 2 * q];
+            v[0] = a.x * scale; v[1] = a.y * scale; v[2] = a.z * scale; v[3] = a.w * scale;
+            if (q < 3) { const float4 b = nx_df[row * (EGN_FEAT_STRIDE / 4) + 2 * q + 1]; v[4] = b.x * scale; v[5] = b.y * scale; v[6] = b.z * scale; v[7] = b.w * scale; }
+        }
+        if (warp < 4) {
+            const int r = 32 * warp + lane;
+            const long long mg = t * TC_TM + r;
+            YYCoord cc;
+            cc.c[0] = cc.c[1] = cc.c[2] = -3.f;
+            cc.yang = 0;
+            float dsg = 0.f;
+            const bool glive = mg < M;
+            if (glive) {
+                if (k.coords != nullptr) {                           // saved by the fused forward (egn_fused.cu, phase 1b)
+                    const float4 sv = nx_co[r];
+                    cc.c[0] = sv.x; cc.c[1] = sv.y; cc.c[2] = sv.z; cc.yang = __float_as_int(sv.w);
+                } else {
+                    const long long ray = egn_ray_of(mg, k.S);
+                    const float z = zs[mg];
+                    const float* ry = rays + ray * 6;
+                    cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
+                }
+                dsg = nx_ds[r];
+            }
+            s_coord[mb * TC_TM + r] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang | (glive ? 2 : 0)));
+            s_dsg[mb * TC_TM + r] = dsg;
+            s_yang[mb * TC_TM + r] = (unsigned char)cc.yang;
+        }
+        int yang;
+        if (k.coords != nullptr) {                                   // the row's hemisphere straight from the staged record: no barrier
+            yang = (gm < M) ? (__float_as_int(nx_co[row].w) & 1) : 0;
+        } else {
+            __syncthreads();                                         // uniform branch: coordinates were computed by warps 0..3
+            yang = s_yang[mb * TC_TM + row];
+        }
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unsigned char* df = dfs + mb * 16 * TC_CHUNK;
+        store_chunk_h(df, 4 * yang + q, row, v);
+        store_chunk_h(df, 4 * (1 - yang) + q, row, zero);
+    };
+    auto issue_mma1 = [&](uint32_t mb) {                             // thread 0, after the barrier that follows stage_a
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)                              // K = 64 basis outputs (yin | yang)
+            tc_mma(tmem + GT_TM_DV + 160 * mb, desc_k(df_s + mb * 16 * TC_CHUNK + ks * 2 * TC_CHUNK), desc_mn(bb_s + ks * 256, GT_BB_CHUNK),
+                   IDESC_DV, ks > 0);
+        tc_commit(bar);
+    };
+    if ((long long)blockIdx.x < tiles) {
+        stage_a(blockIdx.x, 0);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        prefetch((long long)blockIdx.x + gridDim.x);
+        if (tid == 0) issue_mma1(0);
+    }
+#endif
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const uint32_t par = it & 1;
+#if GT_PIPE
+        const uint32_t mb = par;
+        const float4* cur_coord = s_coord + mb * TC_TM;
+        const float* cur_dsg = s_dsg + mb * TC_TM;
+        const uint32_t df_cur = df_s + mb * 16 * TC_CHUNK;
+        // ---- Ph2. dV rows of this tile (MMA1 was issued one tile ago) -> smem ----
+        ok &= mbar_wait(bar, par);
+        tc_fence_after();
+        {
+            uint32_t r[32], r4[4];
+            tmem_ld32(tmem_lane + GT_TM_DV + 160 * mb + 36 * q, r);
+            tmem_ld4(tmem_lane + GT_TM_DV + 160 * mb + 36 * q + 32, r4);
+            float4* dst = reinterpret_cast<float4*>(dvs + row * GT_DVS + 36 * q);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                dst[g] = make_float4(__uint_as_float(r[4 * g]) * inv_scale, __uint_as_float(r[4 * g + 1]) * inv_scale,
+                                     __uint_as_float(r[4 * g + 2]) * inv_scale, __uint_as_float(r[4 * g + 3]) * inv_scale);
+            dst[8] = make_float4(__uint_as_float(r4[0]) * inv_scale, __uint_as_float(r4[1]) * inv_scale, __uint_as_float(r4[2]) * inv_scale,
+                                 __uint_as_float(r4[3]) * inv_scale);
+        }
+        if (it > 0) ok &= mbar_wait(bar + 8, (it - 1) & 1);     // MMA2 of the previous tile has finished with its dF2 buffer and with V
+        gt_cp_wait();                                            // staged inputs of the next tile: own copies landed, the barrier covers the rest
+        tc_fence_before();
+        __syncthreads();
+        // ---- stage A of the NEXT tile, then its MMA1: both run behind this tile's scatter phase ----
+        const bool has_next = tile + gridDim.x < tiles;
+        if (has_next) stage_a(tile + gridDim.x, mb ^ 1);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        prefetch(tile + 2ll * gridDim.x);                       // staging consumed by everybody: refill it behind Ph3
+        if (has_next && tid == 0) issue_mma1(mb ^ 1);
+#else
+        const float4* cur_coord = s_coord;
+        const float* cur_dsg = s_dsg;
+        const uint32_t df_cur = df_s;
         // ---- Ph1a. this thread's 8 values of d_feat ----
         float v[8];
 #pragma unroll
@@ -293,6 +401,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         }
         tc_fence_before();
         __syncthreads();
+#endif
         // ---- Ph3. re-gather, local gradients, scatter, V rows ----
         // Ray coherence: the 8 samples of this warp are consecutive along one ray, so the angular plane (theta x phi) and
         // the theta / phi lines are hit at the same texels by (almost) all of them.  Their contributions are summed in
@@ -309,11 +418,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             // samples two apart, so the register cache below flushes less
             const int src = GT_CONSECUTIVE ? 4 * (lane >> 4) + itr : 2 * itr + (lane >> 4);              // sample within the warp's 8
             const int srow = 8 * warp + src;
-            const float4 sc = s_coord[srow];
+            const float4 sc = cur_coord[srow];
             const float c[3] = {sc.x, sc.y, sc.z};
             const int yang = __float_as_int(sc.w) & 1;
             const bool slive = (__float_as_int(sc.w) & 2) != 0;
-            const float dsig = s_dsg[srow];
+            const float dsig = cur_dsg[srow];
             unsigned j0[3], j1[3];
             float wa0[3], wa1[3];
 #pragma unroll
@@ -424,7 +533,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             const uint32_t first = it > 0 ? 1u : 0u;
 #pragma unroll
             for (int ks = 0; ks < TC_TM / 16; ++ks)
-                tc_mma(tmem + GT_TM_DB, desc_mn(df_s + ks * 256), desc_mn(v_s + ks * 256, GT_VCHUNK), IDESC_DB, first | (ks > 0));
+                tc_mma(tmem + GT_TM_DB, desc_mn(df_cur + ks * 256), desc_mn(v_s + ks * 256, GT_VCHUNK), IDESC_DB, first | (ks > 0));
             tc_commit(bar + 8);
         }
     }

@@ -20,7 +20,7 @@ opt = TableAdam(model, 0.02, 0.001, 0.1)
 rays = make_rays(16384, 'isotropic', seed=2000).to(dev)
 target = torch.rand(16384, 3, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-steps = 20
+steps = int(os.environ.get("EGN_QUICK_STEPS", 20))
 for i in range(steps + 3):
     if i == 3:
         ev[0].record()
