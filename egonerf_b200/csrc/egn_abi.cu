@@ -39,7 +39,7 @@ static int validate(const EgnConfig* c, bool need_schedule) {
     if (c->c_sigma != EGN_CS || c->c_app != EGN_CA)
         return fail("this build supports n_lamb_sigma=[%d]*3, n_lamb_sh=[%d]*3 (got %d, %d)", EGN_CS, EGN_CA, c->c_sigma, c->c_app);
     for (int a = 0; a < 3; ++a)
-        if (c->grid[a] < 4) return fail("grid[%d]=%d too small", a, c->grid[a]);
+        if (c->grid[a] < 4 || c->grid[a] > 65535) return fail("grid[%d]=%d outside [4, 65535]", a, c->grid[a]);
     if (c->grid[0] + 2 > EGN_MAX_KNOTS) return fail("N_r=%d exceeds %d", c->grid[0], EGN_MAX_KNOTS - 2);
     if (c->app_dim < 1 || c->app_dim > 27) return fail("app_dim=%d unsupported (1..27)", c->app_dim);
     if (c->shading < 0 || c->shading > 3) return fail("unknown shading %d", c->shading);

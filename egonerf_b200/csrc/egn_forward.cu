@@ -13,15 +13,11 @@
 // zeros padding, align_corners=True) written out as taps.  C = channels per texel of this table set,
 // `sub` = which float4 of the texel this lane owns.  All 18 loads are issued before any use.
 // -------------------------------------------------------------------------------------------------
-template <int C>
-__device__ __forceinline__ void egn_gather_products(const float* __restrict__ tab, const long long pofs[3],
-                                                    const long long lofs[3], const int G[3], const float c[3],
-                                                    int sub, float4 prod[3]) {
-    // per axis: clamped texel indices and tap weights with the zero padding folded in — an out-of-range tap gets
-    // weight 0 and reads a clamped in-range texel, so every load is unconditional (no predication, no divergence);
-    // the arithmetic on in-range taps is unchanged
-    unsigned j0[3], j1[3];
-    float wa0[3], wa1[3];
+// per axis: clamped texel indices and tap weights with the zero padding folded in — an out-of-range tap gets
+// weight 0 and reads a clamped in-range texel, so every load is unconditional (no predication, no divergence);
+// the arithmetic on in-range taps is unchanged
+struct EgnAxisTaps { unsigned j0[3], j1[3]; float wa0[3], wa1[3]; };
+__device__ __forceinline__ void egn_axis_taps(const int G[3], const float c[3], EgnAxisTaps& A) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float ix = egn_unnorm(c[a], G[a]);
@@ -29,38 +25,50 @@ __device__ __forceinline__ void egn_gather_products(const float* __restrict__ ta
         const float fr = ix - fl;
         // clamp before the int conversion so far-out-of-range samples stay "invalid" instead of wrapping
         const int i0 = (int)fminf(fmaxf(fl, -2.f), (float)G[a] + 1.f);
-        wa0[a] = ((i0 >= 0) & (i0 < G[a])) ? 1.f - fr : 0.f;
-        wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G[a])) ? fr : 0.f;
-        j0[a] = (unsigned)min(max(i0, 0), G[a] - 1);
-        j1[a] = (unsigned)min(max(i0 + 1, 0), G[a] - 1);
+        A.wa0[a] = ((i0 >= 0) & (i0 < G[a])) ? 1.f - fr : 0.f;
+        A.wa1[a] = ((i0 + 1 >= 0) & (i0 + 1 < G[a])) ? fr : 0.f;
+        A.j0[a] = (unsigned)min(max(i0, 0), G[a] - 1);
+        A.j1[a] = (unsigned)min(max(i0 + 1, 0), G[a] - 1);
     }
+}
+template <int C>
+__device__ __forceinline__ void egn_gather_taps(const float* __restrict__ tab, const long long pofs[3], const long long lofs[3],
+                                                const int G[3], const EgnAxisTaps& A, int sub, float4 prod[3]) {
     float4 t[3][4], l[3][2];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
         const unsigned W = (unsigned)G[ax];
         const unsigned pbase = (unsigned)pofs[i] + sub * 4, lbase = (unsigned)lofs[i] + sub * 4;
-        const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
-        t[i][0] = ldg4(tab + (size_t)(pbase + (ra + j0[ax]) * C));
-        t[i][1] = ldg4(tab + (size_t)(pbase + (ra + j1[ax]) * C));
-        t[i][2] = ldg4(tab + (size_t)(pbase + (rb + j0[ax]) * C));
-        t[i][3] = ldg4(tab + (size_t)(pbase + (rb + j1[ax]) * C));
-        l[i][0] = ldg4(tab + (size_t)(lbase + j0[al] * C));
-        l[i][1] = ldg4(tab + (size_t)(lbase + j1[al] * C));
+        const unsigned ra = A.j0[ay] * W, rb = A.j1[ay] * W;
+        t[i][0] = ldg4(tab + (size_t)(pbase + (ra + A.j0[ax]) * C));
+        t[i][1] = ldg4(tab + (size_t)(pbase + (ra + A.j1[ax]) * C));
+        t[i][2] = ldg4(tab + (size_t)(pbase + (rb + A.j0[ax]) * C));
+        t[i][3] = ldg4(tab + (size_t)(pbase + (rb + A.j1[ax]) * C));
+        l[i][0] = ldg4(tab + (size_t)(lbase + A.j0[al] * C));
+        l[i][1] = ldg4(tab + (size_t)(lbase + A.j1[al] * C));
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
         float4 P = f4zero();
-        P = f4fma(wa0[ax] * wa0[ay], t[i][0], P);
-        P = f4fma(wa1[ax] * wa0[ay], t[i][1], P);
-        P = f4fma(wa0[ax] * wa1[ay], t[i][2], P);
-        P = f4fma(wa1[ax] * wa1[ay], t[i][3], P);
+        P = f4fma(A.wa0[ax] * A.wa0[ay], t[i][0], P);
+        P = f4fma(A.wa1[ax] * A.wa0[ay], t[i][1], P);
+        P = f4fma(A.wa0[ax] * A.wa1[ay], t[i][2], P);
+        P = f4fma(A.wa1[ax] * A.wa1[ay], t[i][3], P);
         float4 Lv = f4zero();
-        Lv = f4fma(wa0[al], l[i][0], Lv);
-        Lv = f4fma(wa1[al], l[i][1], Lv);
+        Lv = f4fma(A.wa0[al], l[i][0], Lv);
+        Lv = f4fma(A.wa1[al], l[i][1], Lv);
         prod[i] = f4mul(P, Lv);
     }
+}
+template <int C>
+__device__ __forceinline__ void egn_gather_products(const float* __restrict__ tab, const long long pofs[3],
+                                                    const long long lofs[3], const int G[3], const float c[3],
+                                                    int sub, float4 prod[3]) {
+    EgnAxisTaps A;
+    egn_axis_taps(G, c, A);
+    egn_gather_taps<C>(tab, pofs, lofs, G, A, sub, prod);
 }
 
 // Bitonic sort of 32 * EF floats held EF per lane in blocked order (element index = lane * EF + e), ascending.
@@ -115,6 +123,9 @@ __device__ __forceinline__ float egn_aabb_entry(const EgnKernelCfg& k, float ox,
 #define K1_WARPS 8
 #define K1_MAXC 256
 
+#ifndef K1_SHARED_TAPS
+#define K1_SHARED_TAPS 1             // per-axis texel indices / tap weights computed by the sample's owner lane and shuffled (coarse grids < 65 536 texels per axis)
+#endif
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 2
 #endif
@@ -205,17 +216,38 @@ egn_coarse_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restric
             const int j = t * 32 + lane;
             const float z = (k.march && !is_train) ? zn[j] : zc[j];
             YYCoord cc = egn_cart_to_yinyang(ox + dx * z, oy + dy * z, oz + dz * z, k, s_knots, k.knots_last_c, k.r_div_c);
+#if K1_SHARED_TAPS
+            // texel indices / tap weights of the sample once, in its owner lane (the four lanes of a sample used to repeat
+            // this arithmetic); the two indices of an axis travel in one register
+            EgnAxisTaps mine;
+            egn_axis_taps(k.lay.Gc, cc.c, mine);
+            unsigned jj[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) jj[a] = mine.j0[a] | (mine.j1[a] << 16);
+#endif
             float myf = 0.f;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {         // 8 samples per pass, 4 lanes (one float4 each) per sample
                 const int src = p * 8 + (lane >> 2);
+                const int yang = __shfl_sync(FULL, cc.yang, src);
+                float4 prod[3];
+#if K1_SHARED_TAPS
+                EgnAxisTaps A;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const unsigned j = __shfl_sync(FULL, jj[a], src);
+                    A.j0[a] = j & 0xffffu; A.j1[a] = j >> 16;
+                    A.wa0[a] = __shfl_sync(FULL, mine.wa0[a], src);
+                    A.wa1[a] = __shfl_sync(FULL, mine.wa1[a], src);
+                }
+                egn_gather_taps<EGN_CS>(k.tables, k.lay.pc[yang], k.lay.lc[yang], k.lay.Gc, A, lane & 3, prod);
+#else
                 float c[3];
                 c[0] = __shfl_sync(FULL, cc.c[0], src);
                 c[1] = __shfl_sync(FULL, cc.c[1], src);
                 c[2] = __shfl_sync(FULL, cc.c[2], src);
-                const int yang = __shfl_sync(FULL, cc.yang, src);
-                float4 prod[3];
                 egn_gather_products<EGN_CS>(k.tables, k.lay.pc[yang], k.lay.lc[yang], k.lay.Gc, c, lane & 3, prod);
+#endif
                 float f = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {

@@ -60,21 +60,86 @@ __device__ __forceinline__ void gt_cp4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void gt_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gt_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ void gt_red4(float* addr, float4 v) { atomicAdd(reinterpret_cast<float4*>(addr), v); }
+#ifndef GT_DIAG
+#define GT_DIAG 0                    // timing diagnostics only (WRONG gradients): 1 = no reductions for the (r, angle) planes, 2 = no reductions at all
+#endif
+__device__ __forceinline__ void gt_red4(float* addr, float4 v) {
+#if GT_DIAG < 2
+    atomicAdd(reinterpret_cast<float4*>(addr), v);
+#endif
+}
+#ifndef GT_FFMA2
+#define GT_FFMA2 0                   // 1: Ph3 arithmetic with the packed fp32 instructions of sm_100 (FFMA2 / FMUL2; same roundings) -- measured 6.915 vs 6.912 ms per step: off
+#endif
+#if GT_FFMA2
+__device__ __forceinline__ unsigned long long gt_pk(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void gt_unpk(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ float4 gt_fma4(float w, float4 a, float4 acc) {
+    const unsigned long long ww = gt_pk(w, w);
+    unsigned long long lo, hi;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(lo) : "l"(ww), "l"(gt_pk(a.x, a.y)), "l"(gt_pk(acc.x, acc.y)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(hi) : "l"(ww), "l"(gt_pk(a.z, a.w)), "l"(gt_pk(acc.z, acc.w)));
+    float4 r;
+    gt_unpk(lo, r.x, r.y); gt_unpk(hi, r.z, r.w);
+    return r;
+}
+__device__ __forceinline__ float4 gt_mul4(float4 a, float4 b) {
+    unsigned long long lo, hi;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(lo) : "l"(gt_pk(a.x, a.y)), "l"(gt_pk(b.x, b.y)));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hi) : "l"(gt_pk(a.z, a.w)), "l"(gt_pk(b.z, b.w)));
+    float4 r;
+    gt_unpk(lo, r.x, r.y); gt_unpk(hi, r.z, r.w);
+    return r;
+}
+__device__ __forceinline__ float4 gt_scale(float s, float4 a) { return gt_mul4(make_float4(s, s, s, s), a); }
+#else
+__device__ __forceinline__ float4 gt_fma4(float w, float4 a, float4 acc) { return f4fma(w, a, acc); }
+__device__ __forceinline__ float4 gt_mul4(float4 a, float4 b) { return f4mul(a, b); }
 __device__ __forceinline__ float4 gt_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+#endif
 
 // register cache of the angular-tap gradients of one half-warp (see Ph3)
 #ifndef GT_LINES_CACHED
 #define GT_LINES_CACHED 2            // 2: phi / theta lines; 3: the r line too (10 more registers)
 #endif
+#ifndef GT_TAP_DEPTH
+#define GT_TAP_DEPTH 3               // factor pairs of taps in flight per half-warp (3 = all 18 taps up front; 2 frees no registers in practice)
+#endif
+#ifndef GT_SHIFT
+#define GT_SHIFT 0                   // 1: the (r, angle) planes and the r line keep the contributions of their j1 column / tap pending for one sample: along
+#endif                               //    a ray r advances about one texel per sample, so the next sample's j0 column is that very column (4 -> 2 and 2 -> 1
+                                     //    reductions).  Correct (gradient tests green) but 25 more registers at the 128 cap: 104 B of spills in the scatter loop and
+                                     //    half-warp-divergent flushes -- measured 8.18 vs 6.90 ms per training step: off (profiles/r02_backward.md)
 struct GtCache {
     unsigned po[4], lo[GT_LINES_CACHED][2];        // element offsets of the cached taps (0xffffffff = empty)
     float4 pa[4], la[GT_LINES_CACHED][2];
+#if GT_SHIFT
+    unsigned so[2][2], ro;                          // pending j1 column (rows a, b) of planes 0 / 1; pending j1 tap of the r line
+    float4 sa[2][2], ra;
+    __device__ __forceinline__ void flush_shift(float* d_tab, int i) {
+        if (so[i][0] != 0xffffffffu) {
+            if (nz(sa[i][0])) gt_red4(d_tab + so[i][0], sa[i][0]);
+            if (nz(sa[i][1])) gt_red4(d_tab + so[i][1], sa[i][1]);
+        }
+    }
+    __device__ __forceinline__ void flush_rline(float* d_tab) {
+        if (ro != 0xffffffffu && nz(ra)) gt_red4(d_tab + ro, ra);
+    }
+#endif
     __device__ __forceinline__ void reset() {
 #pragma unroll
         for (int t = 0; t < 4; ++t) { po[t] = 0xffffffffu; pa[t] = f4zero(); }
 #pragma unroll
         for (int i = 0; i < GT_LINES_CACHED; ++i) { lo[i][0] = lo[i][1] = 0xffffffffu; la[i][0] = la[i][1] = f4zero(); }
+#if GT_SHIFT
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { so[i][0] = so[i][1] = 0xffffffffu; sa[i][0] = sa[i][1] = f4zero(); }
+        ro = 0xffffffffu; ra = f4zero();
+#endif
     }
     __device__ __forceinline__ static bool nz(const float4& v) { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); }
     __device__ __forceinline__ void flush_plane(float* d_tab) {
@@ -439,18 +504,21 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             }
             // bf16 tables: all 18 taps of the sample are requested before the first one is used (8 B per lane and tap stay
             // packed until then) -- three times the loads in flight of a per-factor-pair loop
-            uint2 raw[BF16 ? 3 : 1][6];
+            // (GT_TAP_DEPTH 2: the third factor pair is requested as soon as the first one has been widened -- 12 registers
+            // less for the pending-column caches of GT_SHIFT)
+            uint2 raw[BF16 ? GT_TAP_DEPTH : 1][6];
+            auto request = [&](int i, uint2 (&dst)[6]) {
+                const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
+                const unsigned W = (unsigned)k.lay.G[ax];
+                const unsigned pbase = (unsigned)k.lay.pf[yang][i] + sub * 4, lbase = (unsigned)k.lay.lf[yang][i] + sub * 4;
+                const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
+                dst[0] = gt_raw(k, pbase + (ra + j0[ax]) * EGN_CF); dst[1] = gt_raw(k, pbase + (ra + j1[ax]) * EGN_CF);
+                dst[2] = gt_raw(k, pbase + (rb + j0[ax]) * EGN_CF); dst[3] = gt_raw(k, pbase + (rb + j1[ax]) * EGN_CF);
+                dst[4] = gt_raw(k, lbase + j0[al] * EGN_CF); dst[5] = gt_raw(k, lbase + j1[al] * EGN_CF);
+            };
             if constexpr (BF16) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int ax = egn_mx(i), ay = egn_my(i), al = egn_vl(i);
-                    const unsigned W = (unsigned)k.lay.G[ax];
-                    const unsigned pbase = (unsigned)k.lay.pf[yang][i] + sub * 4, lbase = (unsigned)k.lay.lf[yang][i] + sub * 4;
-                    const unsigned ra = j0[ay] * W, rb = j1[ay] * W;
-                    raw[i][0] = gt_raw(k, pbase + (ra + j0[ax]) * EGN_CF); raw[i][1] = gt_raw(k, pbase + (ra + j1[ax]) * EGN_CF);
-                    raw[i][2] = gt_raw(k, pbase + (rb + j0[ax]) * EGN_CF); raw[i][3] = gt_raw(k, pbase + (rb + j1[ax]) * EGN_CF);
-                    raw[i][4] = gt_raw(k, lbase + j0[al] * EGN_CF); raw[i][5] = gt_raw(k, lbase + j1[al] * EGN_CF);
-                }
+                for (int i = 0; i < GT_TAP_DEPTH; ++i) request(i, raw[i]);
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -463,8 +531,10 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 const unsigned q0 = lbase + j0[al] * EGN_CF, q1 = lbase + j1[al] * EGN_CF;
                 float4 t0, t1, t2, t3, l0, l1;
                 if constexpr (BF16) {
-                    t0 = gt_widen(raw[i][0]); t1 = gt_widen(raw[i][1]); t2 = gt_widen(raw[i][2]); t3 = gt_widen(raw[i][3]);
-                    l0 = gt_widen(raw[i][4]); l1 = gt_widen(raw[i][5]);
+                    uint2 (&rw)[6] = raw[i % GT_TAP_DEPTH];
+                    t0 = gt_widen(rw[0]); t1 = gt_widen(rw[1]); t2 = gt_widen(rw[2]); t3 = gt_widen(rw[3]);
+                    l0 = gt_widen(rw[4]); l1 = gt_widen(rw[5]);
+                    if (i + GT_TAP_DEPTH < 3) request(i + GT_TAP_DEPTH, rw);
                 } else {
                     t0 = gt_tap<BF16>(k, o0); t1 = gt_tap<BF16>(k, o1); t2 = gt_tap<BF16>(k, o2); t3 = gt_tap<BF16>(k, o3);
                     l0 = gt_tap<BF16>(k, q0); l1 = gt_tap<BF16>(k, q1);
@@ -472,10 +542,10 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 const float w0 = wa0[ax] * wa0[ay], w1 = wa1[ax] * wa0[ay], w2 = wa0[ax] * wa1[ay], w3 = wa1[ax] * wa1[ay];
                 const float u0 = wa0[al], u1 = wa1[al];
                 float4 P = f4zero();
-                P = f4fma(w0, t0, P); P = f4fma(w1, t1, P); P = f4fma(w2, t2, P); P = f4fma(w3, t3, P);
+                P = gt_fma4(w0, t0, P); P = gt_fma4(w1, t1, P); P = gt_fma4(w2, t2, P); P = gt_fma4(w3, t3, P);
                 float4 Lv = f4zero();
-                Lv = f4fma(u0, l0, Lv); Lv = f4fma(u1, l1, Lv);
-                const float4 prod = f4mul(P, Lv);
+                Lv = gt_fma4(u0, l0, Lv); Lv = gt_fma4(u1, l1, Lv);
+                const float4 prod = gt_mul4(P, Lv);
                 float s = hsum4(prod);                          // density lanes: relu mask of this product (EgoNeRF.py:346)
                 s += __shfl_xor_sync(FULL, s, 1);
                 s += __shfl_xor_sync(FULL, s, 2);
@@ -490,30 +560,64 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                         make_uint2(pack_h2(prod.x, prod.y), pack_h2(prod.z, prod.w));
                 }
                 if (slive) {
-                    const float4 dP = f4mul(up, Lv), dL = f4mul(up, P);
+                    const float4 dP = gt_mul4(up, Lv), dL = gt_mul4(up, P);
                     if (i == 2) {                                   // angular plane: cached
                         if (cache.po[0] != o0 || cache.po[3] != o3) {
                             cache.flush_plane(d_tab);
                             cache.po[0] = o0; cache.po[1] = o1; cache.po[2] = o2; cache.po[3] = o3;
                         }
-                        cache.pa[0] = f4fma(w0, dP, cache.pa[0]); cache.pa[1] = f4fma(w1, dP, cache.pa[1]);
-                        cache.pa[2] = f4fma(w2, dP, cache.pa[2]); cache.pa[3] = f4fma(w3, dP, cache.pa[3]);
-                    } else {
+                        cache.pa[0] = gt_fma4(w0, dP, cache.pa[0]); cache.pa[1] = gt_fma4(w1, dP, cache.pa[1]);
+                        cache.pa[2] = gt_fma4(w2, dP, cache.pa[2]); cache.pa[3] = gt_fma4(w3, dP, cache.pa[3]);
+                    } else if (GT_DIAG == 0) {
+#if GT_SHIFT
+                        // planes (r, theta) / (r, phi): column j0 = taps 0, 2; column j1 = taps 1, 3 (r is the fast axis)
+                        float4 c0 = gt_scale(w0, dP), c2 = gt_scale(w2, dP);
+                        const float4 c1 = gt_scale(w1, dP), c3 = gt_scale(w3, dP);
+                        const bool shift = cache.so[i][0] == o0 && cache.so[i][1] == o2;      // pending column is this sample's j0 column
+                        const bool same = cache.so[i][0] == o1 && cache.so[i][1] == o3;       // r did not advance: pending column is the j1 column again
+                        if (shift) {
+                            c0.x += cache.sa[i][0].x; c0.y += cache.sa[i][0].y; c0.z += cache.sa[i][0].z; c0.w += cache.sa[i][0].w;
+                            c2.x += cache.sa[i][1].x; c2.y += cache.sa[i][1].y; c2.z += cache.sa[i][1].z; c2.w += cache.sa[i][1].w;
+                        } else if (!same) {
+                            cache.flush_shift(d_tab, i);
+                        }
+                        if (GtCache::nz(c0)) gt_red4(d_tab + o0, c0);
+                        if (GtCache::nz(c2)) gt_red4(d_tab + o2, c2);
+                        if (same) {
+                            cache.sa[i][0].x += c1.x; cache.sa[i][0].y += c1.y; cache.sa[i][0].z += c1.z; cache.sa[i][0].w += c1.w;
+                            cache.sa[i][1].x += c3.x; cache.sa[i][1].y += c3.y; cache.sa[i][1].z += c3.z; cache.sa[i][1].w += c3.w;
+                        } else {
+                            cache.so[i][0] = o1; cache.so[i][1] = o3;
+                            cache.sa[i][0] = c1; cache.sa[i][1] = c3;
+                        }
+#else
                         if (w0 != 0.f) gt_red4(d_tab + o0, gt_scale(w0, dP));
                         if (w1 != 0.f) gt_red4(d_tab + o1, gt_scale(w1, dP));
                         if (w2 != 0.f) gt_red4(d_tab + o2, gt_scale(w2, dP));
                         if (w3 != 0.f) gt_red4(d_tab + o3, gt_scale(w3, dP));
+#endif
                     }
                     if (i < GT_LINES_CACHED) {                      // phi / theta (/ r) lines: cached
                         if (cache.lo[i][0] != q0 || cache.lo[i][1] != q1) {
                             cache.flush_line(d_tab, i);
                             cache.lo[i][0] = q0; cache.lo[i][1] = q1;
                         }
-                        cache.la[i][0] = f4fma(u0, dL, cache.la[i][0]);
-                        cache.la[i][1] = f4fma(u1, dL, cache.la[i][1]);
+                        cache.la[i][0] = gt_fma4(u0, dL, cache.la[i][0]);
+                        cache.la[i][1] = gt_fma4(u1, dL, cache.la[i][1]);
                     } else {
+#if GT_SHIFT
+                        float4 d0 = gt_scale(u0, dL);
+                        const float4 d1 = gt_scale(u1, dL);
+                        const bool shift = cache.ro == q0, same = cache.ro == q1;
+                        if (shift) { d0.x += cache.ra.x; d0.y += cache.ra.y; d0.z += cache.ra.z; d0.w += cache.ra.w; }
+                        else if (!same) cache.flush_rline(d_tab);
+                        if (GtCache::nz(d0)) gt_red4(d_tab + q0, d0);
+                        if (same) { cache.ra.x += d1.x; cache.ra.y += d1.y; cache.ra.z += d1.z; cache.ra.w += d1.w; }
+                        else { cache.ro = q1; cache.ra = d1; }
+#else
                         if (u0 != 0.f) gt_red4(d_tab + q0, gt_scale(u0, dL));
                         if (u1 != 0.f) gt_red4(d_tab + q1, gt_scale(u1, dL));
+#endif
                     }
                 }
             }
@@ -521,6 +625,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         cache.flush_plane(d_tab);
 #pragma unroll
         for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_tab, i);
+#if GT_SHIFT
+        cache.flush_shift(d_tab, 0);
+        cache.flush_shift(d_tab, 1);
+        cache.flush_rline(d_tab);
+#endif
 #if GT_PREFETCH
         gt_cp_wait();                                            // next tile's inputs: own copies landed; the barrier below covers the rest
 #endif
