@@ -61,10 +61,11 @@ __device__ __forceinline__ void gt_cp_commit() { asm volatile("cp.async.commit_g
 __device__ __forceinline__ void gt_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #ifndef GT_DIAG
-#define GT_DIAG 0                    // timing diagnostics only (WRONG gradients): 1 = no reductions for the (r, angle) planes, 2 = no reductions at all
+#define GT_DIAG 0                    // timing diagnostics only (WRONG gradients): 1 = no reductions for the (r, angle) planes, 2 = no reductions at all,
+                                     // 3 = no reductions for the three lines, 4 = none for the r line only
 #endif
 __device__ __forceinline__ void gt_red4(float* addr, float4 v) {
-#if GT_DIAG < 2
+#if GT_DIAG != 2
     atomicAdd(reinterpret_cast<float4*>(addr), v);
 #endif
 }
@@ -150,8 +151,8 @@ struct GtCache {
     }
     __device__ __forceinline__ void flush_line(float* d_tab, int i) {
         if (lo[i][0] != 0xffffffffu) {
-            if (nz(la[i][0])) gt_red4(d_tab + lo[i][0], la[i][0]);
-            if (nz(la[i][1])) gt_red4(d_tab + lo[i][1], la[i][1]);
+            if (GT_DIAG != 3 && nz(la[i][0])) gt_red4(d_tab + lo[i][0], la[i][0]);
+            if (GT_DIAG != 3 && nz(la[i][1])) gt_red4(d_tab + lo[i][1], la[i][1]);
             la[i][0] = la[i][1] = f4zero();
         }
     }
@@ -189,13 +190,49 @@ __device__ __forceinline__ float4 gt_widen(const uint2& q) {
                        __uint_as_float(q.y & 0xffff0000u));
 }
 
+// compact layout of one private copy of the line gradients: hemisphere-major, then factor pair i (line axis egn_vl(i))
+__host__ __device__ __forceinline__ long long gt_line_floats(const int G[3]) { return 2ll * (G[0] + G[1] + G[2]) * EGN_CF; }
+__host__ __device__ __forceinline__ unsigned gt_line_base(const int G[3], int yang, int i) {
+    unsigned t = yang * (unsigned)(G[0] + G[1] + G[2]);
+    for (int j = 0; j < i; ++j) t += (unsigned)G[egn_vl(j)];
+    return t * EGN_CF;
+}
+
+// table[line sections] += sum over the private copies (runs behind the gather backward on the same stream)
+__global__ void __launch_bounds__(256)
+egn_line_fold_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ priv, int copies, float* __restrict__ d_tab) {
+    const long long LF = gt_line_floats(k.lay.G);
+    for (long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e4 < LF / 4; e4 += (long long)gridDim.x * blockDim.x) {
+        float4 s = f4zero();
+        for (int c = 0; c < copies; ++c) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(priv + c * LF) + e4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        // compact element -> (hemisphere, factor pair, texel, channel) -> table offset
+        long long e = e4 * 4;
+        const long long per_h = LF / 2;
+        const int h = e >= per_h;
+        e -= h * per_h;
+        int i = 0;
+        for (; i < 2; ++i) {
+            const long long n = (long long)k.lay.G[egn_vl(i)] * EGN_CF;
+            if (e < n) break;
+            e -= n;
+        }
+        float4* dst = reinterpret_cast<float4*>(d_tab + k.lay.lf[h][i] + e);
+        float4 o = *dst;
+        o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+        *dst = o;
+    }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
                          const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
                          const float* __restrict__ zs, const float* __restrict__ d_fsig, const float* __restrict__ d_feat,
                          const unsigned* __restrict__ gmax_bits, float* __restrict__ d_tab, float* __restrict__ d_basis0,
-                         float* __restrict__ d_basis1) {
+                         float* __restrict__ d_basis1, float* __restrict__ d_line_priv, int line_copies) {
     using L = GtLayout;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp-uniform
@@ -236,6 +273,10 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bb_s = smem_u32(bbs), df_s = smem_u32(dfs), v_s = smem_u32(vs);
     const int sub = lane & 15;
+    // Line gradients: the three lines of a hemisphere have 838 texels at 300^3 and every sample of every SM reduces into them.
+    // With d_line_priv (GT_LINE_COPIES > 0; measured, off) the CTA reduces into its own compact copy [2 hemispheres][phi | theta | r lines][64] (copy = CTA mod
+    // line_copies); egn_line_fold_kernel adds the copies to the table afterwards.
+    float* const d_lin = d_line_priv ? d_line_priv + (size_t)(blockIdx.x % line_copies) * gt_line_floats(k.lay.G) : d_tab;
     float inv_scale;
     const float scale = tc_grad_scale(gmax_bits, inv_scale);
 
@@ -529,6 +570,9 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 const unsigned o0 = pbase + (ra + j0[ax]) * EGN_CF, o1 = pbase + (ra + j1[ax]) * EGN_CF;
                 const unsigned o2 = pbase + (rb + j0[ax]) * EGN_CF, o3 = pbase + (rb + j1[ax]) * EGN_CF;
                 const unsigned q0 = lbase + j0[al] * EGN_CF, q1 = lbase + j1[al] * EGN_CF;
+                // where the line gradient goes: the table itself, or the CTA's private compact copy
+                const unsigned lred = d_line_priv ? gt_line_base(k.lay.G, yang, i) + sub * 4 : lbase;
+                const unsigned qr0 = lred + j0[al] * EGN_CF, qr1 = lred + j1[al] * EGN_CF;
                 float4 t0, t1, t2, t3, l0, l1;
                 if constexpr (BF16) {
                     uint2 (&rw)[6] = raw[i % GT_TAP_DEPTH];
@@ -568,7 +612,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                         }
                         cache.pa[0] = gt_fma4(w0, dP, cache.pa[0]); cache.pa[1] = gt_fma4(w1, dP, cache.pa[1]);
                         cache.pa[2] = gt_fma4(w2, dP, cache.pa[2]); cache.pa[3] = gt_fma4(w3, dP, cache.pa[3]);
-                    } else if (GT_DIAG == 0) {
+                    } else if (GT_DIAG != 1) {
 #if GT_SHIFT
                         // planes (r, theta) / (r, phi): column j0 = taps 0, 2; column j1 = taps 1, 3 (r is the fast axis)
                         float4 c0 = gt_scale(w0, dP), c2 = gt_scale(w2, dP);
@@ -598,9 +642,9 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 #endif
                     }
                     if (i < GT_LINES_CACHED) {                      // phi / theta (/ r) lines: cached
-                        if (cache.lo[i][0] != q0 || cache.lo[i][1] != q1) {
-                            cache.flush_line(d_tab, i);
-                            cache.lo[i][0] = q0; cache.lo[i][1] = q1;
+                        if (cache.lo[i][0] != qr0 || cache.lo[i][1] != qr1) {
+                            cache.flush_line(d_lin, i);
+                            cache.lo[i][0] = qr0; cache.lo[i][1] = qr1;
                         }
                         cache.la[i][0] = gt_fma4(u0, dL, cache.la[i][0]);
                         cache.la[i][1] = gt_fma4(u1, dL, cache.la[i][1]);
@@ -608,15 +652,15 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 #if GT_SHIFT
                         float4 d0 = gt_scale(u0, dL);
                         const float4 d1 = gt_scale(u1, dL);
-                        const bool shift = cache.ro == q0, same = cache.ro == q1;
+                        const bool shift = cache.ro == qr0, same = cache.ro == qr1;
                         if (shift) { d0.x += cache.ra.x; d0.y += cache.ra.y; d0.z += cache.ra.z; d0.w += cache.ra.w; }
-                        else if (!same) cache.flush_rline(d_tab);
-                        if (GtCache::nz(d0)) gt_red4(d_tab + q0, d0);
+                        else if (!same) cache.flush_rline(d_lin);
+                        if (GtCache::nz(d0)) gt_red4(d_lin + qr0, d0);
                         if (same) { cache.ra.x += d1.x; cache.ra.y += d1.y; cache.ra.z += d1.z; cache.ra.w += d1.w; }
-                        else { cache.ro = q1; cache.ra = d1; }
+                        else { cache.ro = qr1; cache.ra = d1; }
 #else
-                        if (u0 != 0.f) gt_red4(d_tab + q0, gt_scale(u0, dL));
-                        if (u1 != 0.f) gt_red4(d_tab + q1, gt_scale(u1, dL));
+                        if (GT_DIAG != 3 && GT_DIAG != 4 && u0 != 0.f) gt_red4(d_lin + qr0, gt_scale(u0, dL));
+                        if (GT_DIAG != 3 && GT_DIAG != 4 && u1 != 0.f) gt_red4(d_lin + qr1, gt_scale(u1, dL));
 #endif
                     }
                 }
@@ -624,11 +668,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         }
         cache.flush_plane(d_tab);
 #pragma unroll
-        for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_tab, i);
+        for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_lin, i);
 #if GT_SHIFT
         cache.flush_shift(d_tab, 0);
         cache.flush_shift(d_tab, 1);
-        cache.flush_rline(d_tab);
+        cache.flush_rline(d_lin);
 #endif
 #if GT_PREFETCH
         gt_cp_wait();                                            // next tile's inputs: own copies landed; the barrier below covers the rest
@@ -668,21 +712,37 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
 }
 
+#ifndef GT_LINE_COPIES
+#define GT_LINE_COPIES 0             // private per-CTA copies of the line gradients + a fold kernel (0 = reduce into the table directly).  Measured
+                                     // 6.876 (0) / 6.890 (8) / 6.907 (32) / 6.939 ms (148 copies) per training step: contention on the 838 line texels is
+                                     // not what makes the reductions expensive; off (profiles/r02_backward.md)
+#endif
+long long egn_gather_bwd_tc_scratch_floats(const int grid[3]) { return (long long)GT_LINE_COPIES * gt_line_floats(grid); }
+
 int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* d_fsig, const float* d_feat, const unsigned* gmax_bits, float* d_tables, const EgnGrads* g,
-                             cudaStream_t st) {
+                             float* line_scratch, cudaStream_t st) {
     const long long M = n * k.S;
     if (M <= 0) return 0;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     const int blocks = (int)(tiles < 148 ? tiles : 148);
+    const int copies = (line_scratch != nullptr && GT_LINE_COPIES > 0) ? (blocks < GT_LINE_COPIES ? blocks : GT_LINE_COPIES) : 0;
+    float* priv = copies > 0 ? line_scratch : nullptr;
+    if (priv) {
+        cudaError_t e = cudaMemsetAsync(priv, 0, (size_t)copies * gt_line_floats(k.lay.G) * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (k.tables_bf16 != nullptr) {
         cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
         egn_gather_bwd_tc_kernel<true><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
-                                                                                     d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1]);
+                                                                                     d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1],
+                                                                                     priv, copies);
     } else {
         cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
         egn_gather_bwd_tc_kernel<false><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
-                                                                                      d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1]);
+                                                                                      d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1],
+                                                                                      priv, copies);
     }
+    if (priv) egn_line_fold_kernel<<<148, 256, 0, st>>>(k, priv, copies, d_tables);
     return (int)cudaGetLastError();
 }
