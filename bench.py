@@ -146,7 +146,7 @@ def cpu_baseline_record(rps, repeats):
                       f"({os.cpu_count()} threads); identical leg in-line and under --impl reference"}
 
 
-FACT_SOURCES = ("egn_fused.cu", "egn_tc.cuh", "egn_shared.cuh", "egn_device.cuh", "egn_host.h")
+FACT_SOURCES = ("egn_fused.cu", "egn_tc.cuh", "egn_shared.cuh", "egn_device.cuh")
 
 
 def source_sha():
