@@ -67,7 +67,7 @@ class TableAdam:
         self._n_head = (self._n_tables + 3) // 4 * 4
         try:
             self.peer = PeerExchange(self._n_head + int(tail_floats), self._device(), group, blocks)
-        except RuntimeError as e:
+        except Exception as e:                       # raised on every rank alike (PeerExchange agrees on failure collectively)
             import warnings
             warnings.warn(f"egonerf_b200: {e}; gradient exchange stays on NCCL")
             self.peer = None
