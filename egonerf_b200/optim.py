@@ -81,6 +81,10 @@ class TableAdam:
         """Collective: back to the NCCL path; unmaps and frees the peer buffers."""
         if self.peer is not None:
             self.d_tables = None
+            bucket = getattr(self.model, "_bucket", None)
+            if bucket is not None and bucket.external:           # .grad views into the buffer that is about to be freed
+                for p in bucket.params:
+                    p.grad = None
             self.peer_head = self.peer_tail = None
             self.peer.close()
             self.peer = None
