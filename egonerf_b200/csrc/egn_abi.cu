@@ -187,7 +187,7 @@ extern "C" int32_t egn_regularize_tables(const EgnConfig* c, const float* tables
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 // backward processes the MLP in sub-chunks of this many rays so that its M x 128 scratch stays bounded
 #define EGN_BWD_SUB_RAYS 4096
-struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, coord, d_rgbs, d_fsig, d_feat, gmax, h1, h2, dz1, dz2, lines, eval_total, total; };
+struct WsPlan { long long z, image, fsig, rgbs, wgt, bgw, rgbpre, feat, coord, d_rgbs, d_fsig, d_feat, gmax, h1, h2, dz1, dz2, eval_total, total; };
 // the fused fine pass keeps the r ladder in shared memory (EGN_FUSED_MAX_KNOTS entries); larger grids take the unfused kernels
 static bool is_fused(const EgnConfig* c) {
     return c->shading == EGN_SHADE_MLP_FEA && c->mlp_mode == EGN_MLP_TC_F16 && c->grid[0] + 3 <= EGN_FUSED_MAX_KNOTS;
@@ -215,8 +215,6 @@ static WsPlan plan_ws(const EgnConfig* c, long long n) {
     const long long Ms = (n < EGN_BWD_SUB_RAYS ? n : EGN_BWD_SUB_RAYS) * S;
     w.h1 = take(mlp ? Ms * EGN_HID : 0); w.h2 = take(mlp ? Ms * EGN_HID : 0);
     w.dz1 = take(mlp ? Ms * EGN_HID : 0); w.dz2 = take(mlp ? Ms * EGN_HID : 0);
-    // private copies of the line gradients of the tcgen05 gather backward (egn_gather_bwd_tc.cu)
-    w.lines = take(tc_backward(c) ? egn_gather_bwd_tc_scratch_floats(c->grid) : 0);
     w.total = off;
     return w;
 }
@@ -406,7 +404,7 @@ extern "C" int32_t egn_render_backward_sparse_env(const EgnConfig* c, const EgnP
     }
     if (tc_backward(c)) {
         if (is_fused(c)) k.coords = (float*)(base + w.coord);          // written by the forward of this very workspace
-        e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, gmax, d_tables, g, (float*)(base + w.lines), st);
+        e = egn_launch_gather_bwd_tc(k, p, rays, n, z, d_fsig, d_feat, gmax, d_tables, g, st);
     }
     else
         e = egn_launch_gather_bwd(k, p, rays, n, z, d_fsig, d_feat, d_tables, g, st);

@@ -22,23 +22,21 @@
 #define GT_VCHUNK (TC_CHUNK + 64)          // padded K-chunk stride of the V tile (bank-conflict-free row stores, see egn_fused.cu)
 #define IDESC_DV TC_IDESC_F16(0x08250490u)               // M128 N144, A K-major, B MN-major
 #define IDESC_DB TC_IDESC_F16(0x08258490u)               // M128 N144, A MN-major, B MN-major
-#ifndef GT_PIPE
-#define GT_PIPE 0                    // 1: dF2 / MMA1 of tile t+1 are staged BEFORE the scatter phase of tile t (two dF2 tiles, two dV accumulators in TMEM):
-#endif                               //    no MMA wait is exposed and a tile takes three CTA barriers instead of four (needs GT_PREFETCH)
-#define GT_TM_DV 0                   // dV accumulator(s): columns 0..143 (and 160..303 with GT_PIPE)
-#define GT_TM_DB (GT_PIPE ? 320 : 160)
-#define GT_NBUF (GT_PIPE ? 2 : 1)
+// (Staging dF2 / MMA1 of tile t+1 before the scatter phase of tile t -- two dF2 tiles, two dV accumulators -- was built and
+// measured at 6.91 vs 6.90 ms per training step: the barriers do not wait for the MMAs.  Removed; commit a1a3ea4 has it.)
+#define GT_TM_DV 0                   // dV accumulator: columns 0..143
+#define GT_TM_DB 160
 
 struct GtLayout {
     static constexpr int BB = 0;                                          // [64 n][144 k]      18 432
     static constexpr int DF = BB + (GT_VK / 8) * GT_BB_CHUNK;             // [128 m][128]       32 768 (cols 64.. zero)
-    static constexpr int V = DF + GT_NBUF * 16 * TC_CHUNK;                // [128 m][144] bf16  36 864
+    static constexpr int V = DF + 16 * TC_CHUNK;                // [128 m][144] bf16  36 864
     static constexpr int DV = V + (GT_VK / 8) * GT_VCHUNK;                 // [128 m][148] fp32  75 776
     static constexpr int KNOTS = DV + TC_TM * GT_DVS * 4;
     static constexpr int YANG = KNOTS + ((EGN_MAX_KNOTS + 1) * 4 + 15) / 16 * 16;
-    static constexpr int COORD = YANG + GT_NBUF * TC_TM;                   // [128] float4: normalised r, polar, azimuth, flags
-    static constexpr int DSG = COORD + GT_NBUF * TC_TM * 16;               // [128] d(sigma feature)
-    static constexpr int MBAR = DSG + GT_NBUF * TC_TM * 4;
+    static constexpr int COORD = YANG + TC_TM;                   // [128] float4: normalised r, polar, azimuth, flags
+    static constexpr int DSG = COORD + TC_TM * 16;               // [128] d(sigma feature)
+    static constexpr int MBAR = DSG + TC_TM * 4;
     static constexpr int TMEM = MBAR + 16;
     // GT_PREFETCH: inputs of the NEXT tile, fetched by cp.async while this tile is being scattered
     static constexpr int NXT_DF = TMEM + 16;                               // [128 m][28] d_feat rows   14 336
@@ -61,11 +59,10 @@ __device__ __forceinline__ void gt_cp_commit() { asm volatile("cp.async.commit_g
 __device__ __forceinline__ void gt_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #ifndef GT_DIAG
-#define GT_DIAG 0                    // timing diagnostics only (WRONG gradients): 1 = no reductions for the (r, angle) planes, 2 = no reductions at all,
-                                     // 3 = no reductions for the three lines, 4 = none for the r line only
+#define GT_DIAG 0                    // timing diagnostics only (WRONG gradients): 1 = no reductions for the (r, angle) planes, 2 = no reductions at all
 #endif
 __device__ __forceinline__ void gt_red4(float* addr, float4 v) {
-#if GT_DIAG != 2
+#if GT_DIAG < 2
     atomicAdd(reinterpret_cast<float4*>(addr), v);
 #endif
 }
@@ -151,8 +148,8 @@ struct GtCache {
     }
     __device__ __forceinline__ void flush_line(float* d_tab, int i) {
         if (lo[i][0] != 0xffffffffu) {
-            if (GT_DIAG != 3 && nz(la[i][0])) gt_red4(d_tab + lo[i][0], la[i][0]);
-            if (GT_DIAG != 3 && nz(la[i][1])) gt_red4(d_tab + lo[i][1], la[i][1]);
+            if (nz(la[i][0])) gt_red4(d_tab + lo[i][0], la[i][0]);
+            if (nz(la[i][1])) gt_red4(d_tab + lo[i][1], la[i][1]);
             la[i][0] = la[i][1] = f4zero();
         }
     }
@@ -190,49 +187,13 @@ __device__ __forceinline__ float4 gt_widen(const uint2& q) {
                        __uint_as_float(q.y & 0xffff0000u));
 }
 
-// compact layout of one private copy of the line gradients: hemisphere-major, then factor pair i (line axis egn_vl(i))
-__host__ __device__ __forceinline__ long long gt_line_floats(const int G[3]) { return 2ll * (G[0] + G[1] + G[2]) * EGN_CF; }
-__host__ __device__ __forceinline__ unsigned gt_line_base(const int G[3], int yang, int i) {
-    unsigned t = yang * (unsigned)(G[0] + G[1] + G[2]);
-    for (int j = 0; j < i; ++j) t += (unsigned)G[egn_vl(j)];
-    return t * EGN_CF;
-}
-
-// table[line sections] += sum over the private copies (runs behind the gather backward on the same stream)
-__global__ void __launch_bounds__(256)
-egn_line_fold_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ priv, int copies, float* __restrict__ d_tab) {
-    const long long LF = gt_line_floats(k.lay.G);
-    for (long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e4 < LF / 4; e4 += (long long)gridDim.x * blockDim.x) {
-        float4 s = f4zero();
-        for (int c = 0; c < copies; ++c) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(priv + c * LF) + e4);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        // compact element -> (hemisphere, factor pair, texel, channel) -> table offset
-        long long e = e4 * 4;
-        const long long per_h = LF / 2;
-        const int h = e >= per_h;
-        e -= h * per_h;
-        int i = 0;
-        for (; i < 2; ++i) {
-            const long long n = (long long)k.lay.G[egn_vl(i)] * EGN_CF;
-            if (e < n) break;
-            e -= n;
-        }
-        float4* dst = reinterpret_cast<float4*>(d_tab + k.lay.lf[h][i] + e);
-        float4 o = *dst;
-        o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
-        *dst = o;
-    }
-}
-
 template <bool BF16>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __restrict__ basis0,
                          const float* __restrict__ basis1, const float* __restrict__ rays, long long M,
                          const float* __restrict__ zs, const float* __restrict__ d_fsig, const float* __restrict__ d_feat,
                          const unsigned* __restrict__ gmax_bits, float* __restrict__ d_tab, float* __restrict__ d_basis0,
-                         float* __restrict__ d_basis1, float* __restrict__ d_line_priv, int line_copies) {
+                         float* __restrict__ d_basis1) {
     using L = GtLayout;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp-uniform
@@ -263,7 +224,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         const float* B = (n >> 5) ? basis1 : basis0;
         store_elem_h(bbs, n, kk, o < AD ? B[o * GT_VK + kk] : 0.f, GT_BB_CHUNK);
     }
-    for (int i = tid; i < GT_NBUF * 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 16 * TC_CHUNK / 16; i += GT_THREADS) reinterpret_cast<uint4*>(dfs)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i <= k.knots_last; i += GT_THREADS) s_knots[i] = k.r_knots[i];
     fence_async_smem();
     tc_fence_before();
@@ -273,10 +234,6 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bb_s = smem_u32(bbs), df_s = smem_u32(dfs), v_s = smem_u32(vs);
     const int sub = lane & 15;
-    // Line gradients: the three lines of a hemisphere have 838 texels at 300^3 and every sample of every SM reduces into them.
-    // With d_line_priv (GT_LINE_COPIES > 0; measured, off) the CTA reduces into its own compact copy [2 hemispheres][phi | theta | r lines][64] (copy = CTA mod
-    // line_copies); egn_line_fold_kernel adds the copies to the table afterwards.
-    float* const d_lin = d_line_priv ? d_line_priv + (size_t)(blockIdx.x % line_copies) * gt_line_floats(k.lay.G) : d_tab;
     float inv_scale;
     const float scale = tc_grad_scale(gmax_bits, inv_scale);
 
@@ -305,112 +262,8 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     gt_cp_wait();                                                // each thread's own copies have landed ...
     __syncthreads();                                             // ... and so have everybody else's
 #endif
-#if GT_PIPE
-    static_assert(GT_PREFETCH, "GT_PIPE stages the next tile from the cp.async staging buffers");
-    // Stage A of a tile (runs one tile AHEAD of its scatter phase): coordinates / d(sigma) / hemisphere into the tile's meta
-    // buffer mb, the fp16 dF2 operand into dF2 buffer mb (both from the cp.async staging area), then -- after the CTA barrier
-    // that the caller places -- MMA1 into the dV accumulator mb.
-    auto stage_a = [&](long long t, uint32_t mb) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        const long long gm = t * TC_TM + row;
-        if (gm < M) {
-            const float4 a = nx_df[row * (EGN_FEAT_STRIDE / 4) + 2 * q];
-            v[0] = a.x * scale; v[1] = a.y * scale; v[2] = a.z * scale; v[3] = a.w * scale;
-            if (q < 3) { const float4 b = nx_df[row * (EGN_FEAT_STRIDE / 4) + 2 * q + 1]; v[4] = b.x * scale; v[5] = b.y * scale; v[6] = b.z * scale; v[7] = b.w * scale; }
-        }
-        if (warp < 4) {
-            const int r = 32 * warp + lane;
-            const long long mg = t * TC_TM + r;
-            YYCoord cc;
-            cc.c[0] = cc.c[1] = cc.c[2] = -3.f;
-            cc.yang = 0;
-            float dsg = 0.f;
-            const bool glive = mg < M;
-            if (glive) {
-                if (k.coords != nullptr) {                           // saved by the fused forward (egn_fused.cu, phase 1b)
-                    const float4 sv = nx_co[r];
-                    cc.c[0] = sv.x; cc.c[1] = sv.y; cc.c[2] = sv.z; cc.yang = __float_as_int(sv.w);
-                } else {
-                    const long long ray = egn_ray_of(mg, k.S);
-                    const float z = zs[mg];
-                    const float* ry = rays + ray * 6;
-                    cc = egn_cart_to_yinyang(ry[0] + ry[3] * z, ry[1] + ry[4] * z, ry[2] + ry[5] * z, k, s_knots);
-                }
-                dsg = nx_ds[r];
-            }
-            s_coord[mb * TC_TM + r] = make_float4(cc.c[0], cc.c[1], cc.c[2], __int_as_float(cc.yang | (glive ? 2 : 0)));
-            s_dsg[mb * TC_TM + r] = dsg;
-            s_yang[mb * TC_TM + r] = (unsigned char)cc.yang;
-        }
-        int yang;
-        if (k.coords != nullptr) {                                   // the row's hemisphere straight from the staged record: no barrier
-            yang = (gm < M) ? (__float_as_int(nx_co[row].w) & 1) : 0;
-        } else {
-            __syncthreads();                                         // uniform branch: coordinates were computed by warps 0..3
-            yang = s_yang[mb * TC_TM + row];
-        }
-        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        unsigned char* df = dfs + mb * 16 * TC_CHUNK;
-        store_chunk_h(df, 4 * yang + q, row, v);
-        store_chunk_h(df, 4 * (1 - yang) + q, row, zero);
-    };
-    auto issue_mma1 = [&](uint32_t mb) {                             // thread 0, after the barrier that follows stage_a
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)                              // K = 64 basis outputs (yin | yang)
-            tc_mma(tmem + GT_TM_DV + 160 * mb, desc_k(df_s + mb * 16 * TC_CHUNK + ks * 2 * TC_CHUNK), desc_mn(bb_s + ks * 256, GT_BB_CHUNK),
-                   IDESC_DV, ks > 0);
-        tc_commit(bar);
-    };
-    if ((long long)blockIdx.x < tiles) {
-        stage_a(blockIdx.x, 0);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        prefetch((long long)blockIdx.x + gridDim.x);
-        if (tid == 0) issue_mma1(0);
-    }
-#endif
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const uint32_t par = it & 1;
-#if GT_PIPE
-        const uint32_t mb = par;
-        const float4* cur_coord = s_coord + mb * TC_TM;
-        const float* cur_dsg = s_dsg + mb * TC_TM;
-        const uint32_t df_cur = df_s + mb * 16 * TC_CHUNK;
-        // ---- Ph2. dV rows of this tile (MMA1 was issued one tile ago) -> smem ----
-        ok &= mbar_wait(bar, par);
-        tc_fence_after();
-        {
-            uint32_t r[32], r4[4];
-            tmem_ld32(tmem_lane + GT_TM_DV + 160 * mb + 36 * q, r);
-            tmem_ld4(tmem_lane + GT_TM_DV + 160 * mb + 36 * q + 32, r4);
-            float4* dst = reinterpret_cast<float4*>(dvs + row * GT_DVS + 36 * q);
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-                dst[g] = make_float4(__uint_as_float(r[4 * g]) * inv_scale, __uint_as_float(r[4 * g + 1]) * inv_scale,
-                                     __uint_as_float(r[4 * g + 2]) * inv_scale, __uint_as_float(r[4 * g + 3]) * inv_scale);
-            dst[8] = make_float4(__uint_as_float(r4[0]) * inv_scale, __uint_as_float(r4[1]) * inv_scale, __uint_as_float(r4[2]) * inv_scale,
-                                 __uint_as_float(r4[3]) * inv_scale);
-        }
-        if (it > 0) ok &= mbar_wait(bar + 8, (it - 1) & 1);     // MMA2 of the previous tile has finished with its dF2 buffer and with V
-        gt_cp_wait();                                            // staged inputs of the next tile: own copies landed, the barrier covers the rest
-        tc_fence_before();
-        __syncthreads();
-        // ---- stage A of the NEXT tile, then its MMA1: both run behind this tile's scatter phase ----
-        const bool has_next = tile + gridDim.x < tiles;
-        if (has_next) stage_a(tile + gridDim.x, mb ^ 1);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        prefetch(tile + 2ll * gridDim.x);                       // staging consumed by everybody: refill it behind Ph3
-        if (has_next && tid == 0) issue_mma1(mb ^ 1);
-#else
-        const float4* cur_coord = s_coord;
-        const float* cur_dsg = s_dsg;
-        const uint32_t df_cur = df_s;
         // ---- Ph1a. this thread's 8 values of d_feat ----
         float v[8];
 #pragma unroll
@@ -507,7 +360,6 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         }
         tc_fence_before();
         __syncthreads();
-#endif
         // ---- Ph3. re-gather, local gradients, scatter, V rows ----
         // Ray coherence: the 8 samples of this warp are consecutive along one ray, so the angular plane (theta x phi) and
         // the theta / phi lines are hit at the same texels by (almost) all of them.  Their contributions are summed in
@@ -524,11 +376,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             // samples two apart, so the register cache below flushes less
             const int src = GT_CONSECUTIVE ? 4 * (lane >> 4) + itr : 2 * itr + (lane >> 4);              // sample within the warp's 8
             const int srow = 8 * warp + src;
-            const float4 sc = cur_coord[srow];
+            const float4 sc = s_coord[srow];
             const float c[3] = {sc.x, sc.y, sc.z};
             const int yang = __float_as_int(sc.w) & 1;
             const bool slive = (__float_as_int(sc.w) & 2) != 0;
-            const float dsig = cur_dsg[srow];
+            const float dsig = s_dsg[srow];
             unsigned j0[3], j1[3];
             float wa0[3], wa1[3];
 #pragma unroll
@@ -570,9 +422,6 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                 const unsigned o0 = pbase + (ra + j0[ax]) * EGN_CF, o1 = pbase + (ra + j1[ax]) * EGN_CF;
                 const unsigned o2 = pbase + (rb + j0[ax]) * EGN_CF, o3 = pbase + (rb + j1[ax]) * EGN_CF;
                 const unsigned q0 = lbase + j0[al] * EGN_CF, q1 = lbase + j1[al] * EGN_CF;
-                // where the line gradient goes: the table itself, or the CTA's private compact copy
-                const unsigned lred = d_line_priv ? gt_line_base(k.lay.G, yang, i) + sub * 4 : lbase;
-                const unsigned qr0 = lred + j0[al] * EGN_CF, qr1 = lred + j1[al] * EGN_CF;
                 float4 t0, t1, t2, t3, l0, l1;
                 if constexpr (BF16) {
                     uint2 (&rw)[6] = raw[i % GT_TAP_DEPTH];
@@ -612,7 +461,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
                         }
                         cache.pa[0] = gt_fma4(w0, dP, cache.pa[0]); cache.pa[1] = gt_fma4(w1, dP, cache.pa[1]);
                         cache.pa[2] = gt_fma4(w2, dP, cache.pa[2]); cache.pa[3] = gt_fma4(w3, dP, cache.pa[3]);
-                    } else if (GT_DIAG != 1) {
+                    } else if (GT_DIAG == 0) {
 #if GT_SHIFT
                         // planes (r, theta) / (r, phi): column j0 = taps 0, 2; column j1 = taps 1, 3 (r is the fast axis)
                         float4 c0 = gt_scale(w0, dP), c2 = gt_scale(w2, dP);
@@ -642,9 +491,9 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 #endif
                     }
                     if (i < GT_LINES_CACHED) {                      // phi / theta (/ r) lines: cached
-                        if (cache.lo[i][0] != qr0 || cache.lo[i][1] != qr1) {
-                            cache.flush_line(d_lin, i);
-                            cache.lo[i][0] = qr0; cache.lo[i][1] = qr1;
+                        if (cache.lo[i][0] != q0 || cache.lo[i][1] != q1) {
+                            cache.flush_line(d_tab, i);
+                            cache.lo[i][0] = q0; cache.lo[i][1] = q1;
                         }
                         cache.la[i][0] = gt_fma4(u0, dL, cache.la[i][0]);
                         cache.la[i][1] = gt_fma4(u1, dL, cache.la[i][1]);
@@ -652,15 +501,15 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
 #if GT_SHIFT
                         float4 d0 = gt_scale(u0, dL);
                         const float4 d1 = gt_scale(u1, dL);
-                        const bool shift = cache.ro == qr0, same = cache.ro == qr1;
+                        const bool shift = cache.ro == q0, same = cache.ro == q1;
                         if (shift) { d0.x += cache.ra.x; d0.y += cache.ra.y; d0.z += cache.ra.z; d0.w += cache.ra.w; }
-                        else if (!same) cache.flush_rline(d_lin);
-                        if (GtCache::nz(d0)) gt_red4(d_lin + qr0, d0);
+                        else if (!same) cache.flush_rline(d_tab);
+                        if (GtCache::nz(d0)) gt_red4(d_tab + q0, d0);
                         if (same) { cache.ra.x += d1.x; cache.ra.y += d1.y; cache.ra.z += d1.z; cache.ra.w += d1.w; }
-                        else { cache.ro = qr1; cache.ra = d1; }
+                        else { cache.ro = q1; cache.ra = d1; }
 #else
-                        if (GT_DIAG != 3 && GT_DIAG != 4 && u0 != 0.f) gt_red4(d_lin + qr0, gt_scale(u0, dL));
-                        if (GT_DIAG != 3 && GT_DIAG != 4 && u1 != 0.f) gt_red4(d_lin + qr1, gt_scale(u1, dL));
+                        if (u0 != 0.f) gt_red4(d_tab + q0, gt_scale(u0, dL));
+                        if (u1 != 0.f) gt_red4(d_tab + q1, gt_scale(u1, dL));
 #endif
                     }
                 }
@@ -668,11 +517,11 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
         }
         cache.flush_plane(d_tab);
 #pragma unroll
-        for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_lin, i);
+        for (int i = 0; i < GT_LINES_CACHED; ++i) cache.flush_line(d_tab, i);
 #if GT_SHIFT
         cache.flush_shift(d_tab, 0);
         cache.flush_shift(d_tab, 1);
-        cache.flush_rline(d_lin);
+        cache.flush_rline(d_tab);
 #endif
 #if GT_PREFETCH
         gt_cp_wait();                                            // next tile's inputs: own copies landed; the barrier below covers the rest
@@ -686,7 +535,7 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
             const uint32_t first = it > 0 ? 1u : 0u;
 #pragma unroll
             for (int ks = 0; ks < TC_TM / 16; ++ks)
-                tc_mma(tmem + GT_TM_DB, desc_mn(df_cur + ks * 256), desc_mn(v_s + ks * 256, GT_VCHUNK), IDESC_DB, first | (ks > 0));
+                tc_mma(tmem + GT_TM_DB, desc_mn(df_s + ks * 256), desc_mn(v_s + ks * 256, GT_VCHUNK), IDESC_DB, first | (ks > 0));
             tc_commit(bar + 8);
         }
     }
@@ -712,37 +561,21 @@ egn_gather_bwd_tc_kernel(const __grid_constant__ EgnKernelCfg k, const float* __
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
 }
 
-#ifndef GT_LINE_COPIES
-#define GT_LINE_COPIES 0             // private per-CTA copies of the line gradients + a fold kernel (0 = reduce into the table directly).  Measured
-                                     // 6.876 (0) / 6.890 (8) / 6.907 (32) / 6.939 ms (148 copies) per training step: contention on the 838 line texels is
-                                     // not what makes the reductions expensive; off (profiles/r02_backward.md)
-#endif
-long long egn_gather_bwd_tc_scratch_floats(const int grid[3]) { return (long long)GT_LINE_COPIES * gt_line_floats(grid); }
-
 int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* d_fsig, const float* d_feat, const unsigned* gmax_bits, float* d_tables, const EgnGrads* g,
-                             float* line_scratch, cudaStream_t st) {
+                             cudaStream_t st) {
     const long long M = n * k.S;
     if (M <= 0) return 0;
     const long long tiles = (M + TC_TM - 1) / TC_TM;
     const int blocks = (int)(tiles < 148 ? tiles : 148);
-    const int copies = (line_scratch != nullptr && GT_LINE_COPIES > 0) ? (blocks < GT_LINE_COPIES ? blocks : GT_LINE_COPIES) : 0;
-    float* priv = copies > 0 ? line_scratch : nullptr;
-    if (priv) {
-        cudaError_t e = cudaMemsetAsync(priv, 0, (size_t)copies * gt_line_floats(k.lay.G) * sizeof(float), st);
-        if (e != cudaSuccess) return (int)e;
-    }
     if (k.tables_bf16 != nullptr) {
         cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
         egn_gather_bwd_tc_kernel<true><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
-                                                                                     d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1],
-                                                                                     priv, copies);
+                                                                                     d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1]);
     } else {
         cudaFuncSetAttribute(egn_gather_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtLayout::TOTAL);
         egn_gather_bwd_tc_kernel<false><<<blocks, GT_THREADS, GtLayout::TOTAL, st>>>(k, p->basis[0], p->basis[1], rays, M, z, d_fsig,
-                                                                                      d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1],
-                                                                                      priv, copies);
+                                                                                      d_feat, gmax_bits, d_tables, g->basis[0], g->basis[1]);
     }
-    if (priv) egn_line_fold_kernel<<<148, 256, 0, st>>>(k, priv, copies, d_tables);
     return (int)cudaGetLastError();
 }

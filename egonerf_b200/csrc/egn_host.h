@@ -57,11 +57,9 @@ int egn_launch_mlp_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* r
 int egn_launch_mlp_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                           const float* rgbs, const float* d_rgbs, const unsigned* gmax_bits, float* d_feat, const EgnGrads* g,
                           cudaStream_t st);
-// line_scratch: egn_gather_bwd_tc_scratch_floats(grid) floats for the private copies of the line gradients (nullptr: reduce into the table)
 int egn_launch_gather_bwd_tc(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
                              const float* d_fsig, const float* d_feat, const unsigned* gmax_bits, float* d_tables, const EgnGrads* g,
-                             float* line_scratch, cudaStream_t st);
-long long egn_gather_bwd_tc_scratch_floats(const int grid[3]);
+                             cudaStream_t st);
 int egn_launch_mlp_save(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* feat,
                         float* h1, float* h2, cudaStream_t st);
 int egn_launch_gather_bwd(const EgnKernelCfg& k, const EgnParams* p, const float* rays, long long n, const float* z,
