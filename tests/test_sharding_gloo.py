@@ -88,3 +88,23 @@ def test_peer_exchange_is_not_used_without_a_process_group():
     opt.peer = None
     opt.model = types.SimpleNamespace()
     assert TableAdam.enable_peer_exchange(opt) is False and opt.peer is None
+
+
+def test_gradient_bucket_on_external_storage():
+    """The exchange bucket may live in someone else's buffer (the tail of the peer-memory gradient buffer): the views alias
+    that storage, zero() clears exactly the bucket's part and re-attaches, gather_from_params copies only foreign gradients."""
+    import torch
+    from egonerf_b200.sharding import GradientBucket
+    a, b = torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))
+    store = torch.full((16,), 7.0)
+    bucket = GradientBucket([a, b], storage=store)
+    assert bucket.external and bucket.flat.data_ptr() == store.data_ptr() and bucket.flat.numel() == 11
+    assert float(store[:11].abs().sum()) == 0.0 and float(store[11:].sum()) == 5 * 7.0      # only the bucket's part was cleared
+    a.grad = torch.ones(3, 2)                     # a gradient autograd allocated on its own
+    bucket.gather_from_params()
+    assert a.grad.data_ptr() == bucket.views[0].data_ptr() and b.grad.data_ptr() == bucket.views[1].data_ptr()
+    assert torch.equal(store[:6], torch.ones(6)) and float(store[6:11].abs().sum()) == 0.0
+    b.grad.add_(2.0)                              # in-place accumulation lands in the external storage
+    assert torch.equal(store[6:11], torch.full((5,), 2.0))
+    bucket.zero()
+    assert float(store[:11].abs().sum()) == 0.0 and a.grad.data_ptr() == store.data_ptr()
